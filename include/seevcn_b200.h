@@ -1,0 +1,237 @@
+/*
+ * seevcn_b200 — C-ABI of the B200-native SEE-VCN object-completion + voxelization hot path.
+ *
+ * Every entry point takes plain device pointers, sizes and a CUDA stream (as void*; pass
+ * NULL for the legacy default stream, which is what the reference launches on).  No torch
+ * types cross this boundary.  The caller owns and allocates every input, output and
+ * workspace buffer (reference convention: SURVEY.md §8(b) "Ownership"); nothing in here
+ * allocates on the hot path.  Every function returns 0 on success and a non-zero
+ * SEEVCN_E_* code on failure (the reference's launchers fprintf+exit(-1) instead,
+ * e.g. detector3d/pcdet/ops/pointnet2/pointnet2_batch/src/sampling_gpu.cu:46-50);
+ * seevcn_last_error() gives the message for the calling thread.
+ *
+ * "ref:" comments cite the reference interface each symbol replaces, relative to the
+ * darrenjkt/SEE-VCN checkout.
+ */
+#ifndef SEEVCN_B200_H_
+#define SEEVCN_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SEEVCN_OK            0
+#define SEEVCN_E_INVALID     1   /* bad argument (shape, null pointer, unsupported size)   */
+#define SEEVCN_E_CUDA        2   /* CUDA runtime / launch error                            */
+#define SEEVCN_E_WORKSPACE   3   /* workspace too small                                    */
+#define SEEVCN_E_UNSUPPORTED 4   /* device is not sm_100                                   */
+
+typedef void* seevcn_stream_t;   /* cudaStream_t */
+
+int         seevcn_abi_version(void);
+const char* seevcn_last_error(void);
+/* Returns 0 when device `dev` is an sm_100 part this library was built for. */
+int         seevcn_check_device(int dev);
+
+/* ---------------------------------------------------------------- stage 1: crop ---- */
+
+/* ref: void points_in_boxes_launcher(int batch_size, int boxes_num, int pts_num,
+ *          const float *boxes, const float *pts, int *box_idx_of_points)
+ *      detector3d/pcdet/ops/roiaware_pool3d/src/roiaware_pool3d_kernel.cu:339-359
+ *      (kernel :313-336, predicate :16-36), bound by roiaware_pool3d.cpp:98-118.
+ * boxes (B,T,7) [x,y,z,dx,dy,dz,heading], pts (B,P,3), out (B,P) int32: lowest box index
+ * containing the point, else -1.  Unlike the reference the output does NOT need to be
+ * pre-filled with -1: every element is written. */
+int seevcn_points_in_boxes(int batch_size, int boxes_num, int pts_num,
+                           const float* boxes, const float* pts,
+                           int* box_idx_of_points, seevcn_stream_t stream);
+
+/* ref: int points_in_boxes_cpu(at::Tensor boxes, at::Tensor pts, at::Tensor pts_indices)
+ *      detector3d/pcdet/ops/roiaware_pool3d/src/roiaware_pool3d.cpp:121-168
+ *      (MARGIN = 1e-2, dense (T,P) 0/1 matrix, no first-box-wins).
+ * boxes (T,7), pts (P,3), out (T,P) int32.  Runs on the GPU; "cpu" in the reference name
+ * describes where the reference computes it, not the semantics. */
+int seevcn_points_in_boxes_dense(int boxes_num, int pts_num,
+                                 const float* boxes, const float* pts,
+                                 int* pts_indices, seevcn_stream_t stream);
+/* Same, with box_trig (T,2) = host-computed {cosf(-heading), sinf(-heading)} per box so
+ * the result is bit-identical to the reference's x86 build (glibc cosf/sinf differ from
+ * CUDA's in the last ulp).  box_trig == NULL computes them on the device. */
+int seevcn_points_in_boxes_dense_trig(int boxes_num, int pts_num,
+                                      const float* boxes, const float* box_trig, const float* pts,
+                                      int* pts_indices, seevcn_stream_t stream);
+
+/* Crop with compaction (the list form SEE's per-object crop needs:
+ * see/surface_completion/SEE_VCN.py:61-82 does one crop per box on the host).
+ * In addition to box_idx_of_points (B,P) it emits, per (frame, box), the ascending list of
+ * point indices inside the box:
+ *   box_counts  (B,T)   int32  number of points in each box
+ *   box_offsets (B,T)   int32  exclusive prefix of box_counts within the frame
+ *   box_points  (B,P)   int32  point indices grouped by box (first sum(counts) entries used)
+ * workspace: seevcn_crop_workspace_bytes(B,T,P) bytes. */
+size_t seevcn_crop_workspace_bytes(int batch_size, int boxes_num, int pts_num);
+int seevcn_crop_points_in_boxes(int batch_size, int boxes_num, int pts_num,
+                                const float* boxes, const float* pts,
+                                int* box_idx_of_points, int* box_counts, int* box_offsets,
+                                int* box_points, void* workspace, size_t workspace_bytes,
+                                seevcn_stream_t stream);
+
+/* ref: ResamplePoints.__call__  see/surface_completion/models/vcn/datasets/data_transforms.py:247-262
+ * (tile to >= n_points, take the first n_points of a random permutation).  The permutation
+ * is supplied by the caller as `choice` (num_obj, n_points) int32 indices into the tiled
+ * list, so a seeded host RNG reproduces the reference bit for bit.
+ * For object o: src = box_points[frame_of[o]*P + box_offsets[o] + choice[o,j] % count[o]],
+ * out[o,j,:] = pts[frame_of[o], src, :].
+ * obj_frame/obj_box (num_obj) name the (frame, box) each object came from. */
+int seevcn_resample_gather(int num_obj, int n_points, int boxes_num, int pts_num,
+                           const float* pts, const int* box_counts, const int* box_offsets,
+                           const int* box_points, const int* obj_frame, const int* obj_box,
+                           const int* choice, float* out, seevcn_stream_t stream);
+
+/* ---------------------------------------------------- stage 3: furthest point sampling */
+
+/* ref: void farthest_point_sampling_kernel_launcher(int b, int n, int m,
+ *          const float *dataset, float *temp, int *idxs)
+ *      detector3d/pcdet/ops/pointnet2/pointnet2_batch/src/sampling_gpu.cu:218-260 (kernel :100-216)
+ * dataset (B,N,3) f32, idxs (B,M) int32.  temp (B,N) may be NULL; when given it receives
+ * the final min-distance array exactly as the reference leaves it (it does not need the
+ * 1e10 pre-fill the reference's python wrapper does). */
+int seevcn_furthest_point_sampling(int b, int n, int m, const float* dataset,
+                                   float* temp, int* idxs, seevcn_stream_t stream);
+
+/* ---------------------------------------------------- stage 4: gather / group / kNN -- */
+
+/* ref: gather_points_kernel_launcher_fast  sampling_gpu.cu:33-51.
+ * points (B,C,N), idx (B,M) -> out (B,C,M) */
+int seevcn_gather_points(int b, int c, int n, int npoints, const float* points,
+                         const int* idx, float* out, seevcn_stream_t stream);
+
+/* ref: group_points_kernel_launcher_fast  pointnet2_batch/src/group_points_gpu.cu:75-92.
+ * points (B,C,N), idx (B,P,S) -> out (B,C,P,S) */
+int seevcn_group_points(int b, int c, int n, int npoints, int nsample, const float* points,
+                        const int* idx, float* out, seevcn_stream_t stream);
+
+/* k nearest neighbours, ascending.  Semantics of scipy cKDTree.query(k) / dist.topk(k,
+ * largest=False) as used by see/surface_completion/models/vcn/utils/sampling.py:30-34,59-61.
+ * ref_pts (B,R,3), query (B,Q,3) -> dist (B,Q,k) f32 Euclidean (not squared), idx (B,Q,k) int32.
+ * 1 <= k <= 64, k <= R.  dist may be NULL. */
+int seevcn_knn(int b, int r, int q, int k, const float* ref_pts, const float* query,
+               float* dist, int* idx, seevcn_stream_t stream);
+
+/* ref: partial_with_KDTree / get_partial_mesh_batch  sampling.py:8-41,69-80.
+ * For every object: S = union of the k nearest `complete` points of every `partial`
+ * point; out = complete[sorted(S)] repeated cyclically to surface_pts rows.
+ * partial (B,Np,3), complete (B,R,3) -> out (B,surface_pts,3), sel_count (B) int32 = |S|.
+ * R <= 16384. */
+int seevcn_knn_surface_select(int b, int n_partial, int r, int k, int surface_pts,
+                              const float* partial, const float* complete,
+                              float* out, int* sel_count, seevcn_stream_t stream);
+
+/* ------------------------------------------- stages 2+5: VCN forward (canonicalise+MLP) */
+
+/* Folded fp32 parameters, all DEVICE pointers, row-major (out,in) like torch Linear /
+ * Conv1d(k=1) weights.  BatchNorm (eval) must already be folded into the preceding
+ * conv's weight and bias by the caller (python host does it).  Names follow the
+ * reference state-dict (see/surface_completion/models/vcn/models/VCN_VC.py:116-131):
+ *   pose_encoder.{0,2,4}  3->64->128->1024   (LeakyReLU 0.01 after 0 and 2)   [VC only]
+ *   pose_fc.{0,2}         1024->512->9       (LeakyReLU after 0)             [VC only]
+ *   encoder.mlp_conv1.{0(+bn1),3}  3->128->256
+ *   encoder.mlp_conv2.{0(+bn1),3}  512->512->1024
+ *   shape_fc.{0,2,4}      1024->1024->1024->3*num_coarse
+ * For VCN_CN (VCN_CN.py:111-157) the pose_* pointers are NULL. */
+typedef struct seevcn_vcn_params {
+    const float *pose_enc0_w, *pose_enc0_b;   /* (64,3)      (64)   */
+    const float *pose_enc2_w, *pose_enc2_b;   /* (128,64)    (128)  */
+    const float *pose_enc4_w, *pose_enc4_b;   /* (1024,128)  (1024) */
+    const float *pose_fc0_w,  *pose_fc0_b;    /* (512,1024)  (512)  */
+    const float *pose_fc2_w,  *pose_fc2_b;    /* (9,512)     (9)    */
+    const float *enc1_0_w,    *enc1_0_b;      /* (128,3)     (128)  BN folded */
+    const float *enc1_3_w,    *enc1_3_b;      /* (256,128)   (256)  */
+    const float *enc2_0_w,    *enc2_0_b;      /* (512,512)   (512)  BN folded */
+    const float *enc2_3_w,    *enc2_3_b;      /* (1024,512)  (1024) */
+    const float *fc0_w,       *fc0_b;         /* (1024,1024) (1024) */
+    const float *fc2_w,       *fc2_b;         /* (1024,1024) (1024) */
+    const float *fc4_w,       *fc4_b;         /* (3*num_coarse,1024) (3*num_coarse) */
+    int num_coarse;                           /* 1024 in the shipped models */
+    int viewer_centred;                       /* 1 = VCN_VC, 0 = VCN_CN */
+} seevcn_vcn_params;
+
+typedef struct seevcn_vcn_model seevcn_vcn_model;   /* opaque: packed bf16 weights on device */
+
+/* Packs the parameters into the kernels' bf16 operand layouts (allocates device memory —
+ * model-load time, not the hot path).  precision: 0 = bf16 tensor-core path (tcgen05),
+ * 1 = fp32 SIMT validation path. */
+int  seevcn_vcn_create(const seevcn_vcn_params* params, seevcn_vcn_model** out_model,
+                       seevcn_stream_t stream);
+void seevcn_vcn_destroy(seevcn_vcn_model* model);
+
+size_t seevcn_vcn_workspace_bytes(const seevcn_vcn_model* model, int num_obj, int n_pts);
+
+/* ref: VCN_VC.forward  see/surface_completion/models/vcn/models/VCN_VC.py:178-213
+ *      VCN_CN.forward  see/surface_completion/models/vcn/models/VCN_CN.py:142-157
+ * input (B,N,3) f32; gt_boxes (B,7) f32 (VCN_CN only, else NULL)
+ * -> coarse (B,num_coarse,3) f32, reg_rot (B,3,3) f32, reg_centre (B,3) f32 (VC only; may be NULL).
+ * precision: 0 = bf16 operands / fp32 accumulate on tcgen05, 1 = fp32 SIMT. */
+int seevcn_vcn_forward(const seevcn_vcn_model* model, int num_obj, int n_pts,
+                       const float* input, const float* gt_boxes,
+                       float* coarse, float* reg_rot, float* reg_centre,
+                       void* workspace, size_t workspace_bytes, int precision,
+                       seevcn_stream_t stream);
+
+/* ------------------------------------------------------------ stage 6: voxelization -- */
+
+/* ref: MeanVFE.forward  detector3d/pcdet/models/backbones_3d/vfe/mean_vfe.py:14-31
+ * voxels (M,T,C) f32, voxel_num_points (M) f32 -> voxel_features (M,C) f32
+ * = sum over T / max(num_points, 1). */
+int seevcn_mean_vfe(int num_voxels, int max_points, int num_features, const float* voxels,
+                    const float* voxel_num_points, float* voxel_features,
+                    seevcn_stream_t stream);
+
+/* ref: DynamicMeanVFE.forward  detector3d/pcdet/models/backbones_3d/vfe/dynamic_mean_vfe.py:37-76
+ * points (N,1+C) f32 rows [batch_idx,x,y,z,...]; pc_range[6], voxel_size[3], grid_size[3]
+ * are HOST arrays (grid constants, like the python attributes of the reference module).
+ * Sort-free hashed scatter-mean.  Outputs (capacity max_voxels rows each):
+ *   voxel_coords   (M,4) int32 [b,z,y,x]
+ *   voxel_features (M,C) f32   mean of all in-voxel points
+ *   voxel_counts   (M)   int32
+ *   num_voxels     (1)   int32 (device)  M
+ * Row order is the hash-table order unless sorted != 0, in which case rows are ordered by
+ * the reference's merge key b*XYZ + x*YZ + y*Z + z like torch.unique (64-bit, so batch >= 24
+ * on the Waymo grid does not overflow as the reference's int32 key does).
+ * workspace: seevcn_dynamic_voxelize_workspace_bytes(N, C, max_voxels). */
+size_t seevcn_dynamic_voxelize_workspace_bytes(int num_points, int num_features, int max_voxels);
+int seevcn_dynamic_voxelize(int num_points, int num_features, const float* points,
+                            const float* pc_range, const float* voxel_size, const int* grid_size,
+                            int max_voxels, int sorted,
+                            int* voxel_coords, float* voxel_features, int* voxel_counts,
+                            int* num_voxels, void* workspace, size_t workspace_bytes,
+                            seevcn_stream_t stream);
+
+/* ref: VoxelGeneratorWrapper.generate  detector3d/pcdet/datasets/processor/data_processor.py:44-60
+ * (spconv hard voxelization: first-seen voxel order, first max_points points per voxel in
+ * point order, at most max_voxels voxels).  points (N,C) f32 (xyz first).
+ *   voxels (max_voxels,max_points,C) f32 zero padded, coordinates (max_voxels,3) int32 zyx,
+ *   num_points_per_voxel (max_voxels) int32, num_voxels (1) int32 (device).
+ * PARITY UNPINNED: spconv is not vendored in the reference (docker/Dockerfile:58). */
+size_t seevcn_hard_voxelize_workspace_bytes(int num_points, int max_points, int max_voxels);
+int seevcn_hard_voxelize(int num_points, int num_features, const float* points,
+                         const float* pc_range, const float* voxel_size, const int* grid_size,
+                         int max_points, int max_voxels,
+                         float* voxels, int* coordinates, int* num_points_per_voxel,
+                         int* num_voxels, void* workspace, size_t workspace_bytes,
+                         seevcn_stream_t stream);
+
+/* ------------------------------------------------------------------ parity metric ---- */
+
+/* ref: chamfer_dist_kernel  see/surface_completion/models/vcn/extensions/chamfer_dist/chamfer.cu:15-145
+ * xyz1 (B,N,3), xyz2 (B,M,3) -> dist1 (B,N) squared distance to nearest in xyz2, dist2 (B,M). */
+int seevcn_chamfer(int b, int n, int m, const float* xyz1, const float* xyz2,
+                   float* dist1, float* dist2, seevcn_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SEEVCN_B200_H_ */

@@ -1,0 +1,115 @@
+"""ctypes binding of ``csrc/libseevcn_b200.so`` (C-ABI declared in ``include/seevcn_b200.h``).
+
+Torch is used only for device memory and the current stream: tensors cross the boundary
+as raw ``data_ptr()`` integers.  There is no fallback — a missing library or a non-CUDA
+tensor raises.
+"""
+import ctypes
+import os
+from ctypes import c_int, c_size_t, c_void_p, c_char_p, POINTER
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "csrc", "libseevcn_b200.so")
+
+_lib = None
+
+P = c_void_p
+I = c_int
+
+
+class VcnParams(ctypes.Structure):
+    """struct seevcn_vcn_params (include/seevcn_b200.h)."""
+    _names = ["pose_enc0", "pose_enc2", "pose_enc4", "pose_fc0", "pose_fc2",
+              "enc1_0", "enc1_3", "enc2_0", "enc2_3", "fc0", "fc2", "fc4"]
+    _fields_ = [(f"{n}_{s}", c_void_p) for n in _names for s in ("w", "b")] + [
+        ("num_coarse", c_int), ("viewer_centred", c_int)]
+
+
+# name -> (restype, argtypes); every symbol include/seevcn_b200.h declares
+SIGNATURES = {
+    "seevcn_abi_version": (I, []),
+    "seevcn_last_error": (c_char_p, []),
+    "seevcn_check_device": (I, [I]),
+    "seevcn_points_in_boxes": (I, [I, I, I, P, P, P, P]),
+    "seevcn_points_in_boxes_dense": (I, [I, I, P, P, P, P]),
+    "seevcn_points_in_boxes_dense_trig": (I, [I, I, P, P, P, P, P]),
+    "seevcn_crop_workspace_bytes": (c_size_t, [I, I, I]),
+    "seevcn_crop_points_in_boxes": (I, [I, I, I, P, P, P, P, P, P, P, c_size_t, P]),
+    "seevcn_resample_gather": (I, [I, I, I, I, P, P, P, P, P, P, P, P, P]),
+    "seevcn_furthest_point_sampling": (I, [I, I, I, P, P, P, P]),
+    "seevcn_gather_points": (I, [I, I, I, I, P, P, P, P]),
+    "seevcn_group_points": (I, [I, I, I, I, I, P, P, P, P]),
+    "seevcn_knn": (I, [I, I, I, I, P, P, P, P, P]),
+    "seevcn_knn_surface_select": (I, [I, I, I, I, I, P, P, P, P, P]),
+    "seevcn_vcn_create": (I, [POINTER(VcnParams), POINTER(c_void_p), P]),
+    "seevcn_vcn_destroy": (None, [P]),
+    "seevcn_vcn_workspace_bytes": (c_size_t, [P, I, I]),
+    "seevcn_vcn_forward": (I, [P, I, I, P, P, P, P, P, P, c_size_t, I, P]),
+    "seevcn_mean_vfe": (I, [I, I, I, P, P, P, P]),
+    "seevcn_dynamic_voxelize_workspace_bytes": (c_size_t, [I, I, I]),
+    "seevcn_dynamic_voxelize": (I, [I, I, P, POINTER(ctypes.c_float), POINTER(ctypes.c_float), POINTER(c_int),
+                                    I, I, P, P, P, P, P, c_size_t, P]),
+    "seevcn_hard_voxelize_workspace_bytes": (c_size_t, [I, I, I]),
+    "seevcn_hard_voxelize": (I, [I, I, P, POINTER(ctypes.c_float), POINTER(ctypes.c_float), POINTER(c_int),
+                                 I, I, P, P, P, P, P, c_size_t, P]),
+    "seevcn_chamfer": (I, [I, I, I, P, P, P, P, P]),
+}
+
+
+def lib():
+    """Load the C-ABI library (once).  Raises if it has not been built."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                f"{LIB_PATH} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                "(there is no CPU fallback)")
+        L = ctypes.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(L, name)
+            fn.restype = res
+            fn.argtypes = args
+        _lib = L
+    return _lib
+
+
+def check(rc):
+    if rc != 0:
+        msg = lib().seevcn_last_error()
+        raise RuntimeError(f"seevcn_b200 error {rc}: {msg.decode() if msg else ''}")
+
+
+_checked_devices = set()
+
+
+def require_cuda(*tensors):
+    """All tensors must be contiguous CUDA tensors on the current sm_100 device."""
+    for t in tensors:
+        if t is None:
+            continue
+        if not t.is_cuda:
+            raise RuntimeError("seevcn_b200 ops need CUDA tensors (no CPU fallback)")
+        if not t.is_contiguous():
+            raise RuntimeError("seevcn_b200 ops need contiguous tensors")
+        dev = t.device.index
+        if dev not in _checked_devices:
+            check(lib().seevcn_check_device(dev))
+            _checked_devices.add(dev)
+
+
+def ptr(t):
+    return None if t is None else c_void_p(t.data_ptr())
+
+
+def stream():
+    return c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def farray(vals):
+    return (ctypes.c_float * len(vals))(*[float(v) for v in vals])
+
+
+def iarray(vals):
+    return (ctypes.c_int * len(vals))(*[int(v) for v in vals])

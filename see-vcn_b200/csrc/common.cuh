@@ -1,0 +1,49 @@
+// Shared helpers for the seevcn_b200 kernels (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+#include <stdio.h>
+#include "../../include/seevcn_b200.h"
+
+#define SEEVCN_NUM_SMS 148   // B200: 2 dies x 74 SMs
+
+void seevcn_set_error(const char* fmt, ...);
+
+#define SEEVCN_REQUIRE(cond, ...)                                   \
+    do {                                                            \
+        if (!(cond)) {                                              \
+            seevcn_set_error(__VA_ARGS__);                          \
+            return SEEVCN_E_INVALID;                                \
+        }                                                           \
+    } while (0)
+
+#define SEEVCN_CUDA_CHECK(expr)                                                        \
+    do {                                                                               \
+        cudaError_t _e = (expr);                                                       \
+        if (_e != cudaSuccess) {                                                       \
+            seevcn_set_error("%s:%d: %s -> %s", __FILE__, __LINE__, #expr,             \
+                             cudaGetErrorString(_e));                                  \
+            return SEEVCN_E_CUDA;                                                      \
+        }                                                                              \
+    } while (0)
+
+#define SEEVCN_LAUNCH_CHECK() SEEVCN_CUDA_CHECK(cudaGetLastError())
+
+static inline cudaStream_t as_stream(seevcn_stream_t s) { return reinterpret_cast<cudaStream_t>(s); }
+
+template <typename T>
+static inline T div_up(T a, T b) { return (a + b - 1) / b; }
+
+static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+// Streaming (read-once) 128-bit load that does not allocate in L1.
+__device__ __forceinline__ float4 ld_stream_f4(const float4* p) {
+    float4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+                 : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p));
+    return r;
+}
+
+__device__ __forceinline__ int lane_id() { return threadIdx.x & 31; }
+__device__ __forceinline__ int warp_id() { return threadIdx.x >> 5; }

@@ -1,0 +1,386 @@
+// Stage 1 — points in rotated boxes (crop), with optional per-box compaction.
+//
+// Replaces detector3d/pcdet/ops/roiaware_pool3d/src/roiaware_pool3d_kernel.cu:313-359
+// (points_in_boxes_kernel / launcher) and roiaware_pool3d.cpp:121-168 (points_in_boxes_cpu).
+//
+// Design (B200): HBM-bound, 16 B/point (12 in + 4 out).
+//  * each CTA stages a tile of 1024 points (12 KB) into shared memory with 128-bit
+//    streaming loads (aligned body, scalar head/tail), then reads it back at stride 3
+//    floats (conflict-free: 3 is coprime to 32 banks);
+//  * per-box constants (centre, cos/sin(-heading), half-extent thresholds) are computed
+//    once per CTA into shared memory instead of once per (point, box) pair as in the
+//    reference (roiaware_pool3d_kernel.cu:16-20 recomputes cos/sin per pair);
+//  * each thread tests 4 points per box read (box constants are warp-broadcast LDS.128);
+//  * results are written coalesced.
+//
+// Bit-exactness with the reference kernel as nvcc 12.9 compiles it for sm_100a: the
+// reference expression tree, including the FMA contraction ptxas picks
+// (local_x = fma(sx, cosa, rn(sy * -sina)), local_y = fma(sy, cosa, rn(sx * sina)))
+// and the double-precision comparisons, is reproduced with explicit intrinsics.  The
+// double comparisons `(double)|l| < (double)d/2.0 + (double)MARGIN` are folded exactly
+// into float thresholds: for float f and double h, f < h  <=>  f < round_up_to_float(h),
+// and f > h <=> f > round_down_to_float(h).
+#include "common.cuh"
+
+namespace {
+
+constexpr int kThreads = 256;
+constexpr int kPtsPerThread = 4;
+constexpr int kTilePts = kThreads * kPtsPerThread;   // 1024 points = 12 KB
+constexpr int kBoxChunk = 256;                       // boxes staged per pass
+constexpr int kMaxCropBoxes = 1024;                  // compaction path: per-warp histograms in smem
+
+struct __align__(16) BoxConst {
+    float cx, cy, cz, hz;        // centre, z half extent (rounded down)
+    float cosa, nsina, tx, ty;   // cos(-rz), -sin(-rz), x/y thresholds (rounded up)
+};
+
+// ref: check_pt_in_box3d + lidar_to_local_coords, roiaware_pool3d_kernel.cu:16-36
+// FUSED selects the GPU kernel's contraction; !FUSED the CPU twin's separately rounded
+// products (g++ x86-64 baseline has no FMA), roiaware_pool3d.cpp:121-140.
+template <bool FUSED>
+__device__ __forceinline__ bool pt_in_box(const BoxConst& b, float x, float y, float z) {
+    if (fabsf(__fsub_rn(z, b.cz)) > b.hz) return false;
+    const float sx = __fsub_rn(x, b.cx), sy = __fsub_rn(y, b.cy);
+    float lx, ly;
+    if (FUSED) {
+        lx = __fmaf_rn(sx, b.cosa, __fmul_rn(sy, b.nsina));
+        ly = __fmaf_rn(sy, b.cosa, __fmul_rn(sx, -b.nsina));
+    } else {
+        lx = __fadd_rn(__fmul_rn(sx, b.cosa), __fmul_rn(sy, b.nsina));
+        ly = __fadd_rn(__fmul_rn(sx, -b.nsina), __fmul_rn(sy, b.cosa));
+    }
+    return (fabsf(lx) < b.tx) & (fabsf(ly) < b.ty);
+}
+
+__device__ __forceinline__ void load_box_const(BoxConst& o, const float* __restrict__ box,
+                                               const float* __restrict__ trig, float margin) {
+    const float cx = box[0], cy = box[1], cz = box[2];
+    const float dx = box[3], dy = box[4], dz = box[5], rz = box[6];
+    float cosa, sina;
+    if (trig) { cosa = trig[0]; sina = trig[1]; }          // host libm values (CPU-twin parity)
+    else      { cosa = cosf(-rz); sina = sinf(-rz); }      // same libdevice calls as the reference
+    o.cx = cx; o.cy = cy; o.cz = cz;
+    o.hz = __double2float_rd((double)dz * 0.5);
+    o.cosa = cosa; o.nsina = -sina;
+    o.tx = __double2float_ru((double)dx * 0.5 + (double)margin);
+    o.ty = __double2float_ru((double)dy * 0.5 + (double)margin);
+}
+
+// Stage `nfl` floats starting at src into smem so that s[mis + j] = src[j], using aligned
+// 128-bit loads for the body.  Returns mis (0..3).
+__device__ __forceinline__ int stage_floats(float* s, const float* __restrict__ src, int nfl) {
+    const int mis = (int)((reinterpret_cast<uintptr_t>(src) >> 2) & 3);
+    const float* base = src - mis;                  // 16 B aligned
+    const int total = mis + nfl;
+    const int nvec = (total + 3) >> 2;
+    for (int v = threadIdx.x; v < nvec; v += blockDim.x) {
+        const int j0 = v * 4;
+        if (j0 >= mis && j0 + 4 <= total) {
+            float4 q = ld_stream_f4(reinterpret_cast<const float4*>(base + j0));
+            *reinterpret_cast<float4*>(s + j0) = q;
+        } else {
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const int j = j0 + e;
+                if (j >= mis && j < total) s[j] = base[j];
+            }
+        }
+    }
+    return mis;
+}
+
+// grid (ceil(P / 1024), B).  HIST: also emit per-(tile, box) counts for the compaction pass.
+template <bool HIST>
+__global__ void __launch_bounds__(kThreads)
+points_in_boxes_kernel(int boxes_num, int pts_num, const float* __restrict__ boxes,
+                       const float* __restrict__ pts, int* __restrict__ box_idx_of_points,
+                       int* __restrict__ tile_counts /* (B, ntiles, T) */) {
+    __shared__ __align__(16) float s_pts[kTilePts * 3 + 8];
+    __shared__ BoxConst s_box[kBoxChunk];
+    extern __shared__ int s_hist[];   // HIST: boxes_num ints
+
+    const int b = blockIdx.y;
+    const int tile = blockIdx.x;
+    const int p0 = tile * kTilePts;
+    const int npts = min(kTilePts, pts_num - p0);
+    const float* src = pts + ((size_t)b * pts_num + p0) * 3;
+    const int mis = stage_floats(s_pts, src, npts * 3);
+    if (HIST) for (int k = threadIdx.x; k < boxes_num; k += kThreads) s_hist[k] = 0;
+
+    int res[kPtsPerThread];
+    float px[kPtsPerThread], py[kPtsPerThread], pz[kPtsPerThread];
+#pragma unroll
+    for (int j = 0; j < kPtsPerThread; ++j) res[j] = -1;
+
+    const float* fboxes = boxes + (size_t)b * boxes_num * 7;
+    for (int k0 = 0; k0 < boxes_num; k0 += kBoxChunk) {
+        const int nb = min(kBoxChunk, boxes_num - k0);
+        __syncthreads();   // staging done (first pass) / previous chunk consumed
+        if (threadIdx.x < nb) load_box_const(s_box[threadIdx.x], fboxes + (size_t)(k0 + threadIdx.x) * 7, nullptr, 1e-5f);
+        __syncthreads();
+        if (k0 == 0) {
+#pragma unroll
+            for (int j = 0; j < kPtsPerThread; ++j) {
+                const int i = threadIdx.x + j * kThreads;
+                const bool ok = i < npts;
+                px[j] = ok ? s_pts[mis + 3 * i + 0] : 0.f;
+                py[j] = ok ? s_pts[mis + 3 * i + 1] : 0.f;
+                pz[j] = ok ? s_pts[mis + 3 * i + 2] : 0.f;
+            }
+        }
+        for (int k = 0; k < nb; ++k) {
+            const BoxConst bc = s_box[k];
+#pragma unroll
+            for (int j = 0; j < kPtsPerThread; ++j)
+                if (res[j] < 0 && pt_in_box<true>(bc, px[j], py[j], pz[j])) res[j] = k0 + k;
+        }
+    }
+    int* out = box_idx_of_points + (size_t)b * pts_num + p0;
+#pragma unroll
+    for (int j = 0; j < kPtsPerThread; ++j) {
+        const int i = threadIdx.x + j * kThreads;
+        if (i < npts) {
+            out[i] = res[j];
+            if (HIST && res[j] >= 0) atomicAdd(&s_hist[res[j]], 1);
+        }
+    }
+    if (HIST) {
+        __syncthreads();
+        int* tc = tile_counts + ((size_t)b * gridDim.x + tile) * boxes_num;
+        for (int k = threadIdx.x; k < boxes_num; k += kThreads) tc[k] = s_hist[k];
+    }
+}
+
+// Dense (T,P) 0/1 matrix with the CPU twin's MARGIN = 1e-2 (roiaware_pool3d.cpp:133).
+// grid (ceil(P/1024)).  Write-bound: 4*T bytes out per point.
+__global__ void __launch_bounds__(kThreads)
+points_in_boxes_dense_kernel(int boxes_num, int pts_num, const float* __restrict__ boxes,
+                             const float* __restrict__ trig, const float* __restrict__ pts,
+                             int* __restrict__ pts_indices) {
+    __shared__ __align__(16) float s_pts[kTilePts * 3 + 8];
+    __shared__ BoxConst s_box[kBoxChunk];
+    const int p0 = blockIdx.x * kTilePts;
+    const int npts = min(kTilePts, pts_num - p0);
+    const int mis = stage_floats(s_pts, pts + (size_t)p0 * 3, npts * 3);
+    float px[kPtsPerThread], py[kPtsPerThread], pz[kPtsPerThread];
+    for (int k0 = 0; k0 < boxes_num; k0 += kBoxChunk) {
+        const int nb = min(kBoxChunk, boxes_num - k0);
+        __syncthreads();
+        if (threadIdx.x < nb)
+            load_box_const(s_box[threadIdx.x], boxes + (size_t)(k0 + threadIdx.x) * 7,
+                           trig ? trig + (size_t)(k0 + threadIdx.x) * 2 : nullptr, 1e-2f);
+        __syncthreads();
+        if (k0 == 0) {
+#pragma unroll
+            for (int j = 0; j < kPtsPerThread; ++j) {
+                const int i = threadIdx.x + j * kThreads;
+                const bool ok = i < npts;
+                px[j] = ok ? s_pts[mis + 3 * i + 0] : 0.f;
+                py[j] = ok ? s_pts[mis + 3 * i + 1] : 0.f;
+                pz[j] = ok ? s_pts[mis + 3 * i + 2] : 0.f;
+            }
+        }
+        for (int k = 0; k < nb; ++k) {
+            const BoxConst bc = s_box[k];
+            int* out = pts_indices + (size_t)(k0 + k) * pts_num + p0;
+#pragma unroll
+            for (int j = 0; j < kPtsPerThread; ++j) {
+                const int i = threadIdx.x + j * kThreads;
+                if (i < npts) out[i] = pt_in_box<false>(bc, px[j], py[j], pz[j]) ? 1 : 0;
+            }
+        }
+    }
+}
+
+// Compaction pass B: per frame, exclusive scan of tile_counts over tiles (in place) and of
+// the per-box totals over boxes.  grid B, block 256.
+__global__ void crop_scan_kernel(int boxes_num, int ntiles, int* __restrict__ tile_counts,
+                                 int* __restrict__ box_counts, int* __restrict__ box_offsets) {
+    extern __shared__ int s_tot[];   // boxes_num
+    const int b = blockIdx.x;
+    int* tc = tile_counts + (size_t)b * ntiles * boxes_num;
+    for (int k = threadIdx.x; k < boxes_num; k += blockDim.x) {
+        int run = 0;
+        for (int t = 0; t < ntiles; ++t) {
+            const int c = tc[(size_t)t * boxes_num + k];
+            tc[(size_t)t * boxes_num + k] = run;
+            run += c;
+        }
+        s_tot[k] = run;
+        box_counts[(size_t)b * boxes_num + k] = run;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {   // boxes_num <= 1024: a serial scan is a few hundred ns
+        int run = 0;
+        for (int k = 0; k < boxes_num; ++k) { box_offsets[(size_t)b * boxes_num + k] = run; run += s_tot[k]; }
+    }
+}
+
+// Compaction pass C: stable scatter of point indices into per-box lists.  Each warp owns a
+// contiguous 128-point slice of the tile; ranks inside a 32-point row come from
+// __match_any_sync (the multi-key form of ballot compaction).
+__global__ void __launch_bounds__(kThreads)
+crop_scatter_kernel(int boxes_num, int pts_num, const int* __restrict__ box_idx_of_points,
+                    const int* __restrict__ tile_offsets, const int* __restrict__ box_offsets,
+                    int* __restrict__ box_points) {
+    extern __shared__ int s_w[];   // (8 warps, boxes_num) running write positions
+    constexpr int kWarps = kThreads / 32;
+    constexpr int kRows = kTilePts / kWarps / 32;   // 4 rows of 32 points per warp
+    const int b = blockIdx.y, tile = blockIdx.x;
+    const int p0 = tile * kTilePts;
+    const int w = warp_id(), l = lane_id();
+    for (int i = threadIdx.x; i < kWarps * boxes_num; i += kThreads) s_w[i] = 0;
+    __syncthreads();
+    int key[kRows];
+    const int* in = box_idx_of_points + (size_t)b * pts_num;
+#pragma unroll
+    for (int r = 0; r < kRows; ++r) {
+        const int p = p0 + (w * kRows + r) * 32 + l;
+        key[r] = p < pts_num ? in[p] : -1;
+        const unsigned m = __match_any_sync(0xffffffffu, key[r]);
+        if (key[r] >= 0 && l == __ffs(m) - 1) s_w[w * boxes_num + key[r]] += __popc(m);
+        __syncwarp();
+    }
+    __syncthreads();
+    // exclusive prefix over warps + tile offset + box offset
+    const int* toff = tile_offsets + ((size_t)b * gridDim.x + tile) * boxes_num;
+    for (int k = threadIdx.x; k < boxes_num; k += kThreads) {
+        int run = toff[k] + box_offsets[(size_t)b * boxes_num + k];
+        for (int ww = 0; ww < kWarps; ++ww) {
+            const int c = s_w[ww * boxes_num + k];
+            s_w[ww * boxes_num + k] = run;
+            run += c;
+        }
+    }
+    __syncthreads();
+    int* out = box_points + (size_t)b * pts_num;
+#pragma unroll
+    for (int r = 0; r < kRows; ++r) {
+        const int p = p0 + (w * kRows + r) * 32 + l;
+        const unsigned m = __match_any_sync(0xffffffffu, key[r]);
+        int base = 0;
+        if (key[r] >= 0) base = s_w[w * boxes_num + key[r]];
+        __syncwarp();
+        if (key[r] >= 0) {
+            out[base + __popc(m & ((1u << l) - 1))] = p;
+            if (l == __ffs(m) - 1) s_w[w * boxes_num + key[r]] = base + __popc(m);
+        }
+        __syncwarp();
+    }
+}
+
+// ref: ResamplePoints, data_transforms.py:247-262 (tile then permute-truncate; the tiled
+// element j is original point j % count).  One warp per 32 output points.
+__global__ void resample_gather_kernel(int num_obj, int n_points, int boxes_num, int pts_num,
+                                       const float* __restrict__ pts, const int* __restrict__ box_counts,
+                                       const int* __restrict__ box_offsets, const int* __restrict__ box_points,
+                                       const int* __restrict__ obj_frame, const int* __restrict__ obj_box,
+                                       const int* __restrict__ choice, float* __restrict__ out) {
+    const int o = blockIdx.y;
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n_points) return;
+    const int f = obj_frame[o], k = obj_box[o];
+    const int cnt = box_counts[(size_t)f * boxes_num + k];
+    float x = 0.f, y = 0.f, z = 0.f;
+    if (cnt > 0) {
+        const int off = box_offsets[(size_t)f * boxes_num + k];
+        const int c = choice[(size_t)o * n_points + j] % cnt;
+        const int p = box_points[(size_t)f * pts_num + off + c];
+        const float* s = pts + ((size_t)f * pts_num + p) * 3;
+        x = s[0]; y = s[1]; z = s[2];
+    }
+    float* d = out + ((size_t)o * n_points + j) * 3;
+    d[0] = x; d[1] = y; d[2] = z;
+}
+
+}  // namespace
+
+extern "C" int seevcn_points_in_boxes(int batch_size, int boxes_num, int pts_num, const float* boxes,
+                                      const float* pts, int* box_idx_of_points, seevcn_stream_t stream) {
+    SEEVCN_REQUIRE(batch_size >= 0 && boxes_num >= 0 && pts_num >= 0, "points_in_boxes: negative size");
+    if (batch_size == 0 || pts_num == 0) return SEEVCN_OK;
+    SEEVCN_REQUIRE(pts && box_idx_of_points && (boxes || boxes_num == 0), "points_in_boxes: null pointer");
+    SEEVCN_REQUIRE(batch_size <= 65535, "points_in_boxes: batch_size > 65535");
+    dim3 grid(div_up(pts_num, kTilePts), batch_size);
+    points_in_boxes_kernel<false><<<grid, kThreads, 0, as_stream(stream)>>>(boxes_num, pts_num, boxes, pts,
+                                                                            box_idx_of_points, nullptr);
+    SEEVCN_LAUNCH_CHECK();
+    return SEEVCN_OK;
+}
+
+// trig: optional (T,2) device array of host-computed {cosf(-rz), sinf(-rz)} so the result
+// is bit-identical to the reference's CPU build (glibc cosf/sinf); exported separately.
+extern "C" int seevcn_points_in_boxes_dense_trig(int boxes_num, int pts_num, const float* boxes,
+                                                 const float* trig, const float* pts, int* pts_indices,
+                                                 seevcn_stream_t stream) {
+    SEEVCN_REQUIRE(boxes_num >= 0 && pts_num >= 0, "points_in_boxes_dense: negative size");
+    if (boxes_num == 0 || pts_num == 0) return SEEVCN_OK;
+    SEEVCN_REQUIRE(boxes && pts && pts_indices, "points_in_boxes_dense: null pointer");
+    points_in_boxes_dense_kernel<<<div_up(pts_num, kTilePts), kThreads, 0, as_stream(stream)>>>(
+        boxes_num, pts_num, boxes, trig, pts, pts_indices);
+    SEEVCN_LAUNCH_CHECK();
+    return SEEVCN_OK;
+}
+
+extern "C" int seevcn_points_in_boxes_dense(int boxes_num, int pts_num, const float* boxes, const float* pts,
+                                            int* pts_indices, seevcn_stream_t stream) {
+    return seevcn_points_in_boxes_dense_trig(boxes_num, pts_num, boxes, nullptr, pts, pts_indices, stream);
+}
+
+extern "C" size_t seevcn_crop_workspace_bytes(int batch_size, int boxes_num, int pts_num) {
+    if (batch_size <= 0 || boxes_num <= 0 || pts_num <= 0) return 16;
+    return align_up((size_t)batch_size * div_up(pts_num, kTilePts) * boxes_num * sizeof(int), 256);
+}
+
+extern "C" int seevcn_crop_points_in_boxes(int batch_size, int boxes_num, int pts_num, const float* boxes,
+                                           const float* pts, int* box_idx_of_points, int* box_counts,
+                                           int* box_offsets, int* box_points, void* workspace,
+                                           size_t workspace_bytes, seevcn_stream_t stream) {
+    SEEVCN_REQUIRE(batch_size >= 0 && boxes_num >= 0 && pts_num >= 0, "crop: negative size");
+    if (batch_size == 0 || boxes_num == 0) return SEEVCN_OK;
+    SEEVCN_REQUIRE(boxes_num <= kMaxCropBoxes, "crop: boxes_num %d > %d", boxes_num, kMaxCropBoxes);
+    SEEVCN_REQUIRE(batch_size <= 65535, "crop: batch_size > 65535");
+    SEEVCN_REQUIRE(box_counts && box_offsets, "crop: null pointer");
+    cudaStream_t st = as_stream(stream);
+    if (pts_num == 0) {
+        SEEVCN_CUDA_CHECK(cudaMemsetAsync(box_counts, 0, (size_t)batch_size * boxes_num * sizeof(int), st));
+        SEEVCN_CUDA_CHECK(cudaMemsetAsync(box_offsets, 0, (size_t)batch_size * boxes_num * sizeof(int), st));
+        return SEEVCN_OK;
+    }
+    SEEVCN_REQUIRE(boxes && pts && box_idx_of_points && box_points && workspace, "crop: null pointer");
+    if (workspace_bytes < seevcn_crop_workspace_bytes(batch_size, boxes_num, pts_num)) {
+        seevcn_set_error("crop: workspace too small");
+        return SEEVCN_E_WORKSPACE;
+    }
+    int* tile_counts = static_cast<int*>(workspace);
+    const int ntiles = div_up(pts_num, kTilePts);
+    dim3 grid(ntiles, batch_size);
+    points_in_boxes_kernel<true><<<grid, kThreads, boxes_num * sizeof(int), st>>>(
+        boxes_num, pts_num, boxes, pts, box_idx_of_points, tile_counts);
+    SEEVCN_LAUNCH_CHECK();
+    crop_scan_kernel<<<batch_size, 256, boxes_num * sizeof(int), st>>>(boxes_num, ntiles, tile_counts,
+                                                                       box_counts, box_offsets);
+    SEEVCN_LAUNCH_CHECK();
+    crop_scatter_kernel<<<grid, kThreads, (kThreads / 32) * boxes_num * sizeof(int), st>>>(
+        boxes_num, pts_num, box_idx_of_points, tile_counts, box_offsets, box_points);
+    SEEVCN_LAUNCH_CHECK();
+    return SEEVCN_OK;
+}
+
+extern "C" int seevcn_resample_gather(int num_obj, int n_points, int boxes_num, int pts_num, const float* pts,
+                                      const int* box_counts, const int* box_offsets, const int* box_points,
+                                      const int* obj_frame, const int* obj_box, const int* choice, float* out,
+                                      seevcn_stream_t stream) {
+    SEEVCN_REQUIRE(num_obj >= 0 && n_points >= 0, "resample_gather: negative size");
+    if (num_obj == 0 || n_points == 0) return SEEVCN_OK;
+    SEEVCN_REQUIRE(num_obj <= 65535, "resample_gather: num_obj > 65535 per call");
+    SEEVCN_REQUIRE(pts && box_counts && box_offsets && box_points && obj_frame && obj_box && choice && out,
+                   "resample_gather: null pointer");
+    dim3 grid(div_up(n_points, 256), num_obj);
+    resample_gather_kernel<<<grid, 256, 0, as_stream(stream)>>>(num_obj, n_points, boxes_num, pts_num, pts,
+                                                                box_counts, box_offsets, box_points, obj_frame,
+                                                                obj_box, choice, out);
+    SEEVCN_LAUNCH_CHECK();
+    return SEEVCN_OK;
+}

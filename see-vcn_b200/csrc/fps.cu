@@ -1,0 +1,199 @@
+// Stage 3 — furthest point sampling.
+//
+// Replaces detector3d/pcdet/ops/pointnet2/pointnet2_batch/src/sampling_gpu.cu:100-260.
+//
+// The reference re-reads xyz (12 B) and temp (4+4 B) for every point from global memory on
+// each of the M-1 rounds and reduces with a 10-barrier shared-memory tree.  Here, per object
+// (one CTA):
+//  * xyz is staged ONCE into shared memory as SoA (3*N floats, N <= 18,900 fits 227 KB);
+//  * the running min-distance array lives in registers (<= 16 points per thread);
+//  * the block argmax is a warp-shuffle reduction + one barrier per round (per-warp
+//    partials are double-buffered in smem and every warp redundantly reduces them).
+// HBM traffic drops from M*N*16 B to the compulsory 12*N + 4*M B per object; what is left
+// is the serial chain of M-1 rounds (on-chip latency bound).
+//
+// Bit-exactness: same block size rule (cuda_utils.h:10-14), same strided point->thread
+// map, the distance expression with the contraction nvcc 12.9 emits for the reference
+// (fma(dz,dz, fma(dy,dy, dx*dx))), fminf, strict '>' inside a thread and lower-thread-wins
+// across threads — i.e. the reference's tie rule, so indices match even on clouds with
+// duplicate points.
+#include <cmath>
+#include "common.cuh"
+
+namespace {
+
+// ref: opt_n_threads, pointnet2_batch/src/cuda_utils.h:10-14
+int ref_block_size(int n) {
+    const int pow_2 = (int)(std::log(static_cast<double>(n)) / std::log(2.0));
+    int bs = 1 << pow_2;
+    if (bs > 1024) bs = 1024;
+    if (bs < 1) bs = 1;
+    return bs;
+}
+
+struct Cand { float v; int i; };
+
+// partner is the HIGHER thread: it wins only with a strictly larger value (ref __update :93-98)
+__device__ __forceinline__ Cand take_hi(Cand lo, Cand hi) { return hi.v > lo.v ? hi : lo; }
+
+__device__ __forceinline__ Cand warp_argmax(Cand c) {
+#pragma unroll
+    for (int off = 16; off >= 1; off >>= 1) {
+        Cand o;
+        o.v = __shfl_down_sync(0xffffffffu, c.v, off);
+        o.i = __shfl_down_sync(0xffffffffu, c.i, off);
+        c = take_hi(c, o);   // out-of-range partner returns own value
+    }
+    return c;   // valid in lane 0
+}
+
+// PPT: points per thread held in registers.  SMEM_XYZ: xyz staged in shared memory.
+template <int PPT, bool SMEM_XYZ>
+__global__ void __launch_bounds__(1024)
+fps_kernel(int n, int m, int bs, const float* __restrict__ dataset, float* __restrict__ temp, int* __restrict__ idxs) {
+    extern __shared__ float s_dyn[];
+    __shared__ float s_v[2][32];
+    __shared__ int s_i[2][32];
+    if (m <= 0) return;
+    // bs = the reference's logical block size (point->thread map, tie rule); blockDim >= 32
+    const int tid = threadIdx.x;
+    const int nwarps = (bs + 31) >> 5;
+    dataset += (size_t)blockIdx.x * n * 3;
+    idxs += (size_t)blockIdx.x * m;
+    if (temp) temp += (size_t)blockIdx.x * n;
+
+    float* sx = s_dyn; float* sy = s_dyn + n; float* sz = s_dyn + 2 * n;
+    if (SMEM_XYZ) {
+        for (int f = tid; f < 3 * n; f += blockDim.x) {
+            const float v = dataset[f];
+            const int k = f / 3, c = f - 3 * k;
+            s_dyn[c * n + k] = v;
+        }
+        __syncthreads();
+    }
+    float dist[PPT];
+    float px[PPT], py[PPT], pz[PPT];
+#pragma unroll
+    for (int j = 0; j < PPT; ++j) {
+        dist[j] = 1e10f;   // pointnet2_utils.py:26
+        const int k = tid + j * bs;
+        if (!SMEM_XYZ || PPT <= 4) {   // few points per thread: keep coordinates in registers too
+            const bool ok = k < n;
+            px[j] = ok ? (SMEM_XYZ ? sx[k] : dataset[k * 3 + 0]) : 0.f;
+            py[j] = ok ? (SMEM_XYZ ? sy[k] : dataset[k * 3 + 1]) : 0.f;
+            pz[j] = ok ? (SMEM_XYZ ? sz[k] : dataset[k * 3 + 2]) : 0.f;
+        }
+    }
+    int old = 0;
+    if (tid == 0) idxs[0] = 0;
+    for (int r = 1; r < m; ++r) {
+        float x1, y1, z1;
+        if (SMEM_XYZ) { x1 = sx[old]; y1 = sy[old]; z1 = sz[old]; }
+        else { x1 = dataset[old * 3 + 0]; y1 = dataset[old * 3 + 1]; z1 = dataset[old * 3 + 2]; }
+        Cand c; c.v = tid < bs ? -1.f : -2.f; c.i = 0;
+#pragma unroll
+        for (int j = 0; j < PPT; ++j) {
+            const int k = tid + j * bs;
+            if (k < n && tid < bs) {
+                float x2, y2, z2;
+                if (!SMEM_XYZ || PPT <= 4) { x2 = px[j]; y2 = py[j]; z2 = pz[j]; }
+                else { x2 = sx[k]; y2 = sy[k]; z2 = sz[k]; }
+                const float dx = __fsub_rn(x2, x1), dy = __fsub_rn(y2, y1), dz = __fsub_rn(z2, z1);
+                const float d = __fmaf_rn(dz, dz, __fmaf_rn(dy, dy, __fmul_rn(dx, dx)));
+                const float d2 = fminf(d, dist[j]);
+                dist[j] = d2;
+                if (d2 > c.v) { c.v = d2; c.i = k; }
+            }
+        }
+        c = warp_argmax(c);
+        const int buf = r & 1;
+        if (lane_id() == 0) { s_v[buf][warp_id()] = c.v; s_i[buf][warp_id()] = c.i; }
+        __syncthreads();
+        Cand w; w.v = -2.f; w.i = 0;
+        if (lane_id() < nwarps) { w.v = s_v[buf][lane_id()]; w.i = s_i[buf][lane_id()]; }
+        w = warp_argmax(w);
+        old = __shfl_sync(0xffffffffu, w.i, 0);
+        if (tid == 0) idxs[r] = old;
+    }
+    if (temp) {
+#pragma unroll
+        for (int j = 0; j < PPT; ++j) {
+            const int k = tid + j * bs;
+            if (k < n && tid < bs) temp[k] = dist[j];
+        }
+    }
+}
+
+// Any N: min-distance array in global `temp` (L2 resident), xyz from global.
+__global__ void __launch_bounds__(1024)
+fps_kernel_global(int n, int m, int bs, const float* __restrict__ dataset, float* __restrict__ temp, int* __restrict__ idxs) {
+    __shared__ float s_v[2][32];
+    __shared__ int s_i[2][32];
+    if (m <= 0) return;
+    const int tid = threadIdx.x;
+    const int nwarps = (bs + 31) >> 5;
+    dataset += (size_t)blockIdx.x * n * 3;
+    idxs += (size_t)blockIdx.x * m;
+    temp += (size_t)blockIdx.x * n;
+    for (int k = tid; k < n; k += blockDim.x) temp[k] = 1e10f;
+    __syncthreads();
+    int old = 0;
+    if (tid == 0) idxs[0] = 0;
+    for (int r = 1; r < m; ++r) {
+        const float x1 = dataset[old * 3 + 0], y1 = dataset[old * 3 + 1], z1 = dataset[old * 3 + 2];
+        Cand c; c.v = tid < bs ? -1.f : -2.f; c.i = 0;
+        for (int k = tid; k < n && tid < bs; k += bs) {
+            const float dx = __fsub_rn(dataset[k * 3 + 0], x1), dy = __fsub_rn(dataset[k * 3 + 1], y1),
+                        dz = __fsub_rn(dataset[k * 3 + 2], z1);
+            const float d = __fmaf_rn(dz, dz, __fmaf_rn(dy, dy, __fmul_rn(dx, dx)));
+            const float d2 = fminf(d, temp[k]);
+            temp[k] = d2;
+            if (d2 > c.v) { c.v = d2; c.i = k; }
+        }
+        c = warp_argmax(c);
+        const int buf = r & 1;
+        if (lane_id() == 0) { s_v[buf][warp_id()] = c.v; s_i[buf][warp_id()] = c.i; }
+        __syncthreads();
+        Cand w; w.v = -2.f; w.i = 0;
+        if (lane_id() < nwarps) { w.v = s_v[buf][lane_id()]; w.i = s_i[buf][lane_id()]; }
+        w = warp_argmax(w);
+        old = __shfl_sync(0xffffffffu, w.i, 0);
+        if (tid == 0) idxs[r] = old;
+    }
+}
+
+template <int PPT>
+int launch_fps(int b, int n, int m, int bs, const float* dataset, float* temp, int* idxs, cudaStream_t st) {
+    const size_t smem = (size_t)3 * n * sizeof(float);
+    auto kern = fps_kernel<PPT, true>;
+    if (smem > 48 * 1024)
+        SEEVCN_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<b, bs < 32 ? 32 : bs, smem, st>>>(n, m, bs, dataset, temp, idxs);
+    SEEVCN_LAUNCH_CHECK();
+    return SEEVCN_OK;
+}
+
+}  // namespace
+
+extern "C" int seevcn_furthest_point_sampling(int b, int n, int m, const float* dataset, float* temp, int* idxs,
+                                              seevcn_stream_t stream) {
+    SEEVCN_REQUIRE(b >= 0 && n >= 0 && m >= 0, "fps: negative size");
+    if (b == 0 || m == 0) return SEEVCN_OK;
+    SEEVCN_REQUIRE(n >= 1, "fps: n must be >= 1 when m > 0");
+    SEEVCN_REQUIRE(dataset && idxs, "fps: null pointer");
+    const int bs = ref_block_size(n);
+    const int ppt = div_up(n, bs);
+    cudaStream_t st = as_stream(stream);
+    const size_t smem = (size_t)3 * n * sizeof(float);
+    if (ppt <= 16 && smem <= 226 * 1024) {
+        if (ppt <= 1) return launch_fps<1>(b, n, m, bs, dataset, temp, idxs, st);
+        if (ppt <= 2) return launch_fps<2>(b, n, m, bs, dataset, temp, idxs, st);
+        if (ppt <= 4) return launch_fps<4>(b, n, m, bs, dataset, temp, idxs, st);
+        if (ppt <= 8) return launch_fps<8>(b, n, m, bs, dataset, temp, idxs, st);
+        return launch_fps<16>(b, n, m, bs, dataset, temp, idxs, st);
+    }
+    SEEVCN_REQUIRE(temp != nullptr, "fps: n=%d needs the temp (B,N) scratch buffer", n);
+    fps_kernel_global<<<b, bs < 32 ? 32 : bs, 0, st>>>(n, m, bs, dataset, temp, idxs);
+    SEEVCN_LAUNCH_CHECK();
+    return SEEVCN_OK;
+}

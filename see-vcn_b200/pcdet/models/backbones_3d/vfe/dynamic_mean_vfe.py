@@ -1,0 +1,62 @@
+"""DynamicMeanVFE on the B200 path: sort-free hashed scatter-mean.
+
+ref: detector3d/pcdet/models/backbones_3d/vfe/dynamic_mean_vfe.py:14-76
+"""
+import torch
+
+from ..... import _abi
+from .vfe_template import VFETemplate
+
+
+def dynamic_voxelize(points, point_cloud_range, voxel_size, grid_size, max_voxels=None, sort=True, workspace=None):
+    """points (N, 1+C) float32 CUDA rows [batch_idx, x, y, z, ...] ->
+    voxel_coords (M, 4) int32 [b, z, y, x], voxel_features (M, C) float32, voxel_counts (M,) int32.
+    ``sort=True`` orders rows by the reference's merge key (torch.unique order)."""
+    points = points.contiguous()
+    _abi.require_cuda(points)
+    assert points.dtype == torch.float32 and points.dim() == 2
+    N, C1 = points.shape
+    C = C1 - 1
+    dev = points.device
+    if max_voxels is None:
+        max_voxels = max(N, 1)
+    L = _abi.lib()
+    ws_bytes = L.seevcn_dynamic_voxelize_workspace_bytes(N, C, max_voxels)
+    if workspace is None or workspace.numel() < ws_bytes:
+        workspace = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+    coords = torch.empty((max_voxels, 4), dtype=torch.int32, device=dev)
+    feats = torch.empty((max_voxels, C), dtype=torch.float32, device=dev)
+    counts = torch.empty((max_voxels,), dtype=torch.int32, device=dev)
+    num = torch.zeros((1,), dtype=torch.int32, device=dev)
+    with torch.cuda.device(dev):
+        _abi.check(L.seevcn_dynamic_voxelize(N, C, _abi.ptr(points), _abi.farray(point_cloud_range),
+                                             _abi.farray(voxel_size), _abi.iarray(grid_size), max_voxels,
+                                             1 if sort else 0, _abi.ptr(coords), _abi.ptr(feats), _abi.ptr(counts),
+                                             _abi.ptr(num), _abi.ptr(workspace), workspace.numel(), _abi.stream()))
+    m = min(int(num.item()), max_voxels)   # the one host sync: M is data dependent, as in the reference
+    return coords[:m], feats[:m], counts[:m]
+
+
+class DynamicMeanVFE(VFETemplate):
+    def __init__(self, model_cfg, num_point_features, voxel_size, grid_size, point_cloud_range, **kwargs):
+        super().__init__(model_cfg=model_cfg)
+        self.num_point_features = num_point_features
+        self.grid_size = [int(g) for g in grid_size]
+        self.voxel_size = [float(v) for v in voxel_size]
+        self.point_cloud_range = [float(v) for v in point_cloud_range]
+        self.sort = kwargs.get('sort', True)
+
+    def get_output_feature_dim(self):
+        return self.num_point_features
+
+    @torch.no_grad()
+    def forward(self, batch_dict, **kwargs):
+        """batch_dict['points'] (sum N, 1+C) [batch_idx, x, y, z, ...] ->
+        ['voxel_features'] (M, C) mean of all in-voxel points, ['voxel_coords'] (M, 4) int32 [b,z,y,x],
+        plus ['voxel_num_points'] (M,) int32 (the reference computes and drops unq_cnt, :63)."""
+        coords, feats, counts = dynamic_voxelize(batch_dict['points'], self.point_cloud_range, self.voxel_size,
+                                                 self.grid_size, sort=self.sort)
+        batch_dict['voxel_features'] = feats.contiguous()
+        batch_dict['voxel_coords'] = coords.contiguous()
+        batch_dict['voxel_num_points'] = counts.contiguous()
+        return batch_dict

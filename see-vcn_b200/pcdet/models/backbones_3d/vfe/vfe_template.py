@@ -1,0 +1,14 @@
+"""ref: detector3d/pcdet/models/backbones_3d/vfe/vfe_template.py:4-22"""
+import torch.nn as nn
+
+
+class VFETemplate(nn.Module):
+    def __init__(self, model_cfg, **kwargs):
+        super().__init__()
+        self.model_cfg = model_cfg
+
+    def get_output_feature_dim(self):
+        raise NotImplementedError
+
+    def forward(self, **kwargs):
+        raise NotImplementedError

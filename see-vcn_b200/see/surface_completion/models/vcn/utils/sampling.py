@@ -1,0 +1,27 @@
+"""kNN surface selection on the device.
+
+ref: see/surface_completion/models/vcn/utils/sampling.py:8-41 (partial_with_KDTree), :69-80 (batch)
+"""
+import torch
+
+from ...... import _abi
+
+
+def get_partial_mesh_batch(batch_partial, batch_complete, k=20, surface_pts=1024, return_count=False):
+    """batch_partial (B, Np, 3), batch_complete (B, R, 3) CUDA float32 -> (B, surface_pts, 3) CUDA.
+
+    For every object: the union of the k nearest completed points of every partial point,
+    in ascending index order, tiled cyclically to ``surface_pts`` rows (the reference returns
+    the same array as numpy after a host round trip)."""
+    batch_partial = batch_partial.contiguous().float()
+    batch_complete = batch_complete.contiguous().float()
+    _abi.require_cuda(batch_partial, batch_complete)
+    B, Np, _ = batch_partial.shape
+    R = batch_complete.shape[1]
+    out = torch.empty((B, surface_pts, 3), dtype=torch.float32, device=batch_partial.device)
+    cnt = torch.empty((B,), dtype=torch.int32, device=batch_partial.device)
+    with torch.cuda.device(batch_partial.device):
+        _abi.check(_abi.lib().seevcn_knn_surface_select(B, Np, R, k, surface_pts, _abi.ptr(batch_partial),
+                                                        _abi.ptr(batch_complete), _abi.ptr(out), _abi.ptr(cnt),
+                                                        _abi.stream()))
+    return (out, cnt) if return_count else out
