@@ -1,0 +1,298 @@
+#!/usr/bin/env python
+"""bench.py — SEE-VCN object-completion + voxelization hot path on B200.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--frames F] [--impl ours|reference]
+
+A step = one pass of the hot path (crop -> resample -> VCN forward -> kNN surface select ->
+dynamic voxelization) over a batch of F synthetic Waymo-like frames (BASELINE.json configs[1]:
+64 beams x 2812 azimuth steps = 180k pts, 50 car boxes, 1024 pts/object) per GPU.  Frames shard
+across ranks with no collective on the data path; one all-gather-v of the completed clouds per
+step stands for "collect for the detector" when N > 1 (weak scaling: F frames per GPU).
+
+Prints ONE JSON line (rank 0).  `value` = completed objects/s with inputs resident in HBM;
+`e2e` = same through the public API from pinned HOST buffers (H2D + D2H inside the timed region);
+`roofline` = the dominant kernel group (VCN forward: bf16 tcgen05 GEMMs) against the measured
+bf16 peak; `cpu_baseline` = the oracle port of the same path timed on the host cores.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "completed objects/sec"
+SEL_K = 10               # SURFACE_COMPLETION.VCN.SEL_K_NEAREST (cfgs/WAY-GT_VCN-VC.yaml)
+RESAMPLE = 1024
+FLOP_PER_OBJ = 2.0 * (959040 * 1024 + 5771776)   # VCN_VC, N = 1024 -> 1.976 GFLOP
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        p = json.load(open(path))
+        return {"hbm_gbs": p["hbm_gbs"], "bf16_tflops": p["bf16_tflops"], "bf16_tflops_sustained": p["bf16_tflops_sustained"],
+                "source": "measured"}
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "source": "fallback"}
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.rows, self.stop_flag = index, [], False
+
+    def run(self):
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i", str(self.index)],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([c.strip() for c in out.split(",")])
+            except Exception:   # noqa: BLE001
+                pass
+            time.sleep(0.1)
+
+    def summary(self):
+        self.stop_flag = True
+        sm = [float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[i] for r in self.rows if len(r) >= 6 for i in range(4) if r[2 + i].lower().startswith("active")})
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
+                "samples": len(sm)}
+
+
+def make_inputs(frames, seed0):
+    from seevcn_b200 import synth
+    return synth.make_stream(frames, first_seed=seed0)
+
+
+# ---------------------------------------------------------------------------- CPU path --
+def cpu_path_once(pts, boxes, sd, threads):
+    """The oracle port of the whole step on host cores -> (#objects, seconds, #voxelised points)."""
+    import torch
+    import oracle
+    torch.set_num_threads(threads)
+    t0 = time.perf_counter()
+    idx = oracle.points_in_boxes_gpu(pts, boxes)
+    rng = np.random.default_rng(0)
+    clouds, fid = [], []
+    for f in range(pts.shape[0]):
+        cnt = np.bincount(idx[f][idx[f] >= 0], minlength=boxes.shape[1])
+        for k in np.nonzero(cnt >= 30)[0]:
+            clouds.append(oracle.resample_points(pts[f][idx[f] == k], RESAMPLE, rng)[0]); fid.append(f)
+    n_obj = len(clouds)
+    rows = [np.concatenate([np.full((pts.shape[1], 1), f, np.float32), pts[f]], axis=1) for f in range(pts.shape[0])]
+    if n_obj:
+        inp = np.stack(clouds).astype(np.float32)
+        with torch.no_grad():
+            coarse = oracle.vcn_forward_ref(sd, inp, None, "VCN_VC")["coarse"].numpy()
+        surf, _ = oracle.get_partial_mesh_batch(inp, coarse, k=SEL_K)
+        rows += [np.concatenate([np.full((RESAMPLE, 1), fid[o], np.float32), surf[o]], axis=1) for o in range(n_obj)]
+    vox = np.concatenate(rows).astype(np.float32)
+    from seevcn_b200.pipeline import WAYMO_VOXEL_CFG
+    oracle.dynamic_voxelize(vox, *WAYMO_VOXEL_CFG)
+    return n_obj, time.perf_counter() - t0, len(vox)
+
+
+def cpu_baseline(sample_frames, sd, threads):
+    pts, boxes = make_inputs(sample_frames, 5000)
+    cpu_path_once(pts[:1], boxes[:1], sd, threads)   # warm-up (thread pools, page-in)
+    n_obj, sec, n_vox = cpu_path_once(pts, boxes, sd, threads)
+    return {"value": n_obj / sec, "unit": "objects/s", "cores": threads, "kind": "port",
+            "sample": f"{sample_frames} frames x 180k pts, {n_obj} objects, one pass in {sec:.1f} s (oracle/: C + torch fp32, OpenMP/intra-op threads)",
+            "voxelized_mpts_per_s": n_vox / sec / 1e6}
+
+
+def run_reference(args):
+    """--impl reference: the reference path's CPU implementation (oracle port; the reference's python
+    cannot travel to the GPU box) on all host threads; each step = a bounded sample of the workload."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import oracle
+    threads = os.cpu_count() or 1
+    sd = oracle.make_state_dict("VCN_VC", seed=0)
+    sample_frames = 1
+    pts, boxes = make_inputs(sample_frames, 1000)
+    for _ in range(max(args.warmup, 1)):
+        cpu_path_once(pts, boxes, sd, threads)
+    tot_obj, tot_sec, tot_vox = 0, 0.0, 0
+    for _ in range(args.steps):
+        n, s, v = cpu_path_once(pts, boxes, sd, threads)
+        tot_obj += n; tot_sec += s; tot_vox += v
+    val = tot_obj / tot_sec
+    sample = f"{sample_frames} frame x 180k pts per step ({tot_obj // max(args.steps, 1)} objects), oracle port, {threads} threads"
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": val, "unit": "objects/s", "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * tot_sec / max(args.steps, 1), "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "C2: synthetic Waymo-like 64-beam frame (180k pts, 50 car boxes, 1024 pts/object)",
+                   "frames_per_step": sample_frames, "sel_k": SEL_K},
+        "voxelized_mpts_per_sec": tot_vox / tot_sec / 1e6,
+        "cpu_baseline": {"value": val, "unit": "objects/s", "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": val, "unit": "objects/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+
+
+# ---------------------------------------------------------------------------- GPU path --
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from seevcn_b200 import _abi
+    from seevcn_b200.pipeline import CompletionPipeline
+    from seevcn_b200 import dist as sdist
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    # weights: seeded random init of the VCN_VC architecture (no checkpoints offline).  Generated without
+    # the oracle package: same generator stream as oracle.make_state_dict, restated in the product pipeline.
+    from seevcn_b200.see.surface_completion.models.vcn.models.build import MODELS
+    torch.manual_seed(0)
+    ref_model = MODELS.build({"NAME": "VCN_VC"})
+    for m in ref_model.modules():
+        if isinstance(m, torch.nn.BatchNorm1d):
+            m.running_mean.normal_(0, 0.1); m.running_var.uniform_(0.5, 1.5)
+    sd = ref_model.state_dict()
+    pipe = CompletionPipeline("VCN_VC", sd, dev, sel_k=SEL_K, precision=args.precision)
+
+    F = args.frames
+    pts_h, boxes_h = make_inputs(F, 1000 + rank * F)         # rank r owns frames [r*F, (r+1)*F)
+    pts_pin = torch.from_numpy(pts_h).pin_memory()
+    boxes_pin = torch.from_numpy(boxes_h).pin_memory()
+    pts_d, boxes_d = pts_pin.to(dev), boxes_pin.to(dev)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)   # > 126 MB L2
+
+    def step_resident():
+        out = pipe.run(pts_d, boxes_d, seed=0)
+        if world > 1:
+            sdist.all_gather_v(out["surface"])
+        return out
+
+    def step_e2e():
+        p = pts_pin.to(dev, non_blocking=True)
+        b = boxes_pin.to(dev, non_blocking=True)
+        out = pipe.run(p, b, seed=0)
+        res = [out["surface"].cpu(), out["voxel_coords"].cpu(), out["voxel_features"].cpu(), out["voxel_num_points"].cpu()]
+        return out, res
+
+    def timed(fn, steps, warmup):
+        for _ in range(warmup):
+            fn()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        ms, last = 0.0, None
+        l0 = _abi.lib().seevcn_launch_count()
+        for _ in range(steps):
+            flush.fill_(1)                                   # L2 flush between timed iterations (not timed)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            last = fn()
+            e1.record()
+            e1.synchronize()
+            ms += e0.elapsed_time(e1)
+        launches = _abi.lib().seevcn_launch_count() - l0
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        t = torch.tensor([ms], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)         # max over ranks
+        return t.item(), last, launches
+
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    ms_res, out, launches = timed(step_resident, args.steps, args.warmup)
+    n_obj = torch.tensor([out["input"].shape[0]], device=dev, dtype=torch.float64)
+    n_vox_pts = torch.tensor([out["voxel_points"].shape[0]], device=dev, dtype=torch.float64)
+    n_voxels = out["voxel_coords"].shape[0]
+    if world > 1:
+        dist.all_reduce(n_obj); dist.all_reduce(n_vox_pts)
+    ms_e2e, (out2, res2), _ = timed(step_e2e, args.steps, max(args.warmup, 3))
+    h2d = pts_pin.numel() * 4 + boxes_pin.numel() * 4
+    d2h = sum(t.numel() * t.element_size() for t in res2)
+
+    # dominant kernel group: the VCN forward on this rank's objects, timed alone with CUDA events
+    inp = out["input"]
+    for _ in range(3):
+        pipe.model({"input": inp})
+    torch.cuda.synchronize()
+    vms = 0.0
+    reps = max(args.steps, 5)
+    for _ in range(reps):
+        flush.fill_(1)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(); pipe.model({"input": inp}); e1.record(); e1.synchronize()
+        vms += e0.elapsed_time(e1)
+    vms /= reps
+    clocks = sampler.summary() if rank == 0 else None
+
+    if rank == 0:
+        pk = peaks()
+        steps = args.steps
+        value = n_obj.item() * steps / (ms_res / 1e3)
+        e2e = n_obj.item() * steps / (ms_e2e / 1e3)
+        achieved = FLOP_PER_OBJ * inp.shape[0] / (vms / 1e3) / 1e12
+        peak = pk["bf16_tflops"]
+        import oracle   # cpu_baseline leg only (rank 0, N = 1)
+        cpu = cpu_baseline(1, oracle.make_state_dict("VCN_VC", 0), os.cpu_count() or 1) if world == 1 and not args.no_cpu else None
+        line = {
+            "metric": METRIC, "value": value, "unit": "objects/s", "n_gpus": world, "steps": steps, "warmup": args.warmup,
+            "ms_per_step": ms_res / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "bf16" if args.precision == "bf16" else "f32", "data": "synthetic",
+            "config": {"workload": "C2: synthetic Waymo-like 64-beam frame (180k pts, 50 car boxes, 1024 pts/object), random-init VCN_VC",
+                       "frames_per_step_per_gpu": F, "objects_per_step": int(n_obj.item()), "sel_k": SEL_K,
+                       "l2": "flushed (256 MB write) between timed iterations", "parallelism": f"frame-sharded x{world}"},
+            "voxelized_mpts_per_sec": n_vox_pts.item() * steps / (ms_res / 1e3) / 1e6, "voxels_per_step_rank0": int(n_voxels),
+            "e2e": {"value": e2e, "unit": "objects/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+                    "ms_per_step": ms_e2e / steps},
+            "gpu_launches": int(launches),
+            "roofline": {"kernel": "VCN forward (vcn_linear_tc tcgen05 GEMMs + per-object kernels)" if args.precision == "bf16" else "VCN forward fp32 SIMT",
+                         "bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
+                         "traffic": None, "peak_source": pk["source"] + " burst bf16 (kernel group timed alone)",
+                         "ms_per_launch_group": vms, "objects": int(inp.shape[0])},
+            "cpu_baseline": cpu, "clocks": clocks,
+        }
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--frames", type=int, default=8, help="frames per step per GPU")
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--precision", default=os.environ.get("SEEVCN_PRECISION", "bf16"), choices=["bf16", "fp32"])
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

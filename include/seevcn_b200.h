@@ -33,6 +33,8 @@ typedef void* seevcn_stream_t;   /* cudaStream_t */
 
 int         seevcn_abi_version(void);
 const char* seevcn_last_error(void);
+/* Number of kernels this library has launched in this process (bench.py's gpu_launches). */
+unsigned long long seevcn_launch_count(void);
 /* Returns 0 when device `dev` is an sm_100 part this library was built for. */
 int         seevcn_check_device(int dev);
 
@@ -130,6 +132,16 @@ int seevcn_knn_surface_select(int b, int n_partial, int r, int k, int surface_pt
                               const float* partial, const float* complete,
                               float* out, int* sel_count, seevcn_stream_t stream);
 
+/* ref: get_largest_cluster(_batch)  see/surface_completion/models/vcn/utils/sampling.py:83-109
+ * (open3d cluster_dbscan(eps, min_points) -> largest cluster -> tiled to total_pts rows), called with
+ * min_points = 2 at see/surface_completion/models/VCN.py:95-98.  min_points in {1, 2}: DBSCAN is then exactly
+ * connected components of the eps-graph (strict d < eps, float64), isolated points are noise when
+ * min_points = 2.  pts (B,n,3), n <= 1024 -> out (B,total_pts,3): members of the largest component in
+ * ascending row order, repeated cyclically; out_count (B) = members (0: everything was noise, rows zero).
+ * PARITY UNPINNED (open3d is not vendored). */
+int seevcn_largest_cluster(int b, int n, int total_pts, double eps, int min_points, const float* pts,
+                           float* out, int* out_count, seevcn_stream_t stream);
+
 /* ------------------------------------------- stages 2+5: VCN forward (canonicalise+MLP) */
 
 /* Folded fp32 parameters, all DEVICE pointers, row-major (out,in) like torch Linear /
@@ -180,6 +192,17 @@ int seevcn_vcn_forward(const seevcn_vcn_model* model, int num_obj, int n_pts,
                        float* coarse, float* reg_rot, float* reg_centre,
                        void* workspace, size_t workspace_bytes, int precision,
                        seevcn_stream_t stream);
+
+/* One shared-MLP layer on the tcgen05 path, standalone (the building block of seevcn_vcn_forward;
+ * ref: nn.Conv1d(k=1) / nn.Linear as used in VCN_VC.py:116-131):
+ *   Y[r, c] = act(sum_k bf16(X[r,k]) * bf16(W[c,k]) + bias[c] + obj_bias[r / rows_per_obj, c])   (fp32 accumulate)
+ * X (rows,cin) f32, W (cout,cin) f32, bias (cout) or NULL, obj_bias (rows/rows_per_obj, cout) or NULL,
+ * act 0 none / 1 ReLU / 2 LeakyReLU(0.01).  Y (rows,cout) f32 or NULL; colmax (rows/rows_per_obj, cout) f32 or
+ * NULL receives the per-object max over rows (must be pre-filled with -inf).  */
+size_t seevcn_linear_bf16_workspace_bytes(int rows, int cin, int cout);
+int seevcn_linear_bf16(int rows, int cin, int cout, const float* X, const float* W, const float* bias,
+                       const float* obj_bias, int rows_per_obj, int act, float* Y, float* colmax,
+                       void* workspace, size_t workspace_bytes, seevcn_stream_t stream);
 
 /* ------------------------------------------------------------ stage 6: voxelization -- */
 

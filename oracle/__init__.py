@@ -46,6 +46,7 @@ def lib():
         L.orc_fps.argtypes = [_I, _I, _I, _f, _f, _i]
         L.orc_knn.argtypes = [_I, _I, _I, _I, _f, _f, ctypes.c_void_p, _i]
         L.orc_knn_surface_select.argtypes = [_I, _I, _I, _I, _I, _f, _f, _f, _i]
+        L.orc_largest_cluster.argtypes = [_I, _I, _I, ctypes.c_double, _I, _f, _f, _i]
         L.orc_dynamic_voxelize.argtypes = [_I, _I, _f, _f, _f, _i, _i, _f, _i]
         L.orc_dynamic_voxelize.restype = _I
         L.orc_hard_voxelize.argtypes = [_I, _I, _f, _f, _f, _i, _I, _I, _f, _i, _i]
@@ -146,6 +147,17 @@ def get_partial_mesh_batch(partial, complete, k=20, surface_pts=1024):
     out = np.empty((B, surface_pts, 3), np.float32)
     cnt = np.empty((B,), np.int32)
     lib().orc_knn_surface_select(B, NP, R, k, surface_pts, partial, complete, out, cnt)
+    return out, cnt
+
+
+def get_largest_cluster_batch(pc, eps=0.4, min_points=1, total_pts=1024):
+    """ref: sampling.py:83-109 (open3d DBSCAN -> largest cluster) — PARITY UNPINNED.  pc (B,N,3) ->
+    (B,total_pts,3), member counts (B,)"""
+    pc = _c(pc)
+    B, N, _ = pc.shape
+    out = np.empty((B, total_pts, 3), np.float32)
+    cnt = np.empty((B,), np.int32)
+    lib().orc_largest_cluster(B, N, total_pts, float(eps), int(min_points), pc, out, cnt)
     return out, cnt
 
 

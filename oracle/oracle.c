@@ -21,15 +21,16 @@
  *      detector3d/pcdet/ops/roiaware_pool3d/src/roiaware_pool3d.cpp:121-140    (CPU, MARGIN 1e-2)
  * fused != 0 reproduces the GPU build's contraction:
  *      local_x = fma(sx, cosa, rn(sy * -sina)); local_y = fma(sy, cosa, rn(sx * sina))
- * Returns the in-box flag; *slack (optional) receives the smallest absolute distance of any
- * of the three comparisons from its decision boundary, so tests can tell decided points from
- * ones that sit within an ulp of a face (where cosf/sinf of libm and CUDA may disagree). */
+ * Returns the in-box flag; *slack (optional) receives the smallest absolute distance of the
+ * x / y comparisons from their decision boundary (1e30 when z already rejects), so tests can tell
+ * decided points from ones that sit within an ulp of a face (where cosf/sinf of libm and CUDA
+ * may round differently). */
 static int pt_in_box(const float* pt, const float* box, float margin, int fused, double* slack) {
     const float x = pt[0], y = pt[1], z = pt[2];
     const float cx = box[0], cy = box[1], cz = box[2];
     const float dx = box[3], dy = box[4], dz = box[5], rz = box[6];
     const float az = fabsf(z - cz);
-    if (slack) *slack = fabs((double)az - (double)dz / 2.0);
+    if (slack) *slack = 1e30;   /* the z test involves no cos/sin: it is exact on both sides */
     if ((double)az > (double)dz / 2.0) return 0;
     const float cosa = cosf(-rz), sina = sinf(-rz);
     const float sx = x - cx, sy = y - cy;
@@ -79,9 +80,18 @@ void orc_points_in_boxes_cpu(int T, int P, const float* boxes, const float* pts,
 /* ---- furthest point sampling -------------------------------------------------------------
  * ref: farthest_point_sampling_kernel, pointnet2_batch/src/sampling_gpu.cu:100-216;
  *      block size rule opt_n_threads, cuda_utils.h:10-14; temp pre-fill 1e10, pointnet2_utils.py:26.
- * Tie rule of the kernel: a thread keeps the first (lowest k) strict maximum of its stride,
- * the tree keeps the LOWER thread on equal values -> the winner is the candidate of the
- * lowest thread id among the maxima.  Iterating thread-major with a strict '>' is the same. */
+ * Tie rule of the kernel: a thread keeps the first (lowest k) strict maximum of its stride; the
+ * shared-memory tree (strides bs/2 ... 1, `v2 > v1 ? i2 : i1`) keeps the LOWER position on equal
+ * values.  After the level with stride s position p holds the winner of the threads == p (mod s), so
+ * the last level decides by thread-id bit 0, the one before by bit 1, ...: among equal maxima the
+ * thread with the smallest BIT-REVERSED id wins. */
+static unsigned brev32(unsigned v) {
+    v = ((v >> 1) & 0x55555555u) | ((v & 0x55555555u) << 1);
+    v = ((v >> 2) & 0x33333333u) | ((v & 0x33333333u) << 2);
+    v = ((v >> 4) & 0x0f0f0f0fu) | ((v & 0x0f0f0f0fu) << 4);
+    v = ((v >> 8) & 0x00ff00ffu) | ((v & 0x00ff00ffu) << 8);
+    return (v >> 16) | (v << 16);
+}
 static int opt_n_threads(int n) {
     const int pow_2 = (int)(log((double)n) / log(2.0));
     int bs = 1 << pow_2;
@@ -109,10 +119,12 @@ void orc_fps(int B, int N, int M, const float* xyz, float* temp, int* idxs) {
                 const float dd = fmaf(ddz, ddz, fmaf(ddy, ddy, ddx * ddx));
                 t[k] = fminf(dd, t[k]);
             }
-            for (int tid = 0; tid < bs; ++tid) {   /* argmax in the kernel's thread-major order */
+            unsigned bestkey = 0xffffffffu;
+            for (int tid = 0; tid < bs; ++tid) {   /* per-thread strict max, then the tree's tie rule */
                 float tb = -1.f; int ti = 0;
                 for (int k = tid; k < N; k += bs) if (t[k] > tb) { tb = t[k]; ti = k; }
-                if (tb > best) { best = tb; besti = ti; }
+                const unsigned key = brev32((unsigned)tid);
+                if (tb > best || (tb == best && key < bestkey)) { best = tb; besti = ti; bestkey = key; }
             }
             old = besti;
             out[j] = old;
@@ -170,6 +182,47 @@ void orc_knn_surface_select(int B, int NP, int R, int K, int SP, const float* pa
             else o[0] = o[1] = o[2] = 0.f;
         }
         free(sel); free(nn); free(mark);
+    }
+}
+
+/* ref: get_largest_cluster, see/surface_completion/models/vcn/utils/sampling.py:83-109 -> open3d
+ * cluster_dbscan (NOT vendored; setup.py:25 pins 0.14.1) — PARITY UNPINNED.  Restated for min_points <= 2,
+ * where DBSCAN = connected components of the graph {d^2 < eps^2} on float64 copies of the points
+ * (isolated points are noise for min_points = 2); clusters are labelled in order of their first point,
+ * np.bincount/argmax picks the largest (first on ties), members keep row order and are tiled to total_pts. */
+static int uf_find(int* p, int i) { while (p[i] != i) { p[i] = p[p[i]]; i = p[i]; } return i; }
+void orc_largest_cluster(int B, int N, int TP, double eps, int min_points, const float* pts, float* out, int* out_count) {
+#pragma omp parallel for schedule(dynamic)
+    for (int b = 0; b < B; ++b) {
+        const float* p = pts + (long long)b * N * 3;
+        int* par = (int*)malloc(sizeof(int) * (size_t)(N > 0 ? N : 1));
+        int* deg = (int*)calloc((size_t)(N > 0 ? N : 1), sizeof(int));
+        int* sz = (int*)calloc((size_t)(N > 0 ? N : 1), sizeof(int));
+        for (int i = 0; i < N; ++i) par[i] = i;
+        for (int i = 0; i < N; ++i)
+            for (int j = i; j < N; ++j) {
+                const double dx = (double)p[i * 3] - (double)p[j * 3], dy = (double)p[i * 3 + 1] - (double)p[j * 3 + 1],
+                             dz = (double)p[i * 3 + 2] - (double)p[j * 3 + 2];
+                const double d2 = (dx * dx + dy * dy) + dz * dz;
+                if (d2 < eps * eps) {
+                    ++deg[i]; if (j != i) ++deg[j];
+                    if (j != i) { const int a = uf_find(par, i), c = uf_find(par, j); if (a < c) par[c] = a; else par[a] = c; }
+                }
+            }
+        int best = -1, bestsize = 0;
+        for (int i = 0; i < N; ++i) if (deg[i] >= min_points) ++sz[uf_find(par, i)];
+        for (int i = 0; i < N; ++i) if (sz[i] > bestsize) { bestsize = sz[i]; best = i; }   /* root = smallest index */
+        float* o = out + (long long)b * TP * 3;
+        out_count[b] = bestsize;
+        if (best < 0) { memset(o, 0, sizeof(float) * 3 * (size_t)TP); }
+        else {
+            int* list = (int*)malloc(sizeof(int) * (size_t)bestsize);
+            int m = 0;
+            for (int i = 0; i < N; ++i) if (deg[i] >= min_points && uf_find(par, i) == best) list[m++] = i;
+            for (int j = 0; j < TP; ++j) memcpy(o + (long long)j * 3, p + (long long)list[j % m] * 3, 12);
+            free(list);
+        }
+        free(par); free(deg); free(sz);
     }
 }
 

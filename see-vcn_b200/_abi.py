@@ -31,6 +31,7 @@ class VcnParams(ctypes.Structure):
 SIGNATURES = {
     "seevcn_abi_version": (I, []),
     "seevcn_last_error": (c_char_p, []),
+    "seevcn_launch_count": (ctypes.c_ulonglong, []),
     "seevcn_check_device": (I, [I]),
     "seevcn_points_in_boxes": (I, [I, I, I, P, P, P, P]),
     "seevcn_points_in_boxes_dense": (I, [I, I, P, P, P, P]),
@@ -43,10 +44,13 @@ SIGNATURES = {
     "seevcn_group_points": (I, [I, I, I, I, I, P, P, P, P]),
     "seevcn_knn": (I, [I, I, I, I, P, P, P, P, P]),
     "seevcn_knn_surface_select": (I, [I, I, I, I, I, P, P, P, P, P]),
+    "seevcn_largest_cluster": (I, [I, I, I, ctypes.c_double, I, P, P, P, P]),
     "seevcn_vcn_create": (I, [POINTER(VcnParams), POINTER(c_void_p), P]),
     "seevcn_vcn_destroy": (None, [P]),
     "seevcn_vcn_workspace_bytes": (c_size_t, [P, I, I]),
     "seevcn_vcn_forward": (I, [P, I, I, P, P, P, P, P, P, c_size_t, I, P]),
+    "seevcn_linear_bf16_workspace_bytes": (c_size_t, [I, I, I]),
+    "seevcn_linear_bf16": (I, [I, I, I, P, P, P, P, I, I, P, P, P, c_size_t, P]),
     "seevcn_mean_vfe": (I, [I, I, I, P, P, P, P]),
     "seevcn_dynamic_voxelize_workspace_bytes": (c_size_t, [I, I, I]),
     "seevcn_dynamic_voxelize": (I, [I, I, P, POINTER(ctypes.c_float), POINTER(ctypes.c_float), POINTER(c_int),

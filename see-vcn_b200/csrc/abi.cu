@@ -1,4 +1,5 @@
 // C-ABI plumbing: version, per-thread error message, device check.
+#include <atomic>
 #include <stdarg.h>
 #include <string.h>
 #include "common.cuh"
@@ -11,6 +12,10 @@ void seevcn_set_error(const char* fmt, ...) {
     vsnprintf(g_err, sizeof(g_err), fmt, ap);
     va_end(ap);
 }
+
+static std::atomic<unsigned long long> g_launches{0};
+void seevcn_count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+extern "C" unsigned long long seevcn_launch_count(void) { return g_launches.load(); }
 
 extern "C" int seevcn_abi_version(void) { return 1; }
 extern "C" const char* seevcn_last_error(void) { return g_err; }

@@ -28,7 +28,12 @@ void seevcn_set_error(const char* fmt, ...);
         }                                                                              \
     } while (0)
 
-#define SEEVCN_LAUNCH_CHECK() SEEVCN_CUDA_CHECK(cudaGetLastError())
+void seevcn_count_launch();
+#define SEEVCN_LAUNCH_CHECK()                      \
+    do {                                           \
+        seevcn_count_launch();                     \
+        SEEVCN_CUDA_CHECK(cudaGetLastError());     \
+    } while (0)
 
 static inline cudaStream_t as_stream(seevcn_stream_t s) { return reinterpret_cast<cudaStream_t>(s); }
 

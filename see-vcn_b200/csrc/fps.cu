@@ -14,9 +14,9 @@
 //
 // Bit-exactness: same block size rule (cuda_utils.h:10-14), same strided point->thread
 // map, the distance expression with the contraction nvcc 12.9 emits for the reference
-// (fma(dz,dz, fma(dy,dy, dx*dx))), fminf, strict '>' inside a thread and lower-thread-wins
-// across threads — i.e. the reference's tie rule, so indices match even on clouds with
-// duplicate points.
+// (fma(dz,dz, fma(dy,dy, dx*dx))), fminf, strict '>' inside a thread and the reference tree's
+// tie rule across threads (smallest bit-reversed thread id, see better()), so indices match even
+// on clouds with duplicate points.
 #include <cmath>
 #include "common.cuh"
 
@@ -33,18 +33,26 @@ int ref_block_size(int n) {
 
 struct Cand { float v; int i; };
 
-// partner is the HIGHER thread: it wins only with a strictly larger value (ref __update :93-98)
-__device__ __forceinline__ Cand take_hi(Cand lo, Cand hi) { return hi.v > lo.v ? hi : lo; }
+// The reference's shared-memory tree (__update, sampling_gpu.cu:93-98, strides bs/2..1) keeps the
+// LOWER position on equal values; after the level with stride s position p holds the winner of the
+// threads == p (mod s), so among equal maxima the thread with the smallest bit-reversed id wins.
+// The owning thread of candidate k is k & (bs-1), which makes the rule a pure function of (v, i):
+// any reduction order gives the reference's answer.
+__device__ __forceinline__ Cand better(Cand a, Cand b, unsigned mask) {
+    if (b.v > a.v) return b;
+    if (b.v == a.v && __brev((unsigned)b.i & mask) < __brev((unsigned)a.i & mask)) return b;
+    return a;
+}
 
-__device__ __forceinline__ Cand warp_argmax(Cand c) {
+__device__ __forceinline__ Cand warp_argmax(Cand c, unsigned mask) {
 #pragma unroll
     for (int off = 16; off >= 1; off >>= 1) {
         Cand o;
-        o.v = __shfl_down_sync(0xffffffffu, c.v, off);
-        o.i = __shfl_down_sync(0xffffffffu, c.i, off);
-        c = take_hi(c, o);   // out-of-range partner returns own value
+        o.v = __shfl_xor_sync(0xffffffffu, c.v, off);
+        o.i = __shfl_xor_sync(0xffffffffu, c.i, off);
+        c = better(c, o, mask);
     }
-    return c;   // valid in lane 0
+    return c;   // valid in every lane
 }
 
 // PPT: points per thread held in registers.  SMEM_XYZ: xyz staged in shared memory.
@@ -105,14 +113,14 @@ fps_kernel(int n, int m, int bs, const float* __restrict__ dataset, float* __res
                 if (d2 > c.v) { c.v = d2; c.i = k; }
             }
         }
-        c = warp_argmax(c);
+        c = warp_argmax(c, (unsigned)bs - 1u);
         const int buf = r & 1;
         if (lane_id() == 0) { s_v[buf][warp_id()] = c.v; s_i[buf][warp_id()] = c.i; }
         __syncthreads();
         Cand w; w.v = -2.f; w.i = 0;
         if (lane_id() < nwarps) { w.v = s_v[buf][lane_id()]; w.i = s_i[buf][lane_id()]; }
-        w = warp_argmax(w);
-        old = __shfl_sync(0xffffffffu, w.i, 0);
+        w = warp_argmax(w, (unsigned)bs - 1u);
+        old = w.i;
         if (tid == 0) idxs[r] = old;
     }
     if (temp) {
@@ -150,14 +158,14 @@ fps_kernel_global(int n, int m, int bs, const float* __restrict__ dataset, float
             temp[k] = d2;
             if (d2 > c.v) { c.v = d2; c.i = k; }
         }
-        c = warp_argmax(c);
+        c = warp_argmax(c, (unsigned)bs - 1u);
         const int buf = r & 1;
         if (lane_id() == 0) { s_v[buf][warp_id()] = c.v; s_i[buf][warp_id()] = c.i; }
         __syncthreads();
         Cand w; w.v = -2.f; w.i = 0;
         if (lane_id() < nwarps) { w.v = s_v[buf][lane_id()]; w.i = s_i[buf][lane_id()]; }
-        w = warp_argmax(w);
-        old = __shfl_sync(0xffffffffu, w.i, 0);
+        w = warp_argmax(w, (unsigned)bs - 1u);
+        old = w.i;
         if (tid == 0) idxs[r] = old;
     }
 }
@@ -166,7 +174,7 @@ template <int PPT>
 int launch_fps(int b, int n, int m, int bs, const float* dataset, float* temp, int* idxs, cudaStream_t st) {
     const size_t smem = (size_t)3 * n * sizeof(float);
     auto kern = fps_kernel<PPT, true>;
-    if (smem > 48 * 1024)
+    if (smem > 40 * 1024)   // dynamic + 512 B static must stay under the 48 KB default
         SEEVCN_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     kern<<<b, bs < 32 ? 32 : bs, smem, st>>>(n, m, bs, dataset, temp, idxs);
     SEEVCN_LAUNCH_CHECK();

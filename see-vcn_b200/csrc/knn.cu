@@ -221,7 +221,7 @@ static int launch_select(int b, int np, int r, int k, int surface_pts, const flo
     const size_t smem = (size_t)(3 * r + 3 * np) * 4 + (size_t)hash_size * 4 + (size_t)nwords * 4 + (size_t)(nwords + 1) * 4;
     SEEVCN_REQUIRE(smem <= 227 * 1024, "knn_surface_select: r=%d np=%d needs %zu B of shared memory (> 227 KB)", r, np, smem);
     auto kern = knn_surface_select_kernel<KMAX>;
-    if (smem > 48 * 1024)
+    if (smem > 40 * 1024)
         SEEVCN_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     kern<<<b, kSelThreads, smem, st>>>(np, r, k, surface_pts, hash_size, partial, complete, out, sel_count);
     SEEVCN_LAUNCH_CHECK();

@@ -21,6 +21,7 @@
 int vcn_linear_tc(const LinearW& L, int rows, const __nv_bfloat16* X, int ldx, const float* obj_bias,
                   int rows_per_obj, int act, __nv_bfloat16* Y, int ldy, float* Yf32, float* colmax,
                   cudaStream_t st);   // vcn_tc.cu
+int vcn_pointwise3(const LinearW& L, size_t rows, const float* X, int act, __nv_bfloat16* Y, int ldy, cudaStream_t st);
 
 namespace {
 
@@ -272,11 +273,11 @@ int fill(float* p, size_t n, float v, cudaStream_t st) {
 
 // ----------------------------------------------------------------- workspace layout --
 constexpr int kChunkObjF32 = 16;   // objects per pass of the fp32 path (activations 2 x 32 MB at N=1024)
-constexpr int kChunkObjTC = 128;   // bf16 path: 128 x 1024 x 512 x 2 B = 128 MB per buffer... see vcn_ws()
+constexpr int kChunkObjTC = 64;    // bf16 path: 64 x 1024 x 512 x 2 B = 64 MB per activation buffer (L2-sized)
 
 struct VcnWs {
     size_t frames, poses, pts3, pose_feat, h512, rel, g256, objbias, feat, fc_a, fc_b, coarse_cn, act_a, act_b,
-        pts16, total;
+        fcx_a, fcx_b, total;
     int chunk;
 };
 
@@ -303,7 +304,8 @@ VcnWs vcn_ws(int num_obj, int n, int num_coarse, int precision) {
     const size_t esz = precision == 1 ? 4 : 2;
     w.act_a = take(rows * 512 * esz);
     w.act_b = take(rows * 512 * esz);
-    w.pts16 = take(rows * 64 * 2);   // bf16 path: K-padded copy of the 3-vector inputs
+    w.fcx_a = take(B * 1024 * 2);    // bf16 path: bf16 copies of the per-object feature vectors
+    w.fcx_b = take(B * 1024 * 2);
     w.total = o;
     return w;
 }
@@ -422,26 +424,30 @@ extern "C" int seevcn_vcn_forward(const seevcn_vcn_model* M, int num_obj, int n,
     float* actB = reinterpret_cast<float*>(ws + w.act_b);
     auto* actA16 = reinterpret_cast<__nv_bfloat16*>(ws + w.act_a);
     auto* actB16 = reinterpret_cast<__nv_bfloat16*>(ws + w.act_b);
-    auto* pts16 = reinterpret_cast<__nv_bfloat16*>(ws + w.pts16);
     const float NEG_INF = -__builtin_huge_valf();
 
-    // per-point layer: X (rows, cin) -> act(X W^T + b [+ obj_bias]); fp32 or bf16 buffers by path
+    auto* fcxA = reinterpret_cast<__nv_bfloat16*>(ws + w.fcx_a);
+    auto* fcxB = reinterpret_cast<__nv_bfloat16*>(ws + w.fcx_b);
+    // per-point layer: X (rows, cin) -> act(X W^T + b [+ obj_bias]); fp32 SIMT or bf16 tcgen05 by path.
+    // K = 3 input layers read the fp32 points directly on both paths.
     auto pp_layer = [&](const LinearW& L, int rows, const void* X, int ldx, const float* ob, int act, void* Y, int ldy,
                         float* colmax) -> int {
-        if (tc) return vcn_linear_tc(L, rows, static_cast<const __nv_bfloat16*>(X), ldx, ob, n, act,
-                                     static_cast<__nv_bfloat16*>(Y), ldy, nullptr, colmax, st);
-        return linear_f32(L, rows, static_cast<const float*>(X), ldx, ob, n, act, static_cast<float*>(Y), ldy, colmax, st);
+        if (!tc) return linear_f32(L, rows, static_cast<const float*>(X), ldx, ob, n, act, static_cast<float*>(Y), ldy, colmax, st);
+        if (L.cin == 3) return vcn_pointwise3(L, (size_t)rows, static_cast<const float*>(X), act, static_cast<__nv_bfloat16*>(Y), ldy, st);
+        return vcn_linear_tc(L, rows, static_cast<const __nv_bfloat16*>(X), ldx, ob, n, act,
+                             static_cast<__nv_bfloat16*>(Y), ldy, nullptr, colmax, st);
     };
-    // the 3-vector input of a per-point stack, in the layout the path wants
-    auto pts_in = [&](int rows) -> int {
-        if (!tc) return SEEVCN_OK;
-        const size_t tot = (size_t)rows * 64;
-        f32_to_bf16_kernel<<<(unsigned)div_up(tot, (size_t)256), 256, 0, st>>>(rows, 3, pts3, 3, pts16, 64);
+    // per-object FC layer: X fp32 (B, cin) -> fp32 Y (B, cout); the tcgen05 path converts X to bf16 first
+    auto fc_layer = [&](const LinearW& L, const float* X, int act, float* Y, __nv_bfloat16* xb) -> int {
+        if (!tc || L.cout % 128 != 0) return linear_f32(L, num_obj, X, L.cin, nullptr, 1, act, Y, L.cout, nullptr, st);
+        const size_t tot = (size_t)num_obj * L.kpad;
+        f32_to_bf16_kernel<<<(unsigned)div_up(tot, (size_t)256), 256, 0, st>>>(num_obj, L.cin, X, L.cin, xb, L.kpad);
         SEEVCN_LAUNCH_CHECK();
-        return SEEVCN_OK;
+        return vcn_linear_tc(L, num_obj, xb, L.kpad, nullptr, 1, act, nullptr, 0, Y, nullptr, st);
     };
-    const void* ptsX = tc ? static_cast<const void*>(pts16) : static_cast<const void*>(pts3);
-    const int ptsLd = tc ? 64 : 3;
+    auto pts_in = [&](int) -> int { return SEEVCN_OK; };
+    const void* ptsX = pts3;
+    const int ptsLd = 3;
     void* A = tc ? static_cast<void*>(actA16) : static_cast<void*>(actA);
     void* Bf = tc ? static_cast<void*>(actB16) : static_cast<void*>(actB);
 
@@ -456,7 +462,7 @@ extern "C" int seevcn_vcn_forward(const seevcn_vcn_model* M, int num_obj, int n,
             TRY(pp_layer(M->pose_enc2, rows, A, 64, nullptr, ACT_LEAKY, Bf, 128, nullptr));
             TRY(pp_layer(M->pose_enc4, rows, Bf, 128, nullptr, ACT_NONE, nullptr, 0, pose_feat + (size_t)o0 * 1024));
         }
-        TRY(linear_f32(M->pose_fc0, num_obj, pose_feat, 1024, nullptr, 1, ACT_LEAKY, h512, 512, nullptr, st));
+        TRY(fc_layer(M->pose_fc0, pose_feat, ACT_LEAKY, h512, fcxA));
         TRY(linear_f32(M->pose_fc2, num_obj, h512, 512, nullptr, 1, ACT_NONE, rel, 16, nullptr, st));
         vcn_pose_kernel<<<div_up(num_obj, 128), 128, 0, st>>>(num_obj, rel, 16, frames, poses, reg_rot, reg_centre);
         SEEVCN_LAUNCH_CHECK();
@@ -482,9 +488,9 @@ extern "C" int seevcn_vcn_forward(const seevcn_vcn_model* M, int num_obj, int n,
         TRY(pp_layer(M->enc2_0_local, rows, Bf, 256, objbias + (size_t)o0 * 512, ACT_RELU, A, 512, nullptr));
         TRY(pp_layer(M->enc2_3, rows, A, 512, nullptr, ACT_NONE, nullptr, 0, feat + (size_t)o0 * 1024));
     }
-    TRY(linear_f32(M->fc0, num_obj, feat, 1024, nullptr, 1, ACT_RELU, fc_a, 1024, nullptr, st));
-    TRY(linear_f32(M->fc2, num_obj, fc_a, 1024, nullptr, 1, ACT_RELU, fc_b, 1024, nullptr, st));
-    TRY(linear_f32(M->fc4, num_obj, fc_b, 1024, nullptr, 1, ACT_NONE, coarse_cn, 3 * M->num_coarse, nullptr, st));
+    TRY(fc_layer(M->fc0, feat, ACT_RELU, fc_a, fcxA));
+    TRY(fc_layer(M->fc2, fc_a, ACT_RELU, fc_b, fcxB));
+    TRY(fc_layer(M->fc4, fc_b, ACT_NONE, coarse_cn, fcxA));
     vcn_output_kernel<<<dim3(div_up(M->num_coarse, 256), num_obj), 256, 0, st>>>(M->num_coarse, M->viewer_centred,
                                                                                  coarse_cn, frames, poses, coarse);
     SEEVCN_LAUNCH_CHECK();

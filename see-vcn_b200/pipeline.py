@@ -1,0 +1,85 @@
+"""Frame-level driver of the hot path: crop -> resample -> VCN -> kNN surface -> voxelize.
+
+Mirrors what the reference spreads over ``SEE_VCN.isolate_gt_pts`` / ``complete_gt_pts``
+(see/surface_completion/SEE_VCN.py:61-115), ``VCN.inference`` (see/surface_completion/models/VCN.py:43-104)
+and the detector's voxelization front end (detector3d/pcdet/models/backbones_3d/vfe/dynamic_mean_vfe.py:37-76),
+but keeps every tensor on the device between stages: the reference goes through open3d crops on
+the host, a D2H copy + cKDTree per object and a .pcd file.
+"""
+import numpy as np
+import torch
+
+from .pcdet.ops.roiaware_pool3d import roiaware_pool3d_utils as roi
+from .pcdet.models.backbones_3d.vfe.dynamic_mean_vfe import dynamic_voxelize
+from .see.surface_completion.models.vcn.models.build import MODELS
+from .see.surface_completion.models.vcn.utils.sampling import get_partial_mesh_batch
+
+WAYMO_VOXEL_CFG = ([-75.2, -75.2, -2.0, 75.2, 75.2, 4.0], [0.1, 0.1, 0.15], [1504, 1504, 40])   # sc_waymo_dataset.yaml:4,39-45
+
+
+def resample_choice(count, n_points, rng):
+    """Indices into the tiled cloud, as ResamplePoints draws them (data_transforms.py:254-262)."""
+    reps = int(np.ceil(n_points / count))
+    return rng.permutation(reps * count)[:n_points].astype(np.int32)
+
+
+class CompletionPipeline:
+    def __init__(self, model_name="VCN_VC", state_dict=None, device=None, sel_k=10, min_lidar_pts=30, resample_num=1024,
+                 voxel_cfg=WAYMO_VOXEL_CFG, precision="bf16"):
+        self.device = device if device is not None else torch.device("cuda", torch.cuda.current_device())
+        self.model = MODELS.build({"NAME": model_name}, precision=precision)
+        self.state_dict = state_dict
+        if state_dict is not None:
+            self.model.load_state_dict({k.replace("module.", ""): v for k, v in state_dict.items()})
+        self.model.to(self.device).eval()
+        self.model_name = model_name
+        self.sel_k = sel_k                    # SURFACE_COMPLETION.VCN.SEL_K_NEAREST
+        self.min_lidar_pts = min_lidar_pts    # SURFACE_COMPLETION.MIN_LIDAR_PTS
+        self.resample_num = resample_num
+        self.voxel_cfg = voxel_cfg
+
+    @torch.no_grad()
+    def complete(self, points, boxes, seed=0):
+        """points (F,P,3), boxes (F,T,7) CUDA -> dict with the per-object clouds.  One host sync (box counts)."""
+        F, P, _ = points.shape
+        T = boxes.shape[1]
+        idx, counts, offsets, lists = roi.crop_points_in_boxes(points, boxes)
+        cnt = counts.cpu().numpy()                                   # F*T ints: the only D2H before the results
+        keep = np.argwhere(cnt >= self.min_lidar_pts)                # SEE_VCN.py:71
+        out = {"box_idxs_of_pts": idx, "box_counts": counts, "obj_frame": keep[:, 0].astype(np.int32),
+               "obj_box": keep[:, 1].astype(np.int32)}
+        if len(keep) == 0:
+            empty = torch.empty((0, self.resample_num, 3), device=points.device)
+            out.update(input=empty, coarse=empty, surface=empty)
+            return out
+        rng = np.random.default_rng(seed)
+        choice = np.stack([resample_choice(int(cnt[f, k]), self.resample_num, rng) for f, k in keep])
+        h = torch.from_numpy(np.concatenate([keep.astype(np.int32).T.reshape(-1), choice.reshape(-1)])).pin_memory()
+        d = h.to(points.device, non_blocking=True)
+        O = len(keep)
+        obj_frame, obj_box, d_choice = d[:O], d[O:2 * O], d[2 * O:].view(O, self.resample_num)
+        inp = roi.resample_gather(points, counts, offsets, lists, obj_frame.contiguous(), obj_box.contiguous(),
+                                  d_choice.contiguous())
+        in_dict = {"input": inp}
+        if self.model_name == "VCN_CN":
+            in_dict["gt_boxes"] = boxes[obj_frame.long(), obj_box.long()].contiguous()
+        coarse = self.model(in_dict)["coarse"]
+        surface = get_partial_mesh_batch(inp, coarse, k=self.sel_k, surface_pts=self.resample_num)
+        out.update(input=inp, coarse=coarse, surface=surface, obj_frame_dev=obj_frame)
+        return out
+
+    @torch.no_grad()
+    def run(self, points, boxes, seed=0):
+        """complete() + dynamic voxelization of [frame points ++ completed surfaces] -> detector input."""
+        out = self.complete(points, boxes, seed)
+        F, P, _ = points.shape
+        fid = torch.arange(F, device=points.device, dtype=torch.float32).view(F, 1, 1).expand(F, P, 1)
+        rows = [torch.cat((fid, points), dim=2).view(F * P, 4)]
+        if out["surface"].shape[0] > 0:
+            O, S, _ = out["surface"].shape
+            ofid = out["obj_frame_dev"].to(torch.float32).view(O, 1, 1).expand(O, S, 1)
+            rows.append(torch.cat((ofid, out["surface"]), dim=2).view(O * S, 4))
+        vox_pts = torch.cat(rows, dim=0).contiguous()
+        coords, feats, nums = dynamic_voxelize(vox_pts, *self.voxel_cfg, sort=True)
+        out.update(voxel_points=vox_pts, voxel_coords=coords, voxel_features=feats, voxel_num_points=nums)
+        return out

@@ -1,0 +1,398 @@
+"""GPU parity tests: the CUDA path (through the python wrappers -> ctypes -> C-ABI) against the
+oracle on the same seeded inputs, against the committed goldens, against the reference's own
+kernels compiled for sm_100a (oracle/_ref, when present), and size-independent properties at
+BASELINE.json's full sizes.  Run with `pytest -m gpu`."""
+import ctypes
+
+import numpy as np
+import pytest
+import torch
+
+import oracle
+from seevcn_b200 import synth
+from seevcn_b200.pcdet.ops.roiaware_pool3d import roiaware_pool3d_utils as roi
+from seevcn_b200.pcdet.ops.pointnet2.pointnet2_batch import pointnet2_utils as pn2
+from seevcn_b200.pcdet.models.backbones_3d.vfe import MeanVFE, DynamicMeanVFE
+from seevcn_b200.pcdet.models.backbones_3d.vfe.dynamic_mean_vfe import dynamic_voxelize
+from seevcn_b200.pcdet.datasets.processor.data_processor import VoxelGeneratorWrapper
+from seevcn_b200.see.surface_completion.models.vcn.utils.sampling import get_partial_mesh_batch, get_largest_cluster_batch
+from seevcn_b200.see.surface_completion.models.vcn.models.build import MODELS
+
+pytestmark = pytest.mark.gpu
+
+
+def dev(a, cuda):
+    return torch.from_numpy(np.ascontiguousarray(a)).to(cuda)
+
+
+def _ptr(t):
+    return ctypes.c_void_p(t.data_ptr())
+
+
+# ------------------------------------------------------------------------ stage 1: crop --
+@pytest.mark.parametrize("shape", [(1, 20000, 10), (2, 4097, 3), (3, 1000, 300), (1, 5, 1)])
+def test_points_in_boxes_vs_oracle(cuda, shape):
+    B, P, T = shape
+    pts = np.stack([synth.make_frame(1000 + b, n_beams=16, n_az=P // 16 + 1, n_boxes=min(T, 40))[0][:P] for b in range(B)])
+    boxes = np.stack([synth.make_boxes(np.random.default_rng(50 + b), T, r_max=60 + T) for b in range(B)])
+    if T > 40:   # many boxes: draw them on top of the points so they are hit
+        sel = np.linspace(0, P - 1, T).astype(np.int64)
+        boxes[:, :, :3] = pts[:, sel] + 0.2
+    out = roi.points_in_boxes_gpu(dev(pts, cuda), dev(boxes, cuda)).cpu().numpy()
+    ref, slack = oracle.points_in_boxes_gpu(pts, boxes, return_slack=True)
+    decided = slack > 1e-4      # within 1e-4 m of an x/y face libm and CUDA cosf/sinf may round differently
+    np.testing.assert_array_equal(out[decided], ref[decided])
+    assert decided.mean() > 0.99
+    assert (out >= 0).sum() > 0 or T == 1
+
+
+def test_points_in_boxes_bit_exact_vs_reference_kernel(cuda):
+    """Full C2 size against the reference's own kernel compiled for sm_100a: every point, no tolerance."""
+    R = oracle.ref_kernels()
+    if R is None:
+        pytest.skip("oracle/_ref/libref_kernels.so not built (needs /root/reference at build time)")
+    pts, boxes = synth.make_stream(2)
+    boxes = np.concatenate([boxes, np.zeros((2, 6, 7), np.float32)], axis=1)   # zero-padded rows (dataset.py:193-198)
+    d_pts, d_box = dev(pts, cuda), dev(boxes, cuda)
+    out = roi.points_in_boxes_gpu(d_pts, d_box)
+    ref = torch.full_like(out, -1)
+    assert R.ref_points_in_boxes(2, boxes.shape[1], pts.shape[1], _ptr(d_box), _ptr(d_pts), _ptr(ref)) == 0
+    assert torch.equal(out, ref)
+    assert (out >= 0).sum().item() > 20000
+
+
+def test_points_in_boxes_cpu_surface_matches_reference_build(cuda, golden):
+    """host buffers in/out; bit-exact against the reference's x86 build (golden)"""
+    out = roi.points_in_boxes_cpu(golden["pib_points"], golden["pib_boxes"])
+    assert isinstance(out, np.ndarray) and out.dtype == np.int32
+    np.testing.assert_array_equal(out, oracle.points_in_boxes_cpu(golden["pib_points"], golden["pib_boxes"]))
+    if "pib_cpu_out" in golden:
+        ref = np.unpackbits(golden["pib_cpu_out"], axis=1)[:, : out.shape[1]].astype(np.int32)
+        np.testing.assert_array_equal(out, ref)
+
+
+def test_crop_compaction_lists(cuda):
+    pts, boxes = synth.make_stream(3, n_beams=32, n_az=1090, n_boxes=20)
+    idx, counts, offsets, lists = roi.crop_points_in_boxes(dev(pts, cuda), dev(boxes, cuda))
+    idx, counts, offsets, lists = (t.cpu().numpy() for t in (idx, counts, offsets, lists))
+    for b in range(3):
+        want = oracle.crop_lists(idx[b], 20)     # ascending point indices per box, like points[idx == k]
+        assert counts[b].tolist() == [len(w) for w in want]
+        assert offsets[b].tolist() == np.concatenate([[0], np.cumsum(counts[b])[:-1]]).tolist()
+        for k in range(20):
+            np.testing.assert_array_equal(lists[b, offsets[b, k]: offsets[b, k] + counts[b, k]], want[k])
+    assert counts.sum() > 1000
+
+
+def test_crop_empty_and_ragged(cuda):
+    pts = torch.zeros((1, 0, 3), device=cuda)
+    boxes = torch.zeros((1, 4, 7), device=cuda)
+    assert roi.points_in_boxes_gpu(pts, boxes).shape == (1, 0)
+    pts = torch.rand((2, 77, 3), device=cuda)
+    assert (roi.points_in_boxes_gpu(pts, torch.zeros((2, 0, 7), device=cuda)) == -1).all()
+
+
+def test_resample_gather(cuda):
+    pts, boxes = synth.make_stream(2, n_beams=32, n_az=1090, n_boxes=10)
+    d_pts = dev(pts, cuda)
+    idx, counts, offsets, lists = roi.crop_points_in_boxes(d_pts, dev(boxes, cuda))
+    cnt = counts.cpu().numpy()
+    objs = [(f, k) for f in range(2) for k in range(10) if cnt[f, k] >= 30]
+    rng = np.random.default_rng(0)
+    idx_h = idx.cpu().numpy()
+    want, choice = [], []
+    for f, k in objs:
+        r, c = oracle.resample_points(pts[f][idx_h[f] == k], 1024, rng)
+        want.append(r); choice.append(c)
+    got = roi.resample_gather(d_pts, counts, offsets, lists, dev(np.array([o[0] for o in objs], np.int32), cuda),
+                              dev(np.array([o[1] for o in objs], np.int32), cuda), dev(np.stack(choice), cuda))
+    np.testing.assert_array_equal(got.cpu().numpy(), np.stack(want))
+
+
+# ------------------------------------------------------------------------- stage 3: FPS --
+@pytest.mark.parametrize("shape", [(3, 1024, 256), (2, 1000, 64), (2, 16384, 1024), (2, 40, 40), (1, 7, 3), (1, 20000, 128)])
+def test_fps_vs_oracle_bit_exact(cuda, shape):
+    B, N, M = shape
+    _, dense, _ = synth.make_object_clouds(21, B, 64, N)
+    got = pn2.furthest_point_sample(dev(dense, cuda), M).cpu().numpy()
+    np.testing.assert_array_equal(got, oracle.furthest_point_sample(dense, M))
+
+
+def test_fps_duplicates_follow_reference_tie_rule(cuda):
+    part, _, _ = synth.make_object_clouds(3, 2, 200, 0)
+    tiled = np.tile(part, (1, 6, 1))[:, :1024]          # resampled clouds contain exact duplicates
+    got = pn2.furthest_point_sample(dev(tiled, cuda), 300).cpu().numpy()
+    np.testing.assert_array_equal(got, oracle.furthest_point_sample(tiled, 300))
+
+
+def test_fps_gather_group_vs_reference_kernels(cuda):
+    R = oracle.ref_kernels()
+    if R is None:
+        pytest.skip("oracle/_ref/libref_kernels.so not built")
+    _, dense, _ = synth.make_object_clouds(33, 4, 64, 16384)
+    xyz = dev(dense, cuda)
+    got = pn2.furthest_point_sample(xyz, 1024)
+    ref = torch.empty_like(got)
+    temp = torch.full((4, 16384), 1e10, device=cuda)
+    assert R.ref_fps(4, 16384, 1024, _ptr(xyz), _ptr(temp), _ptr(ref)) == 0
+    assert torch.equal(got, ref)
+    feats = xyz.transpose(1, 2).contiguous()
+    g = pn2.gather_operation(feats, got)
+    gref = torch.empty_like(g)
+    assert R.ref_gather(4, 3, 16384, 1024, _ptr(feats), _ptr(got), _ptr(gref)) == 0
+    assert torch.equal(g, gref)
+    _, nn_idx = pn2.knn(16, xyz[:, :2048].contiguous(), g.transpose(1, 2).contiguous())
+    feats2 = feats[:, :, :2048].contiguous()
+    grp = pn2.grouping_operation(feats2, nn_idx)
+    gref = torch.empty_like(grp)
+    assert R.ref_group(4, 3, 2048, 1024, 16, _ptr(feats2), _ptr(nn_idx), _ptr(gref)) == 0
+    assert torch.equal(grp, gref)
+
+
+def test_fps_ties_bit_exact_vs_reference_kernel(cuda):
+    """clouds full of exact duplicates (what ResamplePoints produces): the tie rule of the reference's
+    shared-memory tree must be reproduced, not just its arithmetic"""
+    R = oracle.ref_kernels()
+    if R is None:
+        pytest.skip("oracle/_ref/libref_kernels.so not built")
+    for n, m, src in ((1024, 400, 150), (1000, 300, 77), (4096, 512, 300), (48, 48, 5)):
+        part, _, _ = synth.make_object_clouds(90 + n, 3, src, 0)
+        tiled = np.tile(part, (1, n // src + 1, 1))[:, :n].copy()
+        xyz = dev(tiled, cuda)
+        got = pn2.furthest_point_sample(xyz, m)
+        ref = torch.empty_like(got)
+        temp = torch.full((3, n), 1e10, device=cuda)
+        assert R.ref_fps(3, n, m, _ptr(xyz), _ptr(temp), _ptr(ref)) == 0
+        assert torch.equal(got, ref), (n, m)
+        np.testing.assert_array_equal(got.cpu().numpy(), oracle.furthest_point_sample(tiled, m))
+
+
+def test_gather_group_vs_oracle(cuda):
+    rng = np.random.default_rng(5)
+    feats = rng.standard_normal((3, 7, 500)).astype(np.float32)
+    idx = rng.integers(0, 500, (3, 64)).astype(np.int32)
+    np.testing.assert_array_equal(pn2.gather_operation(dev(feats, cuda), dev(idx, cuda)).cpu().numpy(),
+                                  oracle.gather_operation(feats, idx))
+    idx3 = rng.integers(0, 500, (3, 33, 9)).astype(np.int32)
+    np.testing.assert_array_equal(pn2.grouping_operation(dev(feats, cuda), dev(idx3, cuda)).cpu().numpy(),
+                                  oracle.grouping_operation(feats, idx3))
+
+
+# ------------------------------------------------------------------------- stage 4: kNN --
+@pytest.mark.parametrize("cfg", [(2, 1024, 1024, 10), (2, 1024, 1024, 30), (1, 5000, 300, 16), (1, 64, 10, 64), (2, 16384, 256, 20)])
+def test_knn_vs_oracle(cuda, cfg):
+    B, R, Q, k = cfg
+    part, dense, _ = synth.make_object_clouds(41, B, Q, R)
+    gap = oracle.knn_gap(dense, part, k)
+    dist, idx = pn2.knn(k, dev(dense, cuda), dev(part, cuda))
+    rd, ri = oracle.knn(k, dense, part)
+    ok = gap > 1e-5                     # tie-free queries: k / k+1 gap above fp32 resolution
+    assert ok.mean() > 0.95
+    idx = idx.cpu().numpy()
+    # inside the k-set neighbours closer than fp32 resolution may swap places: compare as sets per query ...
+    np.testing.assert_array_equal(np.sort(idx[ok], axis=-1), np.sort(ri[ok], axis=-1))
+    # ... and exactly where consecutive distances are separated
+    sep = np.all(np.diff(rd, axis=-1) > 1e-5 * np.maximum(rd[..., 1:], 1e-6), axis=-1) & ok
+    np.testing.assert_array_equal(idx[sep], ri[sep])
+    np.testing.assert_allclose(dist.cpu().numpy(), rd, rtol=1e-5, atol=1e-6)
+
+
+def test_surface_select_vs_oracle_and_golden(cuda, golden):
+    for k in (10, 30):
+        out, cnt = get_partial_mesh_batch(dev(golden["vcn_input"], cuda), dev(golden["VCN_VC.coarse"], cuda), k=k,
+                                          return_count=True)
+        want, wcnt = oracle.get_partial_mesh_batch(golden["vcn_input"], golden["VCN_VC.coarse"], k=k)
+        np.testing.assert_array_equal(cnt.cpu().numpy(), wcnt)
+        np.testing.assert_array_equal(out.cpu().numpy(), want)
+        for b in range(3):   # same SET as the reference's cKDTree run (its row order is CPython set order)
+            np.testing.assert_array_equal(np.unique(out[b].cpu().numpy(), axis=0), np.unique(golden[f"surface_k{k}"][b], axis=0))
+
+
+def test_surface_select_with_duplicate_and_padded_objects(cuda):
+    part, dense, _ = synth.make_object_clouds(43, 3, 150, 1024)
+    tiled = np.tile(part, (1, 7, 1))[:, :1024]
+    tiled[2] = 0   # zero-padded object (models/VCN.py:58)
+    out, cnt = get_partial_mesh_batch(dev(tiled, cuda), dev(dense, cuda), k=20, return_count=True)
+    want, wcnt = oracle.get_partial_mesh_batch(tiled, dense, k=20)
+    np.testing.assert_array_equal(cnt.cpu().numpy(), wcnt)
+    np.testing.assert_array_equal(out.cpu().numpy(), want)
+    assert wcnt[2] == 20
+
+
+def test_largest_cluster_vs_oracle(cuda):
+    _, dense, _ = synth.make_object_clouds(51, 4, 64, 1024)
+    pc = dense.copy()
+    pc[:, 600:1000] += 30.0                                             # second, smaller blob
+    pc[:, 1000:] = 99.0 + 5.0 * np.arange(24, dtype=np.float32)[None, :, None]   # isolated points = noise
+    pc[3, :512] = pc[3, 512:]                                            # exact duplicates (tiled surfaces)
+    for eps, mp in ((0.4, 2), (0.2, 2), (0.3, 1)):
+        out, cnt = get_largest_cluster_batch(dev(pc, cuda), eps=eps, min_points=mp, total_pts=1024, return_count=True)
+        want, wcnt = oracle.get_largest_cluster_batch(pc, eps=eps, min_points=mp, total_pts=1024)
+        np.testing.assert_array_equal(cnt.cpu().numpy(), wcnt)
+        np.testing.assert_array_equal(out.cpu().numpy(), want)
+    assert wcnt.max() < 1024 and wcnt.min() >= 1
+
+
+def test_vcn_inference_wrapper(cuda, golden):
+    """host numpy in / out through the reference-shaped VCN.inference"""
+    from seevcn_b200.see.surface_completion.models.VCN import VCN
+    cfg = {"MODEL": "VCN_VC", "NORM_WITH_GT": False, "SEL_K_NEAREST": 10, "CLUSTER_EPS": 0.3, "BATCH_SIZE_LIMIT": 32}
+    sd = oracle.make_state_dict("VCN_VC", seed=0)
+    vcn = VCN(cfg, gpu_id=0, state_dict=sd, precision="fp32")
+    clouds = [golden["vcn_input"][0][:300], golden["vcn_input"][1], golden["vcn_input"][2][:57]]
+    ret = vcn.inference(clouds, batch_size_limit=32, k=10, eps=0.3, rng=np.random.default_rng(4))
+    assert ret["input"].shape == (3, 1024, 3) and ret["coarse"].shape == (3, 1024, 3)
+    want = oracle.vcn_forward_ref(sd, ret["input"], None, "VCN_VC")["coarse"].numpy()
+    np.testing.assert_allclose(ret["coarse"], want, atol=5e-4)
+    surf, _ = oracle.get_partial_mesh_batch(ret["input"], ret["coarse"], k=10)
+    np.testing.assert_array_equal(ret["surface"], surf)
+    clus, _ = oracle.get_largest_cluster_batch(surf, eps=0.3, min_points=2, total_pts=1024)
+    np.testing.assert_array_equal(ret["clustered"], clus)
+
+
+# --------------------------------------------------------------------- stages 2+5: VCN --
+def rel_chamfer(a, b, inp):
+    """Chamfer(a, b) relative to the Chamfer scale of the cloud (Chamfer(b, centroid))"""
+    cd = oracle.chamfer_l2(a, b)
+    scale = ((b - b.mean(axis=1, keepdims=True)) ** 2).sum(-1).mean(-1)
+    return cd / scale
+
+
+@pytest.mark.parametrize("cfg", [(256, 64, 128, 256, 0), (1024, 128, 1024, 1024, 2), (3000, 512, 512, 1000, 1),
+                                 (37, 1024, 3072, 1, 0), (2048 + 77, 256, 256, 2048 + 77, 1), (5, 100, 130, 2, 0)])
+def test_tc_linear_layer_bf16(cuda, cfg):
+    """the tcgen05 GEMM on its own against a float64 product of the bf16-rounded operands"""
+    from seevcn_b200 import _abi
+    rows, cin, cout, rpo, act = cfg
+    g = torch.Generator().manual_seed(rows + cin)
+    X = torch.randn(rows, cin, generator=g); W = torch.randn(cout, cin, generator=g) / cin ** 0.5
+    bias = torch.randn(cout, generator=g)
+    nobj = (rows + rpo - 1) // rpo
+    ob = torch.randn(nobj, cout, generator=g)
+    L = _abi.lib()
+    ws = torch.empty(L.seevcn_linear_bf16_workspace_bytes(rows, cin, cout), dtype=torch.uint8, device=cuda)
+    Y = torch.empty(rows, cout, device=cuda)
+    cm = torch.full((nobj, cout), float("-inf"), device=cuda)
+    dX, dW, db, dob = X.to(cuda), W.to(cuda), bias.to(cuda), ob.to(cuda)
+    _abi.check(L.seevcn_linear_bf16(rows, cin, cout, _abi.ptr(dX), _abi.ptr(dW), _abi.ptr(db), _abi.ptr(dob), rpo, act,
+                                    _abi.ptr(Y), _abi.ptr(cm), _abi.ptr(ws), ws.numel(), _abi.stream()))
+    torch.cuda.synchronize()
+    ref = X.bfloat16().double() @ W.bfloat16().double().t() + bias.double() + ob.double().repeat_interleave(rpo, 0)[:rows]
+    ref = torch.relu(ref) if act == 1 else torch.where(ref > 0, ref, 0.01 * ref) if act == 2 else ref
+    np.testing.assert_allclose(Y.cpu().double().numpy(), ref.numpy(), rtol=1e-4, atol=1e-4)
+    want_max = torch.stack([ref[o * rpo: min((o + 1) * rpo, rows)].max(0)[0] for o in range(nobj)])
+    np.testing.assert_allclose(cm.cpu().double().numpy(), want_max.numpy(), rtol=1e-4, atol=1e-4)
+
+
+@pytest.mark.parametrize("name", ["VCN_VC", "VCN_CN"])
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_vcn_forward_vs_golden(cuda, golden, name, precision):
+    sd = oracle.make_state_dict(name, seed=0)
+    model = MODELS.build({"NAME": name}, precision=precision)
+    model.load_state_dict(sd)
+    model.to(cuda).eval()
+    ret = model({"input": dev(golden["vcn_input"], cuda), "gt_boxes": dev(golden["vcn_gt_boxes"], cuda)})
+    coarse = ret["coarse"].cpu().numpy()
+    want = golden[f"{name}.coarse"]
+    rc = rel_chamfer(coarse, want, golden["vcn_input"])
+    assert (rc < 1e-3).all(), rc                       # north_star tolerance: 1e-3 relative Chamfer
+    if precision == "fp32":
+        np.testing.assert_allclose(coarse, want, rtol=0, atol=5e-4)
+        if name == "VCN_VC":
+            np.testing.assert_allclose(ret["reg_rot"].cpu().numpy(), golden["VCN_VC.reg_rot"], atol=1e-4)
+            np.testing.assert_allclose(ret["reg_centre"].cpu().numpy(), golden["VCN_VC.reg_centre"], atol=1e-4)
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_vcn_forward_many_objects_vs_oracle(cuda, precision):
+    """crosses the internal object-chunk boundary; ragged last chunk"""
+    part, _, _ = synth.make_object_clouds(77, 37, 1024, 0)
+    sd = oracle.make_state_dict("VCN_VC", seed=5)
+    model = MODELS.build({"NAME": "VCN_VC"}, precision=precision)
+    model.load_state_dict(sd)
+    model.to(cuda).eval()
+    got = model({"input": dev(part, cuda)})["coarse"].cpu().numpy()
+    want = oracle.vcn_forward_ref(sd, part, None, "VCN_VC")["coarse"].numpy()
+    assert (rel_chamfer(got, want, part) < 1e-3).all()
+
+
+# ------------------------------------------------------------------ stage 6: voxelization --
+WAYMO = ([-75.2, -75.2, -2, 75.2, 75.2, 4], [0.1, 0.1, 0.15], [1504, 1504, 40])
+
+
+def test_mean_vfe_vs_golden(cuda, golden):
+    vfe = MeanVFE(model_cfg={}, num_point_features=3)
+    out = vfe({"voxels": dev(golden["meanvfe_voxels"], cuda), "voxel_num_points": dev(golden["meanvfe_num"], cuda)})
+    np.testing.assert_allclose(out["voxel_features"].cpu().numpy(), golden["meanvfe_out"], rtol=1e-6, atol=1e-6)
+    assert vfe.get_output_feature_dim() == 3
+
+
+@pytest.mark.parametrize("nframes", [1, 3])
+def test_dynamic_voxelize_vs_oracle(cuda, nframes):
+    pts, _ = synth.make_stream(nframes)
+    points = np.concatenate([np.concatenate([np.full((pts.shape[1], 1), b, np.float32), pts[b]], axis=1) for b in range(nframes)])
+    want_c, want_f, want_n = oracle.dynamic_voxelize(points, *WAYMO)
+    vfe = DynamicMeanVFE({}, 3, WAYMO[1], WAYMO[2], WAYMO[0])
+    out = vfe({"points": dev(points, cuda), "batch_size": nframes})
+    np.testing.assert_array_equal(out["voxel_coords"].cpu().numpy(), want_c)          # bit-exact, reference order
+    np.testing.assert_array_equal(out["voxel_num_points"].cpu().numpy(), want_n)
+    np.testing.assert_allclose(out["voxel_features"].cpu().numpy(), want_f, rtol=1e-5, atol=1e-5)
+    assert len(want_c) > 50000
+    # unsorted (hash order) output is the same set of rows
+    c, f, n = dynamic_voxelize(dev(points, cuda), *WAYMO, sort=False)
+    order = np.lexsort(c.cpu().numpy()[:, [1, 2, 3, 0]].T)   # lexsort: last key is primary -> b, x, y, z (coords are b,z,y,x)
+    np.testing.assert_array_equal(c.cpu().numpy()[order], want_c)
+    np.testing.assert_array_equal(n.cpu().numpy()[order], want_n)
+
+
+def test_dynamic_voxelize_extra_features_and_overflow_batch(cuda):
+    rng = np.random.default_rng(9)
+    n = 20000
+    pts = np.concatenate([rng.integers(20, 30, (n, 1)).astype(np.float32), rng.uniform(-80, 80, (n, 2)).astype(np.float32),
+                          rng.uniform(-3, 5, (n, 1)).astype(np.float32), rng.standard_normal((n, 2)).astype(np.float32)], axis=1)
+    want_c, want_f, want_n = oracle.dynamic_voxelize(pts, *WAYMO)   # batch >= 24 overflows the reference's int32 key
+    c, f, cnt = dynamic_voxelize(dev(pts, cuda), *WAYMO)
+    np.testing.assert_array_equal(c.cpu().numpy(), want_c)
+    np.testing.assert_array_equal(cnt.cpu().numpy(), want_n)
+    np.testing.assert_allclose(f.cpu().numpy(), want_f, rtol=1e-5, atol=1e-5)
+
+
+def test_dynamic_voxelize_properties_full_size(cuda):
+    """C5-size: counts sum to the in-range points, means lie inside their voxel, voxels are unique."""
+    pts, _ = synth.make_stream(8)
+    points = np.concatenate([np.concatenate([np.full((pts.shape[1], 1), b, np.float32), pts[b]], axis=1) for b in range(8)])
+    c, f, n = dynamic_voxelize(dev(points, cuda), *WAYMO, sort=False)
+    c, f, n = c.cpu().numpy(), f.cpu().numpy(), n.cpu().numpy()
+    lo, vs, gs = np.array(WAYMO[0][:3], np.float32), np.array(WAYMO[1], np.float32), np.array(WAYMO[2])
+    pc = np.floor((points[:, 1:4] - lo) / vs)
+    inside = ((pc >= 0) & (pc < gs)).all(axis=1)
+    assert n.sum() == inside.sum()
+    assert len(np.unique(c, axis=0)) == len(c)
+    vox_lo = lo + c[:, [3, 2, 1]] * vs
+    assert ((f >= vox_lo - 1e-3) & (f <= vox_lo + vs + 1e-3)).all()
+
+
+def test_hard_voxelize_vs_oracle(cuda):
+    pts, _ = synth.make_frame(1002)
+    pts = pts[np.random.default_rng(1).permutation(len(pts))]     # shuffled like data_processor.py:93-103
+    for max_voxels in (90000, 5000):
+        gen = VoxelGeneratorWrapper(WAYMO[1], WAYMO[0], 3, 5, max_voxels)
+        assert gen.grid_size == WAYMO[2]
+        v, c, n = gen.generate(pts)
+        wv, wc, wn = oracle.hard_voxelize(pts, WAYMO[0], WAYMO[1], WAYMO[2], 5, max_voxels)
+        np.testing.assert_array_equal(c, wc)
+        np.testing.assert_array_equal(n, wn)
+        np.testing.assert_array_equal(v, wv)
+        assert len(c) == min(max_voxels, len(c)) and len(c) > 1000
+
+
+def test_chamfer_kernel(cuda):
+    from seevcn_b200 import _abi
+    rng = np.random.default_rng(2)
+    a = rng.standard_normal((2, 700, 3)).astype(np.float32)
+    b = rng.standard_normal((2, 1300, 3)).astype(np.float32)
+    da, db = dev(a, cuda), dev(b, cuda)
+    d1 = torch.empty((2, 700), device=cuda); d2 = torch.empty((2, 1300), device=cuda)
+    _abi.check(_abi.lib().seevcn_chamfer(2, 700, 1300, _abi.ptr(da), _abi.ptr(db), _abi.ptr(d1), _abi.ptr(d2), _abi.stream()))
+    got = (d1.mean(1) + d2.mean(1)).cpu().numpy()
+    np.testing.assert_allclose(got, oracle.chamfer_l2(a, b), rtol=1e-4)
