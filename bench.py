@@ -4,7 +4,7 @@
   python bench.py [--gpus N] [--steps K] [--warmup W] [--frames F] [--impl ours|reference]
 
 A step = one pass of the hot path (crop -> resample -> VCN forward -> kNN surface select ->
-dynamic voxelization) over a batch of F synthetic Waymo-like frames (BASELINE.json configs[1]:
+largest-cluster filter -> dynamic voxelization) over a batch of F synthetic Waymo-like frames (BASELINE.json configs[1]:
 64 beams x 2812 azimuth steps = 180k pts, 50 car boxes, 1024 pts/object) per GPU.  Frames shard
 across ranks with no collective on the data path; one all-gather-v of the completed clouds per
 step stands for "collect for the detector" when N > 1 (weak scaling: F frames per GPU).
@@ -28,7 +28,8 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 METRIC = "completed objects/sec"
-SEL_K = 10               # SURFACE_COMPLETION.VCN.SEL_K_NEAREST (cfgs/WAY-GT_VCN-VC.yaml)
+SEL_K = 20               # SURFACE_COMPLETION.VCN.SEL_K_NEAREST (see/surface_completion/cfgs/WAY-GT_VCN-VC.yaml:13)
+CLUSTER_EPS = 0.3        # SURFACE_COMPLETION.VCN.CLUSTER_EPS   (WAY-GT_VCN-VC.yaml:14)
 RESAMPLE = 1024
 FLOP_PER_OBJ = 2.0 * (959040 * 1024 + 5771776)   # VCN_VC, N = 1024 -> 1.976 GFLOP
 
@@ -98,6 +99,7 @@ def cpu_path_once(pts, boxes, sd, threads):
         with torch.no_grad():
             coarse = oracle.vcn_forward_ref(sd, inp, None, "VCN_VC")["coarse"].numpy()
         surf, _ = oracle.get_partial_mesh_batch(inp, coarse, k=SEL_K)
+        surf, _ = oracle.get_largest_cluster_batch(surf, eps=CLUSTER_EPS, min_points=2, total_pts=RESAMPLE)
         rows += [np.concatenate([np.full((RESAMPLE, 1), fid[o], np.float32), surf[o]], axis=1) for o in range(n_obj)]
     vox = np.concatenate(rows).astype(np.float32)
     from seevcn_b200.pipeline import WAYMO_VOXEL_CFG
@@ -170,7 +172,7 @@ def run_ours(args):
         if isinstance(m, torch.nn.BatchNorm1d):
             m.running_mean.normal_(0, 0.1); m.running_var.uniform_(0.5, 1.5)
     sd = ref_model.state_dict()
-    pipe = CompletionPipeline("VCN_VC", sd, dev, sel_k=SEL_K, precision=args.precision)
+    pipe = CompletionPipeline("VCN_VC", sd, dev, sel_k=SEL_K, precision=args.precision, cluster_eps=CLUSTER_EPS)
 
     F = args.frames
     pts_h, boxes_h = make_inputs(F, 1000 + rank * F)         # rank r owns frames [r*F, (r+1)*F)
@@ -182,14 +184,14 @@ def run_ours(args):
     def step_resident():
         out = pipe.run(pts_d, boxes_d, seed=0)
         if world > 1:
-            sdist.all_gather_v(out["surface"])
+            sdist.all_gather_v(out["clustered"])
         return out
 
     def step_e2e():
         p = pts_pin.to(dev, non_blocking=True)
         b = boxes_pin.to(dev, non_blocking=True)
         out = pipe.run(p, b, seed=0)
-        res = [out["surface"].cpu(), out["voxel_coords"].cpu(), out["voxel_features"].cpu(), out["voxel_num_points"].cpu()]
+        res = [out["clustered"].cpu(), out["voxel_coords"].cpu(), out["voxel_features"].cpu(), out["voxel_num_points"].cpu()]
         return out, res
 
     def timed(fn, steps, warmup):
@@ -260,7 +262,7 @@ def run_ours(args):
             "ms_per_step": ms_res / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "bf16" if args.precision == "bf16" else "f32", "data": "synthetic",
             "config": {"workload": "C2: synthetic Waymo-like 64-beam frame (180k pts, 50 car boxes, 1024 pts/object), random-init VCN_VC",
-                       "frames_per_step_per_gpu": F, "objects_per_step": int(n_obj.item()), "sel_k": SEL_K,
+                       "frames_per_step_per_gpu": F, "objects_per_step": int(n_obj.item()), "sel_k": SEL_K, "cluster_eps": CLUSTER_EPS,
                        "l2": "flushed (256 MB write) between timed iterations", "parallelism": f"frame-sharded x{world}"},
             "voxelized_mpts_per_sec": n_vox_pts.item() * steps / (ms_res / 1e3) / 1e6, "voxels_per_step_rank0": int(n_voxels),
             "e2e": {"value": e2e, "unit": "objects/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),

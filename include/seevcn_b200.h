@@ -93,6 +93,16 @@ int seevcn_resample_gather(int num_obj, int n_points, int boxes_num, int pts_num
                            const int* box_points, const int* obj_frame, const int* obj_box,
                            const int* choice, float* out, seevcn_stream_t stream);
 
+/* Same draw made on the device: choice[o,j] = perm_o(j), the first n_points entries of a pseudo-random
+ * permutation of the tiled list (4-round Feistel network + cycle walking, keyed by seed and the object's
+ * frame*T+box), so no host RNG, no `choice` upload.  seevcn_resample_perm() evaluates the same permutation
+ * on the host (tests). */
+int seevcn_resample_gather_rng(int num_obj, int n_points, int boxes_num, int pts_num, unsigned seed,
+                               const float* pts, const int* box_counts, const int* box_offsets,
+                               const int* box_points, const int* obj_frame, const int* obj_box,
+                               float* out, seevcn_stream_t stream);
+unsigned seevcn_resample_perm(unsigned j, unsigned n, unsigned seed, unsigned frame_box);
+
 /* ---------------------------------------------------- stage 3: furthest point sampling */
 
 /* ref: void farthest_point_sampling_kernel_launcher(int b, int n, int m,
@@ -224,11 +234,13 @@ int seevcn_mean_vfe(int num_voxels, int max_points, int num_features, const floa
  * Row order is the hash-table order unless sorted != 0, in which case rows are ordered by
  * the reference's merge key b*XYZ + x*YZ + y*Z + z like torch.unique (64-bit, so batch >= 24
  * on the Waymo grid does not overflow as the reference's int32 key does).
+ * batch_hint: upper bound on the batch indices + 1 (batch_dict['batch_size']); only narrows the radix sort
+ * to the key bits in use, <= 0 means unknown.
  * workspace: seevcn_dynamic_voxelize_workspace_bytes(N, C, max_voxels). */
 size_t seevcn_dynamic_voxelize_workspace_bytes(int num_points, int num_features, int max_voxels);
 int seevcn_dynamic_voxelize(int num_points, int num_features, const float* points,
                             const float* pc_range, const float* voxel_size, const int* grid_size,
-                            int max_voxels, int sorted,
+                            int max_voxels, int sorted, int batch_hint,
                             int* voxel_coords, float* voxel_features, int* voxel_counts,
                             int* num_voxels, void* workspace, size_t workspace_bytes,
                             seevcn_stream_t stream);

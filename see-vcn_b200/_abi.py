@@ -39,6 +39,8 @@ SIGNATURES = {
     "seevcn_crop_workspace_bytes": (c_size_t, [I, I, I]),
     "seevcn_crop_points_in_boxes": (I, [I, I, I, P, P, P, P, P, P, P, c_size_t, P]),
     "seevcn_resample_gather": (I, [I, I, I, I, P, P, P, P, P, P, P, P, P]),
+    "seevcn_resample_gather_rng": (I, [I, I, I, I, ctypes.c_uint, P, P, P, P, P, P, P, P]),
+    "seevcn_resample_perm": (ctypes.c_uint, [ctypes.c_uint] * 4),
     "seevcn_furthest_point_sampling": (I, [I, I, I, P, P, P, P]),
     "seevcn_gather_points": (I, [I, I, I, I, P, P, P, P]),
     "seevcn_group_points": (I, [I, I, I, I, I, P, P, P, P]),
@@ -54,7 +56,7 @@ SIGNATURES = {
     "seevcn_mean_vfe": (I, [I, I, I, P, P, P, P]),
     "seevcn_dynamic_voxelize_workspace_bytes": (c_size_t, [I, I, I]),
     "seevcn_dynamic_voxelize": (I, [I, I, P, POINTER(ctypes.c_float), POINTER(ctypes.c_float), POINTER(c_int),
-                                    I, I, P, P, P, P, P, c_size_t, P]),
+                                    I, I, I, P, P, P, P, P, c_size_t, P]),
     "seevcn_hard_voxelize_workspace_bytes": (c_size_t, [I, I, I]),
     "seevcn_hard_voxelize": (I, [I, I, P, POINTER(ctypes.c_float), POINTER(ctypes.c_float), POINTER(c_int),
                                  I, I, P, P, P, P, P, c_size_t, P]),

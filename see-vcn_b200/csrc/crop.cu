@@ -194,26 +194,48 @@ points_in_boxes_dense_kernel(int boxes_num, int pts_num, const float* __restrict
 }
 
 // Compaction pass B: per frame, exclusive scan of tile_counts over tiles (in place) and of
-// the per-box totals over boxes.  grid B, block 256.
-__global__ void crop_scan_kernel(int boxes_num, int ntiles, int* __restrict__ tile_counts,
-                                 int* __restrict__ box_counts, int* __restrict__ box_offsets) {
+// the per-box totals over boxes.  grid B, block 256: one warp per box, lanes stride over tiles with a
+// shuffle scan; then warp 0 scans the box totals.
+__device__ __forceinline__ int warp_excl_scan(int v, int& total) {
+    int inc = v;
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) {
+        const int t = __shfl_up_sync(0xffffffffu, inc, off);
+        if (lane_id() >= off) inc += t;
+    }
+    total = __shfl_sync(0xffffffffu, inc, 31);
+    return inc - v;
+}
+
+__global__ void __launch_bounds__(256)
+crop_scan_kernel(int boxes_num, int ntiles, int* __restrict__ tile_counts,
+                 int* __restrict__ box_counts, int* __restrict__ box_offsets) {
     extern __shared__ int s_tot[];   // boxes_num
     const int b = blockIdx.x;
     int* tc = tile_counts + (size_t)b * ntiles * boxes_num;
-    for (int k = threadIdx.x; k < boxes_num; k += blockDim.x) {
+    for (int k = warp_id(); k < boxes_num; k += 8) {
         int run = 0;
-        for (int t = 0; t < ntiles; ++t) {
-            const int c = tc[(size_t)t * boxes_num + k];
-            tc[(size_t)t * boxes_num + k] = run;
-            run += c;
+        for (int t0 = 0; t0 < ntiles; t0 += 32) {
+            const int t = t0 + lane_id();
+            const int c = t < ntiles ? tc[(size_t)t * boxes_num + k] : 0;
+            int tot;
+            const int ex = warp_excl_scan(c, tot);
+            if (t < ntiles) tc[(size_t)t * boxes_num + k] = run + ex;
+            run += tot;
         }
-        s_tot[k] = run;
-        box_counts[(size_t)b * boxes_num + k] = run;
+        if (lane_id() == 0) { s_tot[k] = run; box_counts[(size_t)b * boxes_num + k] = run; }
     }
     __syncthreads();
-    if (threadIdx.x == 0) {   // boxes_num <= 1024: a serial scan is a few hundred ns
+    if (warp_id() == 0) {
         int run = 0;
-        for (int k = 0; k < boxes_num; ++k) { box_offsets[(size_t)b * boxes_num + k] = run; run += s_tot[k]; }
+        for (int k0 = 0; k0 < boxes_num; k0 += 32) {
+            const int k = k0 + lane_id();
+            const int c = k < boxes_num ? s_tot[k] : 0;
+            int tot;
+            const int ex = warp_excl_scan(c, tot);
+            if (k < boxes_num) box_offsets[(size_t)b * boxes_num + k] = run + ex;
+            run += tot;
+        }
     }
 }
 
@@ -294,7 +316,77 @@ __global__ void resample_gather_kernel(int num_obj, int n_points, int boxes_num,
     d[0] = x; d[1] = y; d[2] = z;
 }
 
+// Pseudo-random permutation of [0, n) evaluated point-wise: a 4-round Feistel network on
+// m = ceil(log2 n) bits (made even) with cycle walking.  perm(j) for j = 0..n_points-1 are the first
+// n_points entries of one permutation — exactly what ResamplePoints draws
+// (np.random.permutation(len)[:n], data_transforms.py:258-260), without a host RNG or a sort.
+__host__ __device__ inline unsigned mix32(unsigned x) {
+    x ^= x >> 16; x *= 0x7feb352du; x ^= x >> 15; x *= 0x846ca68bu; x ^= x >> 16;
+    return x;
+}
+__host__ __device__ inline unsigned feistel_perm(unsigned j, unsigned n, unsigned key) {
+    unsigned bits = 2;
+    while ((1u << bits) < n) bits += 2;            // even number of bits >= log2 n
+    const unsigned half = bits >> 1, hmask = (1u << half) - 1u;
+    unsigned v = j;
+    do {
+        unsigned l = v >> half, r = v & hmask;
+#pragma unroll
+        for (unsigned round = 0; round < 4; ++round) {
+            const unsigned f = mix32(r ^ (key + 0x9e3779b9u * (round + 1))) & hmask;
+            const unsigned nl = r; r = l ^ f; l = nl;
+        }
+        v = (l << half) | r;
+    } while (v >= n);                               // cycle walking keeps it a bijection on [0, n)
+    return v;
+}
+
+__global__ void resample_gather_rng_kernel(int num_obj, int n_points, int boxes_num, int pts_num, unsigned seed,
+                                           const float* __restrict__ pts, const int* __restrict__ box_counts,
+                                           const int* __restrict__ box_offsets, const int* __restrict__ box_points,
+                                           const int* __restrict__ obj_frame, const int* __restrict__ obj_box,
+                                           float* __restrict__ out) {
+    const int o = blockIdx.y;
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n_points) return;
+    const int f = obj_frame[o], k = obj_box[o];
+    const int cnt = box_counts[(size_t)f * boxes_num + k];
+    float x = 0.f, y = 0.f, z = 0.f;
+    if (cnt > 0) {
+        const int off = box_offsets[(size_t)f * boxes_num + k];
+        const unsigned reps = (unsigned)((n_points + cnt - 1) / cnt);
+        const unsigned c = feistel_perm((unsigned)j, reps * (unsigned)cnt, mix32(seed ^ mix32((unsigned)(f * boxes_num + k))));
+        const int p = box_points[(size_t)f * pts_num + off + (int)(c % (unsigned)cnt)];
+        const float* s = pts + ((size_t)f * pts_num + p) * 3;
+        x = s[0]; y = s[1]; z = s[2];
+    }
+    float* d = out + ((size_t)o * n_points + j) * 3;
+    d[0] = x; d[1] = y; d[2] = z;
+}
+
 }  // namespace
+
+// Host-visible copy of the permutation so tests / the oracle can reproduce the draw.
+extern "C" unsigned seevcn_resample_perm(unsigned j, unsigned n, unsigned seed, unsigned frame_box) {
+    return feistel_perm(j, n, mix32(seed ^ mix32(frame_box)));
+}
+
+extern "C" int seevcn_resample_gather_rng(int num_obj, int n_points, int boxes_num, int pts_num, unsigned seed,
+                                          const float* pts, const int* box_counts, const int* box_offsets,
+                                          const int* box_points, const int* obj_frame, const int* obj_box, float* out,
+                                          seevcn_stream_t stream) {
+    SEEVCN_REQUIRE(num_obj >= 0 && n_points >= 0, "resample_gather_rng: negative size");
+    if (num_obj == 0 || n_points == 0) return SEEVCN_OK;
+    SEEVCN_REQUIRE(num_obj <= 65535, "resample_gather_rng: num_obj > 65535 per call");
+    SEEVCN_REQUIRE(pts && box_counts && box_offsets && box_points && obj_frame && obj_box && out,
+                   "resample_gather_rng: null pointer");
+    dim3 grid(div_up(n_points, 256), num_obj);
+    resample_gather_rng_kernel<<<grid, 256, 0, as_stream(stream)>>>(num_obj, n_points, boxes_num, pts_num, seed, pts,
+                                                                    box_counts, box_offsets, box_points, obj_frame,
+                                                                    obj_box, out);
+    SEEVCN_LAUNCH_CHECK();
+    return SEEVCN_OK;
+}
 
 extern "C" int seevcn_points_in_boxes(int batch_size, int boxes_num, int pts_num, const float* boxes,
                                       const float* pts, int* box_idx_of_points, seevcn_stream_t stream) {

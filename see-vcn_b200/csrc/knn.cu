@@ -4,96 +4,123 @@
 // see/surface_completion/models/vcn/utils/sampling.py:8-41 (partial_with_KDTree) and its
 // torch twin :43-67 (dist.topk(k, largest=False)); batch driver :69-80.
 //
-// Brute force on chip: reference points are staged in shared memory (SoA), every thread
-// owns one query and keeps its k best (ascending, ties -> lower index first) in registers.
-// The surface-select kernel runs one CTA per object, de-duplicates the queries with a
-// shared-memory hash set (the union of neighbour sets is unchanged by duplicate queries —
-// the reference's np.unique(partial) at sampling.py:31 is the same optimisation), marks the
-// union in a bitmask, and emits complete[sorted(S)] cyclically — no host round trip.
+// Brute force on chip.  Reference points are staged in shared memory as float4; every thread owns one
+// query.  The k best of a thread live in shared memory as 64-bit keys (distance bits << 32 | index:
+// non-negative float bits order like unsigned ints, so one u64 compare orders by distance and then by
+// LOWER index, the tie order of a stable scan) in an UNSORTED list with a tracked maximum ("replace the
+// max").  To keep warps convergent, candidates that beat the current k-th distance are first appended
+// to a small per-thread buffer; the warp merges buffers into lists together, when any lane's buffer
+// runs full.  The fast path per (query, reference) pair is 1 LDS.128 + 6 FP32 ops + compare.
+//
+// The surface-select kernel runs one CTA per object: it de-duplicates the queries with a shared-memory
+// hash set (duplicate queries cannot change a union — the reference's np.unique(partial) at
+// sampling.py:31 is the same optimisation; resampled clouds are mostly duplicates), scans only the
+// unique ones, marks the union of neighbour sets in a bitmask and emits complete[sorted(S)] cyclically.
 #include "common.cuh"
 
 namespace {
 
-template <int KMAX>
-struct TopK {
-    float d[KMAX];
-    int i[KMAX];
-    // The k live entries occupy slots [KMAX-k, KMAX) so that every register index is static;
-    // slots below hold -inf sentinels that nothing can displace.
-    __device__ __forceinline__ void init(int k) {
-#pragma unroll
-        for (int j = 0; j < KMAX; ++j) {
-            d[j] = __int_as_float(j < KMAX - k ? 0xff800000 : 0x7f800000);
-            i[j] = -1;
-        }
-    }
-    // keeps ascending order; an equal distance goes AFTER existing entries (lower index first)
-    __device__ __forceinline__ void push(float cd, int ci) {
-        if (cd < d[KMAX - 1]) {
-#pragma unroll
-            for (int j = 0; j < KMAX; ++j) {
-                if (cd < d[j]) {
-                    const float td = d[j]; d[j] = cd; cd = td;
-                    const int ti = i[j]; i[j] = ci; ci = ti;
-                }
-            }
-        }
-    }
-};
+typedef unsigned long long u64;
+constexpr u64 kInfKey = ~0ull;
+constexpr int kBuf = 16;   // per-thread candidate buffer (flushed when more than 8 are pending)
 
-__device__ __forceinline__ float sqdist(float qx, float qy, float qz, float rx, float ry, float rz) {
-    const float dx = __fsub_rn(rx, qx), dy = __fsub_rn(ry, qy), dz = __fsub_rn(rz, qz);
+__device__ __forceinline__ float sqdist(float qx, float qy, float qz, float4 r) {
+    const float dx = __fsub_rn(r.x, qx), dy = __fsub_rn(r.y, qy), dz = __fsub_rn(r.z, qz);
     return __fmaf_rn(dz, dz, __fmaf_rn(dy, dy, __fmul_rn(dx, dx)));
 }
 
-template <int KMAX>
-__device__ __forceinline__ void scan_refs(TopK<KMAX>& tk, float qx, float qy, float qz,
-                                          const float* sx, const float* sy, const float* sz, int cnt, int base) {
-    for (int r = 0; r < cnt; ++r) {
-        const float d = sqdist(qx, qy, qz, sx[r], sy[r], sz[r]);
-        tk.push(d, base + r);
+// Per-thread top-k state.  list / buf are this thread's columns of [slot][T] arrays in shared memory.
+template <int T>
+struct TopK {
+    u64* list; u64* buf;
+    u64 thr; float thr_f; int maxpos, nbuf, k;
+    __device__ __forceinline__ void init(u64* list_, u64* buf_, int k_) {
+        list = list_; buf = buf_; k = k_;
+        for (int j = 0; j < k; ++j) list[j * T] = kInfKey;
+        thr = kInfKey; thr_f = __int_as_float(0x7f800000); maxpos = 0; nbuf = 0;
     }
+    __device__ __forceinline__ void offer(float d, int idx) {
+        if (d < thr_f) { buf[nbuf * T] = ((u64)__float_as_uint(d) << 32) | (unsigned)idx; ++nbuf; }
+    }
+    __device__ __forceinline__ void flush() {
+        for (int e = 0; e < nbuf; ++e) {
+            const u64 key = buf[e * T];
+            if (key < thr) {
+                list[maxpos * T] = key;
+                u64 m = 0; int mp = 0;
+                for (int j = 0; j < k; ++j) { const u64 v = list[j * T]; if (v > m) { m = v; mp = j; } }
+                thr = m; maxpos = mp;
+                thr_f = thr == kInfKey ? __int_as_float(0x7f800000) : __uint_as_float((unsigned)(thr >> 32));
+            }
+        }
+        nbuf = 0;
+    }
+};
+
+// Scan `cnt` staged references (global indices base..base+cnt) for this thread's query.  Whole warps call
+// this together; `active` lanes own a query.
+template <int T>
+__device__ __forceinline__ void scan_refs(TopK<T>& tk, bool active, float qx, float qy, float qz, const float4* refs,
+                                          int cnt, int base) {
+    for (int r0 = 0; r0 < cnt; r0 += 8) {
+        if (active) {
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const int r = r0 + u;
+                if (r < cnt) tk.offer(sqdist(qx, qy, qz, refs[r]), base + r);
+            }
+        }
+        if (__any_sync(0xffffffffu, tk.nbuf > kBuf - 8)) tk.flush();
+    }
+    tk.flush();
 }
 
 constexpr int kKnnThreads = 128;
-constexpr int kRefTile = 2048;
+constexpr int kRefTile = 1024;
 
-// grid (ceil(Q/128), B)
-template <int KMAX>
+// grid (ceil(Q/128), B); dynamic smem: list (k x T u64) | buf (kBuf x T u64)
 __global__ void __launch_bounds__(kKnnThreads)
 knn_kernel(int r, int q, int k, const float* __restrict__ ref_pts, const float* __restrict__ query,
            float* __restrict__ dist, int* __restrict__ idx) {
-    __shared__ float sx[kRefTile], sy[kRefTile], sz[kRefTile];
+    __shared__ float4 s_ref[kRefTile];
+    extern __shared__ __align__(16) unsigned char s_raw[];
+    u64* s_list = reinterpret_cast<u64*>(s_raw);
+    u64* s_buf = s_list + (size_t)k * kKnnThreads;
     const int b = blockIdx.y;
     const int qi = blockIdx.x * kKnnThreads + threadIdx.x;
     const float* rp = ref_pts + (size_t)b * r * 3;
+    const bool active = qi < q;
     float qx = 0.f, qy = 0.f, qz = 0.f;
-    if (qi < q) {
+    if (active) {
         const float* qp = query + ((size_t)b * q + qi) * 3;
         qx = qp[0]; qy = qp[1]; qz = qp[2];
     }
-    TopK<KMAX> tk; tk.init(k);
+    TopK<kKnnThreads> tk;
+    tk.init(s_list + threadIdx.x, s_buf + threadIdx.x, k);
     for (int r0 = 0; r0 < r; r0 += kRefTile) {
         const int cnt = min(kRefTile, r - r0);
         __syncthreads();
-        for (int f = threadIdx.x; f < cnt * 3; f += kKnnThreads) {
-            const float v = rp[(size_t)r0 * 3 + f];
-            const int p = f / 3, c = f - 3 * p;
-            (c == 0 ? sx : c == 1 ? sy : sz)[p] = v;
+        for (int p = threadIdx.x; p < cnt; p += kKnnThreads) {
+            const float* s = rp + (size_t)(r0 + p) * 3;
+            s_ref[p] = make_float4(s[0], s[1], s[2], 0.f);
         }
         __syncthreads();
-        if (qi < q) scan_refs<KMAX>(tk, qx, qy, qz, sx, sy, sz, cnt, r0);
+        scan_refs<kKnnThreads>(tk, active, qx, qy, qz, s_ref, cnt, r0);
     }
-    if (qi < q) {
+    if (active) {
+        // ascending order: insertion sort of this thread's k keys
+        for (int a = 1; a < k; ++a) {
+            const u64 key = tk.list[a * kKnnThreads];
+            int j = a - 1;
+            while (j >= 0 && tk.list[j * kKnnThreads] > key) { tk.list[(j + 1) * kKnnThreads] = tk.list[j * kKnnThreads]; --j; }
+            tk.list[(j + 1) * kKnnThreads] = key;
+        }
         int* io = idx + ((size_t)b * q + qi) * k;
         float* dop = dist ? dist + ((size_t)b * q + qi) * k : nullptr;
-#pragma unroll
-        for (int j = 0; j < KMAX; ++j) {
-            const int o = j - (KMAX - k);
-            if (o >= 0) {
-                io[o] = tk.i[j];
-                if (dop) dop[o] = sqrtf(tk.d[j]);
-            }
+        for (int j = 0; j < k; ++j) {
+            const u64 key = tk.list[j * kKnnThreads];
+            io[j] = (int)(unsigned)key;
+            if (dop) dop[j] = sqrtf(__uint_as_float((unsigned)(key >> 32)));
         }
     }
 }
@@ -105,57 +132,67 @@ __device__ __forceinline__ unsigned hash3(float x, float y, float z) {
     return h ^ (h >> 15);
 }
 
-constexpr int kSelThreads = 256;
-
-// One CTA per object.  Dynamic smem: complete SoA (3R floats) | partial SoA (3Np floats) |
-// hash table (H ints) | bitmask (R/32 words) | word prefix (R/32 + 1 ints)
-template <int KMAX>
-__global__ void __launch_bounds__(kSelThreads)
+// One CTA of T threads per object.  Dynamic smem:
+//   complete float4[R] | list k*T u64 | buf kBuf*T u64 | partial SoA 3*Np f32 | hash table H i32 |
+//   unique list Np i32 | bitmask nw u32 | prefix (nw+1) i32
+template <int T>
+__global__ void __launch_bounds__(T)
 knn_surface_select_kernel(int np, int r, int k, int surface_pts, int hash_size,
                           const float* __restrict__ partial, const float* __restrict__ complete,
                           float* __restrict__ out, int* __restrict__ sel_count) {
     extern __shared__ __align__(16) unsigned char s_raw[];
     const int nwords = (r + 31) >> 5;
-    float* cx = reinterpret_cast<float*>(s_raw);
-    float* cy = cx + r; float* cz = cy + r;
-    float* qx = cz + r; float* qy = qx + np; float* qz = qy + np;
+    float4* cref = reinterpret_cast<float4*>(s_raw);
+    u64* s_list = reinterpret_cast<u64*>(cref + r);
+    u64* s_buf = s_list + (size_t)k * T;
+    float* qx = reinterpret_cast<float*>(s_buf + (size_t)kBuf * T);
+    float* qy = qx + np; float* qz = qy + np;
     int* tab = reinterpret_cast<int*>(qz + np);
-    unsigned* mask = reinterpret_cast<unsigned*>(tab + hash_size);
+    int* uq = tab + hash_size;
+    unsigned* mask = reinterpret_cast<unsigned*>(uq + np);
     int* prefix = reinterpret_cast<int*>(mask + nwords);
-    __shared__ int s_total;
+    __shared__ int s_total, s_nuniq;
 
     const int b = blockIdx.x;
     const float* cp = complete + (size_t)b * r * 3;
     const float* pp = partial + (size_t)b * np * 3;
-    for (int f = threadIdx.x; f < r * 3; f += kSelThreads) {
-        const float v = cp[f]; const int p = f / 3, c = f - 3 * p;
-        (c == 0 ? cx : c == 1 ? cy : cz)[p] = v;
-    }
-    for (int f = threadIdx.x; f < np * 3; f += kSelThreads) {
+    for (int p = threadIdx.x; p < r; p += T) cref[p] = make_float4(cp[p * 3 + 0], cp[p * 3 + 1], cp[p * 3 + 2], 0.f);
+    for (int f = threadIdx.x; f < np * 3; f += T) {
         const float v = pp[f]; const int p = f / 3, c = f - 3 * p;
         (c == 0 ? qx : c == 1 ? qy : qz)[p] = v;
     }
-    for (int i = threadIdx.x; i < hash_size; i += kSelThreads) tab[i] = -1;
-    for (int i = threadIdx.x; i < nwords; i += kSelThreads) mask[i] = 0u;
+    for (int i = threadIdx.x; i < hash_size; i += T) tab[i] = -1;
+    for (int i = threadIdx.x; i < nwords; i += T) mask[i] = 0u;
+    if (threadIdx.x == 0) s_nuniq = 0;
     __syncthreads();
 
-    for (int qi = threadIdx.x; qi < np; qi += kSelThreads) {
+    // hash-set insert: the first thread to claim a slot for these exact coordinates keeps the query
+    for (int qi = threadIdx.x; qi < np; qi += T) {
         const float x = qx[qi], y = qy[qi], z = qz[qi];
-        // hash-set insert: the first thread to claim a slot for these exact coordinates runs the query
         unsigned h = hash3(x, y, z) & (hash_size - 1);
-        bool unique = false;
         while (true) {
             const int prev = atomicCAS(&tab[h], -1, qi);
-            if (prev == -1) { unique = true; break; }
+            if (prev == -1) { uq[atomicAdd(&s_nuniq, 1)] = qi; break; }
             if (qx[prev] == x && qy[prev] == y && qz[prev] == z) break;   // duplicate query
             h = (h + 1) & (hash_size - 1);
         }
-        if (!unique) continue;
-        TopK<KMAX> tk; tk.init(k);
-        scan_refs<KMAX>(tk, x, y, z, cx, cy, cz, r, 0);
-#pragma unroll
-        for (int j = 0; j < KMAX; ++j)
-            if (tk.i[j] >= 0) atomicOr(&mask[tk.i[j] >> 5], 1u << (tk.i[j] & 31));
+    }
+    __syncthreads();
+    const int nuniq = s_nuniq;
+    for (int u0 = 0; u0 < nuniq; u0 += T) {
+        if (u0 + (int)(threadIdx.x & ~31u) >= nuniq) break;     // whole warp idle (warp-uniform)
+        const int u = u0 + threadIdx.x;
+        const bool active = u < nuniq;
+        float x = 0.f, y = 0.f, z = 0.f;
+        if (active) { const int qi = uq[u]; x = qx[qi]; y = qy[qi]; z = qz[qi]; }
+        TopK<T> tk;
+        tk.init(s_list + threadIdx.x, s_buf + threadIdx.x, k);
+        scan_refs<T>(tk, active, x, y, z, cref, r, 0);
+        if (active)
+            for (int j = 0; j < k; ++j) {
+                const u64 key = tk.list[j * T];
+                if (key != kInfKey) { const unsigned i = (unsigned)key; atomicOr(&mask[i >> 5], 1u << (i & 31)); }
+            }
     }
     __syncthreads();
     // exclusive prefix of popcounts over mask words (nwords <= 512): one warp, serial chunks
@@ -178,21 +215,38 @@ knn_surface_select_kernel(int np, int r, int k, int surface_pts, int hash_size,
     __syncthreads();
     const int total = s_total;
     float* o = out + (size_t)b * surface_pts * 3;
-    for (int j = threadIdx.x; j < surface_pts; j += kSelThreads) {
+    for (int j = threadIdx.x; j < surface_pts; j += T) {
         float x = 0.f, y = 0.f, z = 0.f;
         if (total > 0) {
             const int rank = j % total;
             int lo = 0, hi = nwords;           // last w with prefix[w] <= rank
             while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (prefix[mid] <= rank) lo = mid; else hi = mid; }
             const int bit = __fns(mask[lo], 0, rank - prefix[lo] + 1);
-            const int src = (lo << 5) + bit;
-            x = cx[src]; y = cy[src]; z = cz[src];
+            const float4 s = cref[(lo << 5) + bit];
+            x = s.x; y = s.y; z = s.z;
         }
         o[j * 3 + 0] = x; o[j * 3 + 1] = y; o[j * 3 + 2] = z;
     }
 }
 
 int next_pow2(int v) { int p = 1; while (p < v) p <<= 1; return p; }
+
+size_t select_smem(int T, int np, int r, int k, int hash_size) {
+    const int nwords = (r + 31) / 32;
+    return (size_t)r * 16 + (size_t)(k + kBuf) * T * 8 + (size_t)np * 12 + (size_t)hash_size * 4 + (size_t)np * 4 +
+           (size_t)nwords * 4 + (size_t)(nwords + 1) * 4 + 16;
+}
+
+template <int T>
+int launch_select(int b, int np, int r, int k, int surface_pts, int hash_size, size_t smem, const float* partial,
+                  const float* complete, float* out, int* sel_count, cudaStream_t st) {
+    auto kern = knn_surface_select_kernel<T>;
+    if (smem > 40 * 1024)
+        SEEVCN_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<b, T, smem, st>>>(np, r, k, surface_pts, hash_size, partial, complete, out, sel_count);
+    SEEVCN_LAUNCH_CHECK();
+    return SEEVCN_OK;
+}
 
 }  // namespace
 
@@ -205,25 +259,10 @@ extern "C" int seevcn_knn(int b, int r, int q, int k, const float* ref_pts, cons
     SEEVCN_REQUIRE(ref_pts && query && idx, "knn: null pointer");
     SEEVCN_REQUIRE(b <= 65535, "knn: b > 65535");
     dim3 grid(div_up(q, kKnnThreads), b);
-    cudaStream_t st = as_stream(stream);
-    if (k <= 16) knn_kernel<16><<<grid, kKnnThreads, 0, st>>>(r, q, k, ref_pts, query, dist, idx);
-    else if (k <= 32) knn_kernel<32><<<grid, kKnnThreads, 0, st>>>(r, q, k, ref_pts, query, dist, idx);
-    else knn_kernel<64><<<grid, kKnnThreads, 0, st>>>(r, q, k, ref_pts, query, dist, idx);
-    SEEVCN_LAUNCH_CHECK();
-    return SEEVCN_OK;
-}
-
-template <int KMAX>
-static int launch_select(int b, int np, int r, int k, int surface_pts, const float* partial, const float* complete,
-                         float* out, int* sel_count, cudaStream_t st) {
-    const int hash_size = next_pow2(2 * np);
-    const int nwords = (r + 31) / 32;
-    const size_t smem = (size_t)(3 * r + 3 * np) * 4 + (size_t)hash_size * 4 + (size_t)nwords * 4 + (size_t)(nwords + 1) * 4;
-    SEEVCN_REQUIRE(smem <= 227 * 1024, "knn_surface_select: r=%d np=%d needs %zu B of shared memory (> 227 KB)", r, np, smem);
-    auto kern = knn_surface_select_kernel<KMAX>;
-    if (smem > 40 * 1024)
-        SEEVCN_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    kern<<<b, kSelThreads, smem, st>>>(np, r, k, surface_pts, hash_size, partial, complete, out, sel_count);
+    const size_t smem = (size_t)(k + kBuf) * kKnnThreads * 8;
+    if (smem > 30 * 1024)
+        SEEVCN_CUDA_CHECK(cudaFuncSetAttribute(knn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    knn_kernel<<<grid, kKnnThreads, smem, as_stream(stream)>>>(r, q, k, ref_pts, query, dist, idx);
     SEEVCN_LAUNCH_CHECK();
     return SEEVCN_OK;
 }
@@ -237,7 +276,16 @@ extern "C" int seevcn_knn_surface_select(int b, int n_partial, int r, int k, int
     SEEVCN_REQUIRE(k <= r, "knn_surface_select: k=%d > r=%d", k, r);
     SEEVCN_REQUIRE(partial && complete && out && sel_count, "knn_surface_select: null pointer");
     cudaStream_t st = as_stream(stream);
-    if (k <= 16) return launch_select<16>(b, n_partial, r, k, surface_pts, partial, complete, out, sel_count, st);
-    if (k <= 32) return launch_select<32>(b, n_partial, r, k, surface_pts, partial, complete, out, sel_count, st);
-    return launch_select<64>(b, n_partial, r, k, surface_pts, partial, complete, out, sel_count, st);
+    const int hash_size = next_pow2(2 * (n_partial > 0 ? n_partial : 1));
+    // widest block whose per-thread lists still fit next to the staged clouds
+    const size_t lim = 227 * 1024;
+    if (select_smem(256, n_partial, r, k, hash_size) <= lim / 2)   // two CTAs per SM
+        return launch_select<256>(b, n_partial, r, k, surface_pts, hash_size, select_smem(256, n_partial, r, k, hash_size),
+                                  partial, complete, out, sel_count, st);
+    if (select_smem(128, n_partial, r, k, hash_size) <= lim)
+        return launch_select<128>(b, n_partial, r, k, surface_pts, hash_size, select_smem(128, n_partial, r, k, hash_size),
+                                  partial, complete, out, sel_count, st);
+    const size_t need = select_smem(32, n_partial, r, k, hash_size);
+    SEEVCN_REQUIRE(need <= lim, "knn_surface_select: r=%d np=%d k=%d needs %zu B of shared memory (> 227 KB)", r, n_partial, k, need);
+    return launch_select<32>(b, n_partial, r, k, surface_pts, hash_size, need, partial, complete, out, sel_count, st);
 }

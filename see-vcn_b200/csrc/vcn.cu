@@ -254,9 +254,38 @@ linear_f32_kernel(int rows, int cin, int cout, const float* __restrict__ X, int 
     }
 }
 
+// Skinny layer (cout <= 16, e.g. pose_fc.2: 512 -> 9): one warp per row, lanes split K, shuffle reduce.
+__global__ void __launch_bounds__(256)
+linear_skinny_kernel(int rows, int cin, int cout, const float* __restrict__ X, int ldx, const float* __restrict__ W, int ldw,
+                     const float* __restrict__ bias, int act, float* __restrict__ Y, int ldy) {
+    const int row = blockIdx.x * 8 + warp_id();
+    if (row >= rows) return;
+    float acc[16];
+#pragma unroll
+    for (int c = 0; c < 16; ++c) acc[c] = 0.f;
+    const float* x = X + (size_t)row * ldx;
+    for (int k = lane_id(); k < cin; k += 32) {
+        const float xv = x[k];
+#pragma unroll
+        for (int c = 0; c < 16; ++c)
+            if (c < cout) acc[c] = fmaf(xv, W[(size_t)c * ldw + k], acc[c]);
+    }
+#pragma unroll
+    for (int c = 0; c < 16; ++c) {
+#pragma unroll
+        for (int off = 16; off >= 1; off >>= 1) acc[c] += __shfl_xor_sync(0xffffffffu, acc[c], off);
+        if (lane_id() == 0 && c < cout) Y[(size_t)row * ldy + c] = apply_act(acc[c] + (bias ? bias[c] : 0.f), act);
+    }
+}
+
 int linear_f32(const LinearW& L, int rows, const float* X, int ldx, const float* obj_bias, int rows_per_obj, int act,
                float* Y, int ldy, float* colmax, cudaStream_t st) {
     if (rows == 0) return SEEVCN_OK;
+    if (L.cout <= 16 && !obj_bias && !colmax && Y) {
+        linear_skinny_kernel<<<div_up(rows, 8), 256, 0, st>>>(rows, L.cin, L.cout, X, ldx, L.w, L.ldw, L.b, act, Y, ldy);
+        SEEVCN_LAUNCH_CHECK();
+        return SEEVCN_OK;
+    }
     dim3 grid(div_up(L.cout, BN), div_up(rows, BM));
     linear_f32_kernel<<<grid, 256, 0, st>>>(rows, L.cin, L.cout, X, ldx, L.w, L.ldw, L.b, obj_bias, rows_per_obj, act, Y,
                                             ldy, colmax);
@@ -438,12 +467,15 @@ extern "C" int seevcn_vcn_forward(const seevcn_vcn_model* M, int num_obj, int n,
                              static_cast<__nv_bfloat16*>(Y), ldy, nullptr, colmax, st);
     };
     // per-object FC layer: X fp32 (B, cin) -> fp32 Y (B, cout); the tcgen05 path converts X to bf16 first
-    auto fc_layer = [&](const LinearW& L, const float* X, int act, float* Y, __nv_bfloat16* xb) -> int {
-        if (!tc || L.cout % 128 != 0) return linear_f32(L, num_obj, X, L.cin, nullptr, 1, act, Y, L.cout, nullptr, st);
-        const size_t tot = (size_t)num_obj * L.kpad;
-        f32_to_bf16_kernel<<<(unsigned)div_up(tot, (size_t)256), 256, 0, st>>>(num_obj, L.cin, X, L.cin, xb, L.kpad);
+    auto fc_rows = [&](const LinearW& L, int rows, const float* X, int act, float* Y, __nv_bfloat16* xb) -> int {
+        if (!tc || L.cout % 128 != 0) return linear_f32(L, rows, X, L.cin, nullptr, 1, act, Y, L.cout, nullptr, st);
+        const size_t tot = (size_t)rows * L.kpad;
+        f32_to_bf16_kernel<<<(unsigned)div_up(tot, (size_t)256), 256, 0, st>>>(rows, L.cin, X, L.cin, xb, L.kpad);
         SEEVCN_LAUNCH_CHECK();
-        return vcn_linear_tc(L, num_obj, xb, L.kpad, nullptr, 1, act, nullptr, 0, Y, nullptr, st);
+        return vcn_linear_tc(L, rows, xb, L.kpad, nullptr, 1, act, nullptr, 0, Y, nullptr, st);
+    };
+    auto fc_layer = [&](const LinearW& L, const float* X, int act, float* Y, __nv_bfloat16* xb) -> int {
+        return fc_rows(L, num_obj, X, act, Y, xb);
     };
     auto pts_in = [&](int) -> int { return SEEVCN_OK; };
     const void* ptsX = pts3;
@@ -483,8 +515,7 @@ extern "C" int seevcn_vcn_forward(const seevcn_vcn_model* M, int num_obj, int n,
         TRY(pp_layer(M->enc1_0, rows, ptsX, ptsLd, nullptr, ACT_RELU, A, 128, nullptr));
         TRY(pp_layer(M->enc1_3, rows, A, 128, nullptr, ACT_NONE, Bf, 256, g256 + (size_t)o0 * 256));
         // per-object bias = W[:, :256] . global + b   (the torch.cat + expand of VCN_VC.py:100-101, folded)
-        TRY(linear_f32(M->enc2_0_global, nb, g256 + (size_t)o0 * 256, 256, nullptr, 1, ACT_NONE,
-                       objbias + (size_t)o0 * 512, 512, nullptr, st));
+        TRY(fc_rows(M->enc2_0_global, nb, g256 + (size_t)o0 * 256, ACT_NONE, objbias + (size_t)o0 * 512, fcxA));
         TRY(pp_layer(M->enc2_0_local, rows, Bf, 256, objbias + (size_t)o0 * 512, ACT_RELU, A, 512, nullptr));
         TRY(pp_layer(M->enc2_3, rows, A, 512, nullptr, ACT_NONE, nullptr, 0, feat + (size_t)o0 * 1024));
     }

@@ -45,6 +45,7 @@ __device__ __forceinline__ float apply_act(float v, int act) {
 }
 
 __device__ __forceinline__ void atomic_max_float(float* addr, float v) {
+    v += 0.f;   // -0.0 -> +0.0: as an int, -0.0 would order below every negative float
     if (v >= 0.f) atomicMax(reinterpret_cast<int*>(addr), __float_as_int(v));
     else atomicMin(reinterpret_cast<unsigned*>(addr), __float_as_uint(v));
 }

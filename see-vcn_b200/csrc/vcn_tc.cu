@@ -15,7 +15,8 @@
 //   warp 1   MMA issuer: one elected thread issues tcgen05.mma.cta_group::1.kind::f16 (bf16 x bf16 ->
 //            fp32), 4 per stage, accumulating into one of TWO 256-column TMEM accumulators
 //   warp 2   TMEM allocator (512 columns)
-//   warps 4-7 epilogue: tcgen05.ld 32 lanes x 32 columns at a time, bias/act/max, bf16 or fp32 stores;
+//   warps 4-11 epilogue (two per TMEM lane quadrant, one per column half): tcgen05.ld 32 lanes x 32
+//            columns at a time, bias/act/max, bf16 or fp32 stores;
 //            overlaps the next tile's MMAs through the double-buffered accumulator
 // Tiles that share an X tile are adjacent in the schedule so X is read from HBM once and from L2
 // for the other cout/128 - 1 channel tiles.
@@ -32,7 +33,7 @@ constexpr int STAGES = 4;
 constexpr int A_BYTES = BM * BK * 2;   // 16 KB
 constexpr int B_BYTES = BN * BK * 2;   // 32 KB
 constexpr int SMEM_BYTES = STAGES * (A_BYTES + B_BYTES) + 1024 /*align slack*/ + 256 /*barriers*/;
-constexpr int NUM_THREADS = 256;
+constexpr int NUM_THREADS = 384;   // warps 0-3: TMA / MMA / TMEM alloc / idle; warps 4-11: epilogue
 constexpr int TMEM_COLS = 512;
 
 struct TcArgs {
@@ -134,7 +135,7 @@ vcn_linear_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_co
     }
     if (warp == 1 && lane == 0) {
         for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
-        for (int s = 0; s < 2; ++s) { mbar_init(&tfull[s], 1); mbar_init(&tempty[s], 4); }
+        for (int s = 0; s < 2; ++s) { mbar_init(&tfull[s], 1); mbar_init(&tempty[s], 8); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 2) {
@@ -188,7 +189,10 @@ vcn_linear_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_co
             }
         }
     } else if (warp >= 4) {
-        const int q = warp & 3;                 // TMEM lane quadrant this warp may access
+        // 8 epilogue warps: TMEM lane quadrant q = warp % 4 (hardware restriction), column half h.
+        const int q = warp & 3, h = (warp - 4) >> 2;
+        // act as one branch-free op: v = max(v, slope * v) — slope 1 = none, 0 = ReLU, 0.01 = LeakyReLU
+        const float slope = a.act == ACT_RELU ? 0.f : a.act == ACT_LEAKY ? 0.01f : 1.f;
         int it = 0;
         for (int tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x, ++it) {
             const int acc = it & 1;
@@ -198,48 +202,81 @@ vcn_linear_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_co
             const int row0 = n_tile * BN;
             const int nvalid = min(BN, a.rows - row0);
             const bool c_ok = c < a.cout;
-            const float bias = (a.bias && c_ok) ? a.bias[c] : 0.f;
             const int obj_first = row0 / a.rows_per_obj, obj_last = (row0 + nvalid - 1) / a.rows_per_obj;
             const bool one_obj = obj_first == obj_last;
-            float ob = 0.f;
-            if (one_obj && a.obj_bias && c_ok) ob = a.obj_bias[(size_t)obj_first * a.cout + c];
+            float bt = (a.bias && c_ok) ? a.bias[c] : 0.f;            // bias (+ per-object bias when the tile is one object)
+            if (one_obj && a.obj_bias && c_ok) bt += a.obj_bias[(size_t)obj_first * a.cout + c];
             mbar_wait(&tfull[acc], acc_phase);
             tc_fence_after();
+            const uint32_t t_base = tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN + h * (BN / 2);
             float run_max = -__int_as_float(0x7f800000);
             int run_obj = obj_first;
-            for (int ch = 0; ch < BN / 32; ++ch) {
-                if (ch * 32 >= nvalid) break;   // warp-uniform
+            // max-only tiles inside one object track the RAW accumulator: bias and the monotone activation
+            // commute with max and are applied once at the end
+            const bool raw_max = !a.Y && !a.Yf32 && one_obj;
+#pragma unroll 1
+            for (int ch = 0; ch < BN / 64; ++ch) {
+                const int p0 = h * (BN / 2) + ch * 32;     // first point (column) of this chunk
+                if (p0 >= nvalid) break;                   // warp-uniform
                 uint32_t r[32];
-                tc_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN + ch * 32, r);
+                tc_ld32(t_base + ch * 32, r);
+                if (one_obj && c_ok && p0 + 32 <= nvalid) {
+                    // fast path: full chunk, one object, valid channel
+                    if (a.Y) {
+                        __nv_bfloat16* yp = a.Y + (size_t)(row0 + p0) * a.ldy + c;
 #pragma unroll
-                for (int j = 0; j < 32; ++j) {
-                    const int p = ch * 32 + j;
-                    if (p < nvalid && c_ok) {
+                        for (int j = 0; j < 32; ++j) {
+                            float v = __uint_as_float(r[j]) + bt;
+                            v = fmaxf(v, slope * v);
+                            yp[(size_t)j * a.ldy] = __float2bfloat16(v);
+                            run_max = fmaxf(run_max, v);
+                        }
+                    } else if (a.Yf32) {
+                        float* yp = a.Yf32 + (size_t)(row0 + p0) * a.ldyf + c;
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) {
+                            float v = __uint_as_float(r[j]) + bt;
+                            v = fmaxf(v, slope * v);
+                            yp[(size_t)j * a.ldyf] = v;
+                            run_max = fmaxf(run_max, v);
+                        }
+                    } else {
+                        // max-pool only: bias and the monotone activation commute with max -> applied once below
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) run_max = fmaxf(run_max, __uint_as_float(r[j]));
+                    }
+                } else if (c_ok) {
+                    // generic path: ragged tail and / or several objects inside the tile (FC layers: one object per row)
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) {   // unrolled so r[] keeps static register indices
+                        const int p = p0 + j;
+                        if (p >= nvalid) continue;
                         const int row = row0 + p;
-                        float v = __uint_as_float(r[j]) + bias;
-                        if (one_obj) v += ob;
-                        else if (a.obj_bias) v += a.obj_bias[(size_t)(row / a.rows_per_obj) * a.cout + c];
-                        v = apply_act(v, a.act);
+                        const int o = row / a.rows_per_obj;
+                        float v = __uint_as_float(r[j]) + bt;
+                        if (!one_obj && a.obj_bias) v += a.obj_bias[(size_t)o * a.cout + c];
+                        v = fmaxf(v, slope * v);
                         if (a.Y) a.Y[(size_t)row * a.ldy + c] = __float2bfloat16(v);
                         if (a.Yf32) a.Yf32[(size_t)row * a.ldyf + c] = v;
                         if (a.colmax) {
-                            if (one_obj) run_max = fmaxf(run_max, v);
-                            else {
-                                const int o = row / a.rows_per_obj;
-                                if (o != run_obj) {
-                                    atomic_max_float(&a.colmax[(size_t)run_obj * a.cout + c], run_max);
-                                    run_obj = o; run_max = v;
-                                } else run_max = fmaxf(run_max, v);
+                            if (o != run_obj) {
+                                atomic_max_float(&a.colmax[(size_t)run_obj * a.cout + c], run_max);
+                                run_obj = o; run_max = -__int_as_float(0x7f800000);
                             }
+                            run_max = fmaxf(run_max, raw_max ? __uint_as_float(r[j]) : v);
                         }
                     }
                 }
             }
-            // release the accumulator before the (slow) global atomics
+            // release the accumulator before the global atomics
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&tempty[acc]);
-            if (a.colmax && c_ok) atomic_max_float(&a.colmax[(size_t)run_obj * a.cout + c], run_max);
+            if (a.colmax && c_ok && run_max > -__int_as_float(0x7f800000)) {
+                float v = run_max;
+                if (raw_max) { v = run_max + bt; v = fmaxf(v, slope * v); }
+                atomic_max_float(&a.colmax[(size_t)run_obj * a.cout + c], v);
+            }
         }
     }
     tc_fence_before();
@@ -255,10 +292,13 @@ vcn_linear_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_co
 __global__ void __launch_bounds__(256)
 pointwise3_kernel(size_t rows, int cout, const float* __restrict__ X, const float* __restrict__ W,
                   const float* __restrict__ bias, int act, __nv_bfloat16* __restrict__ Y, int ldy) {
-    extern __shared__ float s_w[];   // cout * 4: w0 w1 w2 b
+    // cout * 4 floats (w0 w1 w2 b), plus 4 floats of padding per group of 8 channels: lanes of a warp read
+    // 16 different groups at once, and an unpadded 128-byte group stride would put them all in one bank
+    extern __shared__ float s_w[];
     for (int i = threadIdx.x; i < cout; i += blockDim.x) {
-        s_w[i * 4 + 0] = W[i * 3 + 0]; s_w[i * 4 + 1] = W[i * 3 + 1]; s_w[i * 4 + 2] = W[i * 3 + 2];
-        s_w[i * 4 + 3] = bias ? bias[i] : 0.f;
+        float* d = s_w + i * 4 + (i >> 3) * 4;
+        d[0] = W[i * 3 + 0]; d[1] = W[i * 3 + 1]; d[2] = W[i * 3 + 2];
+        d[3] = bias ? bias[i] : 0.f;
     }
     __syncthreads();
     const int groups = cout / 8;
@@ -270,7 +310,7 @@ pointwise3_kernel(size_t rows, int cout, const float* __restrict__ X, const floa
     __align__(16) __nv_bfloat16 o[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-        const float4 w = *reinterpret_cast<const float4*>(&s_w[(g * 8 + j) * 4]);
+        const float4 w = *reinterpret_cast<const float4*>(&s_w[(g * 8 + j) * 4 + g * 4]);
         o[j] = __float2bfloat16(apply_act(fmaf(w.z, z, fmaf(w.y, y, fmaf(w.x, x, w.w))), act));
     }
     *reinterpret_cast<uint4*>(Y + r * ldy + g * 8) = *reinterpret_cast<const uint4*>(o);
@@ -340,7 +380,7 @@ int vcn_pointwise3(const LinearW& L, size_t rows, const float* X, int act, __nv_
     if (rows == 0) return SEEVCN_OK;
     SEEVCN_REQUIRE(L.cin == 3 && L.cout % 8 == 0 && ldy % 8 == 0, "vcn_pointwise3: needs cin == 3, cout %% 8 == 0");
     const size_t total = rows * (size_t)(L.cout / 8);
-    pointwise3_kernel<<<(unsigned)div_up(total, (size_t)256), 256, L.cout * 16, st>>>(rows, L.cout, X, L.w, L.b, act, Y, ldy);
+    pointwise3_kernel<<<(unsigned)div_up(total, (size_t)256), 256, L.cout * 16 + (L.cout / 8) * 16, st>>>(rows, L.cout, X, L.w, L.b, act, Y, ldy);
     SEEVCN_LAUNCH_CHECK();
     return SEEVCN_OK;
 }

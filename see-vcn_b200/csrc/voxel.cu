@@ -86,6 +86,8 @@ dynvox_finalize_kernel(unsigned long long nslots, int c, VoxGeom g, const unsign
                        const float* __restrict__ acc, int max_voxels, int* __restrict__ voxel_coords,
                        float* __restrict__ voxel_features, int* __restrict__ voxel_counts,
                        unsigned long long* __restrict__ out_keys, int* __restrict__ num_voxels) {
+    __shared__ int s_wcnt[8];
+    __shared__ int s_base;
     const unsigned long long nthreads = (unsigned long long)gridDim.x * blockDim.x;
     const unsigned long long rounds = (nslots + nthreads - 1) / nthreads;
     for (unsigned long long it = 0; it < rounds; ++it) {
@@ -93,13 +95,19 @@ dynvox_finalize_kernel(unsigned long long nslots, int c, VoxGeom g, const unsign
         unsigned long long key = kEmpty;
         if (s < nslots) key = keys[s];
         const bool occ = key != kEmpty;
+        // one global atomic per CTA per round: warp ballots -> smem prefix over the 8 warps
         const unsigned m = __ballot_sync(0xffffffffu, occ);
-        if (m == 0) continue;
-        int base = 0;
-        if (lane_id() == __ffs(m) - 1) base = atomicAdd(num_voxels, __popc(m));
-        base = __shfl_sync(0xffffffffu, base, __ffs(m) - 1);
+        __syncthreads();                       // previous round's s_base / s_wcnt consumed
+        if (lane_id() == 0) s_wcnt[warp_id()] = __popc(m);
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            int tot = 0;
+            for (int w = 0; w < 8; ++w) { const int c = s_wcnt[w]; s_wcnt[w] = tot; tot += c; }
+            s_base = tot ? atomicAdd(num_voxels, tot) : 0;
+        }
+        __syncthreads();
         if (!occ) continue;
-        const int row = base + __popc(m & ((1u << lane_id()) - 1));
+        const int row = s_base + s_wcnt[warp_id()] + __popc(m & ((1u << lane_id()) - 1));
         if (row >= max_voxels) continue;
         const float* a = acc + s * ACCW;
         const float cnt = a[ACCW - 1];
@@ -323,9 +331,10 @@ extern "C" size_t seevcn_dynamic_voxelize_workspace_bytes(int num_points, int nu
 
 extern "C" int seevcn_dynamic_voxelize(int num_points, int num_features, const float* points, const float* pc_range,
                                        const float* voxel_size, const int* grid_size, int max_voxels, int sorted,
-                                       int* voxel_coords, float* voxel_features, int* voxel_counts, int* num_voxels,
+                                       int batch_hint, int* voxel_coords, float* voxel_features, int* voxel_counts, int* num_voxels,
                                        void* workspace, size_t workspace_bytes, seevcn_stream_t stream) {
     SEEVCN_REQUIRE(num_points >= 0 && max_voxels >= 0, "dynamic_voxelize: negative size");
+    if (batch_hint <= 0) batch_hint = 1 << 20;   // unknown batch size: sort on (almost) all key bits
     SEEVCN_REQUIRE(num_features >= 3 && num_features < kMaxFeat, "dynamic_voxelize: num_features=%d outside [3,%d]",
                    num_features, kMaxFeat - 1);
     SEEVCN_REQUIRE(pc_range && voxel_size && grid_size && num_voxels, "dynamic_voxelize: null pointer");
@@ -379,8 +388,12 @@ extern "C" int seevcn_dynamic_voxelize(int num_points, int num_features, const f
         iota_kernel<<<div_up(max_voxels, 256), 256, 0, st>>>(max_voxels, order_in);
         SEEVCN_LAUNCH_CHECK();
         size_t cub_bytes = w.cub_bytes;
+        // keys are < 2^kb except the all-ones padding of unused rows, which any bit range keeps last
+        int kb = 1;
+        const double span = (double)batch_hint * g.g[0] * g.g[1] * g.g[2];
+        while (kb < 64 && (double)(1ull << kb) < span) ++kb;
         SEEVCN_CUDA_CHECK(cub::DeviceRadixSort::SortPairs(ws + w.off_cub, cub_bytes, o_keys, keys_out, order_in,
-                                                          order_out, max_voxels, 0, 64, st));
+                                                          order_out, max_voxels, 0, kb < 64 ? kb + 1 : 64, st));
         dynvox_permute_kernel<<<div_up(max_voxels, 256), 256, 0, st>>>(
             max_voxels, num_features, num_voxels, order_out, reinterpret_cast<const int4*>(o_coords), o_feat, o_cnt,
             reinterpret_cast<int4*>(voxel_coords), voxel_features, voxel_counts);

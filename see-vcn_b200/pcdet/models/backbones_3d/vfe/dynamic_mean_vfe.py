@@ -8,7 +8,8 @@ from ..... import _abi
 from .vfe_template import VFETemplate
 
 
-def dynamic_voxelize(points, point_cloud_range, voxel_size, grid_size, max_voxels=None, sort=True, workspace=None):
+def dynamic_voxelize(points, point_cloud_range, voxel_size, grid_size, max_voxels=None, sort=True, workspace=None,
+                     batch_size=0):
     """points (N, 1+C) float32 CUDA rows [batch_idx, x, y, z, ...] ->
     voxel_coords (M, 4) int32 [b, z, y, x], voxel_features (M, C) float32, voxel_counts (M,) int32.
     ``sort=True`` orders rows by the reference's merge key (torch.unique order)."""
@@ -31,7 +32,7 @@ def dynamic_voxelize(points, point_cloud_range, voxel_size, grid_size, max_voxel
     with torch.cuda.device(dev):
         _abi.check(L.seevcn_dynamic_voxelize(N, C, _abi.ptr(points), _abi.farray(point_cloud_range),
                                              _abi.farray(voxel_size), _abi.iarray(grid_size), max_voxels,
-                                             1 if sort else 0, _abi.ptr(coords), _abi.ptr(feats), _abi.ptr(counts),
+                                             1 if sort else 0, int(batch_size), _abi.ptr(coords), _abi.ptr(feats), _abi.ptr(counts),
                                              _abi.ptr(num), _abi.ptr(workspace), workspace.numel(), _abi.stream()))
     m = min(int(num.item()), max_voxels)   # the one host sync: M is data dependent, as in the reference
     return coords[:m], feats[:m], counts[:m]
@@ -55,7 +56,7 @@ class DynamicMeanVFE(VFETemplate):
         ['voxel_features'] (M, C) mean of all in-voxel points, ['voxel_coords'] (M, 4) int32 [b,z,y,x],
         plus ['voxel_num_points'] (M,) int32 (the reference computes and drops unq_cnt, :63)."""
         coords, feats, counts = dynamic_voxelize(batch_dict['points'], self.point_cloud_range, self.voxel_size,
-                                                 self.grid_size, sort=self.sort)
+                                                 self.grid_size, sort=self.sort, batch_size=int(batch_dict.get('batch_size', 0)))
         batch_dict['voxel_features'] = feats.contiguous()
         batch_dict['voxel_coords'] = coords.contiguous()
         batch_dict['voxel_num_points'] = counts.contiguous()

@@ -103,3 +103,24 @@ def resample_gather(points, box_counts, box_offsets, box_points, obj_frame, obj_
                                                      _abi.ptr(box_offsets), _abi.ptr(box_points), _abi.ptr(obj_frame),
                                                      _abi.ptr(obj_box), _abi.ptr(choice), _abi.ptr(out), _abi.stream()))
     return out
+
+
+def resample_gather_rng(points, box_counts, box_offsets, box_points, obj_frame, obj_box, n_points, seed):
+    """ResamplePoints with the draw made on the device: object o receives the first ``n_points`` entries of a
+    pseudo-random permutation of its tiled point list (Feistel network keyed by ``seed`` and frame*T+box).
+    points (B, M, 3); obj_frame/obj_box (O,) int32 -> (O, n_points, 3) float32"""
+    _abi.require_cuda(points, box_counts, box_offsets, box_points, obj_frame, obj_box)
+    O = obj_frame.shape[0]
+    B, M, _ = points.shape
+    T = box_counts.shape[1]
+    out = torch.empty((O, n_points, 3), dtype=torch.float32, device=points.device)
+    with torch.cuda.device(points.device):
+        _abi.check(_abi.lib().seevcn_resample_gather_rng(O, n_points, T, M, int(seed) & 0xffffffff, _abi.ptr(points),
+                                                         _abi.ptr(box_counts), _abi.ptr(box_offsets), _abi.ptr(box_points),
+                                                         _abi.ptr(obj_frame), _abi.ptr(obj_box), _abi.ptr(out), _abi.stream()))
+    return out
+
+
+def resample_perm(j, n, seed, frame_box):
+    """Host evaluation of the same permutation (tests)."""
+    return _abi.lib().seevcn_resample_perm(int(j), int(n), int(seed) & 0xffffffff, int(frame_box))

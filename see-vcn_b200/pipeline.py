@@ -12,7 +12,7 @@ import torch
 from .pcdet.ops.roiaware_pool3d import roiaware_pool3d_utils as roi
 from .pcdet.models.backbones_3d.vfe.dynamic_mean_vfe import dynamic_voxelize
 from .see.surface_completion.models.vcn.models.build import MODELS
-from .see.surface_completion.models.vcn.utils.sampling import get_partial_mesh_batch
+from .see.surface_completion.models.vcn.utils.sampling import get_partial_mesh_batch, get_largest_cluster_batch
 
 WAYMO_VOXEL_CFG = ([-75.2, -75.2, -2.0, 75.2, 75.2, 4.0], [0.1, 0.1, 0.15], [1504, 1504, 40])   # sc_waymo_dataset.yaml:4,39-45
 
@@ -25,7 +25,7 @@ def resample_choice(count, n_points, rng):
 
 class CompletionPipeline:
     def __init__(self, model_name="VCN_VC", state_dict=None, device=None, sel_k=10, min_lidar_pts=30, resample_num=1024,
-                 voxel_cfg=WAYMO_VOXEL_CFG, precision="bf16"):
+                 voxel_cfg=WAYMO_VOXEL_CFG, precision="bf16", host_rng=False, cluster_eps=None):
         self.device = device if device is not None else torch.device("cuda", torch.cuda.current_device())
         self.model = MODELS.build({"NAME": model_name}, precision=precision)
         self.state_dict = state_dict
@@ -37,6 +37,8 @@ class CompletionPipeline:
         self.min_lidar_pts = min_lidar_pts    # SURFACE_COMPLETION.MIN_LIDAR_PTS
         self.resample_num = resample_num
         self.voxel_cfg = voxel_cfg
+        self.host_rng = host_rng              # True: numpy permutation per object on the host (reference's draw)
+        self.cluster_eps = cluster_eps        # SURFACE_COMPLETION.VCN.CLUSTER_EPS; None skips the largest-cluster filter
 
     @torch.no_grad()
     def complete(self, points, boxes, seed=0):
@@ -52,20 +54,29 @@ class CompletionPipeline:
             empty = torch.empty((0, self.resample_num, 3), device=points.device)
             out.update(input=empty, coarse=empty, surface=empty)
             return out
-        rng = np.random.default_rng(seed)
-        choice = np.stack([resample_choice(int(cnt[f, k]), self.resample_num, rng) for f, k in keep])
-        h = torch.from_numpy(np.concatenate([keep.astype(np.int32).T.reshape(-1), choice.reshape(-1)])).pin_memory()
-        d = h.to(points.device, non_blocking=True)
         O = len(keep)
-        obj_frame, obj_box, d_choice = d[:O], d[O:2 * O], d[2 * O:].view(O, self.resample_num)
-        inp = roi.resample_gather(points, counts, offsets, lists, obj_frame.contiguous(), obj_box.contiguous(),
-                                  d_choice.contiguous())
+        if self.host_rng:
+            # the reference's own draw (numpy permutation on the host), for bit-for-bit comparisons
+            rng = np.random.default_rng(seed)
+            choice = np.stack([resample_choice(int(cnt[f, k]), self.resample_num, rng) for f, k in keep])
+            h = torch.from_numpy(np.concatenate([keep.astype(np.int32).T.reshape(-1), choice.reshape(-1)])).pin_memory()
+            d = h.to(points.device, non_blocking=True)
+            obj_frame, obj_box, d_choice = d[:O], d[O:2 * O], d[2 * O:].view(O, self.resample_num)
+            inp = roi.resample_gather(points, counts, offsets, lists, obj_frame.contiguous(), obj_box.contiguous(),
+                                      d_choice.contiguous())
+        else:
+            d = torch.from_numpy(np.ascontiguousarray(keep.astype(np.int32).T)).pin_memory().to(points.device, non_blocking=True)
+            obj_frame, obj_box = d[0], d[1]
+            inp = roi.resample_gather_rng(points, counts, offsets, lists, obj_frame, obj_box, self.resample_num, seed)
         in_dict = {"input": inp}
         if self.model_name == "VCN_CN":
             in_dict["gt_boxes"] = boxes[obj_frame.long(), obj_box.long()].contiguous()
         coarse = self.model(in_dict)["coarse"]
         surface = get_partial_mesh_batch(inp, coarse, k=self.sel_k, surface_pts=self.resample_num)
         out.update(input=inp, coarse=coarse, surface=surface, obj_frame_dev=obj_frame)
+        if self.cluster_eps is not None:   # models/VCN.py:95-98
+            out["clustered"] = get_largest_cluster_batch(surface, eps=self.cluster_eps, min_points=2,
+                                                         total_pts=coarse.shape[1])
         return out
 
     @torch.no_grad()
@@ -75,11 +86,12 @@ class CompletionPipeline:
         F, P, _ = points.shape
         fid = torch.arange(F, device=points.device, dtype=torch.float32).view(F, 1, 1).expand(F, P, 1)
         rows = [torch.cat((fid, points), dim=2).view(F * P, 4)]
-        if out["surface"].shape[0] > 0:
-            O, S, _ = out["surface"].shape
+        completed = out.get("clustered", out["surface"])
+        if completed.shape[0] > 0:
+            O, S, _ = completed.shape
             ofid = out["obj_frame_dev"].to(torch.float32).view(O, 1, 1).expand(O, S, 1)
-            rows.append(torch.cat((ofid, out["surface"]), dim=2).view(O * S, 4))
+            rows.append(torch.cat((ofid, completed), dim=2).view(O * S, 4))
         vox_pts = torch.cat(rows, dim=0).contiguous()
-        coords, feats, nums = dynamic_voxelize(vox_pts, *self.voxel_cfg, sort=True)
+        coords, feats, nums = dynamic_voxelize(vox_pts, *self.voxel_cfg, sort=True, batch_size=F)
         out.update(voxel_points=vox_pts, voxel_coords=coords, voxel_features=feats, voxel_num_points=nums)
         return out

@@ -109,6 +109,29 @@ def test_resample_gather(cuda):
     np.testing.assert_array_equal(got.cpu().numpy(), np.stack(want))
 
 
+def test_resample_gather_device_rng(cuda):
+    """device-side draw: every object's cloud is the first 1024 entries of a permutation of its tiled list"""
+    pts, boxes = synth.make_stream(2, n_beams=32, n_az=1090, n_boxes=10)
+    d_pts = dev(pts, cuda)
+    idx, counts, offsets, lists = roi.crop_points_in_boxes(d_pts, dev(boxes, cuda))
+    cnt, off, lst = counts.cpu().numpy(), offsets.cpu().numpy(), lists.cpu().numpy()
+    objs = [(f, k) for f in range(2) for k in range(10) if cnt[f, k] >= 5]
+    of = dev(np.array([o[0] for o in objs], np.int32), cuda); ob = dev(np.array([o[1] for o in objs], np.int32), cuda)
+    got = roi.resample_gather_rng(d_pts, counts, offsets, lists, of, ob, 1024, seed=11).cpu().numpy()
+    again = roi.resample_gather_rng(d_pts, counts, offsets, lists, of, ob, 1024, seed=11).cpu().numpy()
+    other = roi.resample_gather_rng(d_pts, counts, offsets, lists, of, ob, 1024, seed=12).cpu().numpy()
+    np.testing.assert_array_equal(got, again)
+    assert not np.array_equal(got, other)
+    for o, (f, k) in enumerate(objs):
+        c = int(cnt[f, k]); reps = -(-1024 // c)
+        choice = np.array([roi.resample_perm(j, reps * c, 11, f * 10 + k) for j in range(1024)])
+        assert len(np.unique(choice)) == 1024 and choice.max() < reps * c          # a permutation prefix
+        src = lst[f, off[f, k] + choice % c]
+        np.testing.assert_array_equal(got[o], pts[f][src])
+        if c <= 1024:   # ResamplePoints property: every original point survives when the cloud is tiled up
+            assert len(np.unique(choice % c)) >= min(c, 1024 - c + 1) or reps > 1
+
+
 # ------------------------------------------------------------------------- stage 3: FPS --
 @pytest.mark.parametrize("shape", [(3, 1024, 256), (2, 1000, 64), (2, 16384, 1024), (2, 40, 40), (1, 7, 3), (1, 20000, 128)])
 def test_fps_vs_oracle_bit_exact(cuda, shape):
