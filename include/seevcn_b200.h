@@ -146,7 +146,7 @@ int seevcn_knn_surface_select(int b, int n_partial, int r, int k, int surface_pt
  * (open3d cluster_dbscan(eps, min_points) -> largest cluster -> tiled to total_pts rows), called with
  * min_points = 2 at see/surface_completion/models/VCN.py:95-98.  min_points in {1, 2}: DBSCAN is then exactly
  * connected components of the eps-graph (strict d < eps, float64), isolated points are noise when
- * min_points = 2.  pts (B,n,3), n <= 1024 -> out (B,total_pts,3): members of the largest component in
+ * min_points = 2.  pts (B,n,3), n <= 8192 -> out (B,total_pts,3): members of the largest component in
  * ascending row order, repeated cyclically; out_count (B) = members (0: everything was noise, rows zero).
  * PARITY UNPINNED (open3d is not vendored). */
 int seevcn_largest_cluster(int b, int n, int total_pts, double eps, int min_points, const float* pts,

@@ -6,12 +6,17 @@
 //
 // With min_points <= 2 DBSCAN is exactly "connected components of the eps-graph": a point is core iff
 // its eps-ball holds min_points points counting itself, any neighbour of a core point is core by
-// symmetry, and isolated points (min_points = 2) are noise.  Per object (one CTA, n <= 1024 points):
-//   1. adjacency as an n x n bit matrix in shared memory (128 KB at n = 1024); squared distances in
-//      float64 with separately rounded operations, strict `<` against eps^2 — open3d's KD-tree works on
-//      float64 copies of the points (nanoflann radius search, `dist < radius^2`)
-//   2. min-label propagation over the bit rows + pointer jumping until nothing changes
-//      (labels converge to the smallest point index of each component = open3d's label order)
+// symmetry, and isolated points (min_points = 2) are noise, i.e. components of size 1.
+//
+// One CTA per object, everything on chip (24 B of shared memory per point, so several CTAs per SM):
+//   1. every unordered pair {i, j} is tested ONCE: thread t owns rows t and n-1-t (n-1 tests per
+//      thread, balanced) and scans j > i four at a time with 128-bit shared-memory loads.  The test is
+//      fp32 with a guard band; only pairs whose fp32 distance lies within 1e-5 relative of eps^2 are
+//      re-evaluated in float64 with separately rounded operations (open3d's KD-tree works on float64
+//      copies of the points, strict `dist < radius^2`), so the decision is the float64 one everywhere.
+//   2. adjacent pairs are merged in a lock-free union-find in shared memory (CAS-link the larger root
+//      under the smaller one, path halving), so a component's root is its smallest point index
+//      = open3d's label order.
 //   3. component sizes, largest (ties -> first label, np.argmax), members in ascending row order,
 //      tiled cyclically to total_pts rows (np.tile(...)[:total_pts]).
 // PARITY UNPINNED: open3d is not vendored (see/surface_completion/setup.py:25 pins 0.14.1).
@@ -19,114 +24,140 @@
 
 namespace {
 
-constexpr int kMaxN = 1024;
-constexpr int kThreads = 1024;
+constexpr int kMaxN = 8192;      // 24 B/point of shared memory
+constexpr int kThreads = 512;
 
-__global__ void __launch_bounds__(kThreads, 1)
-largest_cluster_kernel(int n, int total_pts, double eps2, int min_points, const float* __restrict__ pts,
-                       float* __restrict__ out, int* __restrict__ out_count) {
+__device__ __forceinline__ int uf_find(volatile int* par, int x) {
+    int p = par[x];
+    while (p != x) {
+        const int g = par[p];
+        if (g != p) par[x] = g;   // path halving: only ever rewrites a non-root with a (possibly stale) ancestor
+        x = p; p = g;
+    }
+    return x;
+}
+
+__device__ __forceinline__ void uf_union(volatile int* par, int a, int b) {
+    while (true) {
+        a = uf_find(par, a); b = uf_find(par, b);
+        if (a == b) return;
+        if (a < b) { const int t = a; a = b; b = t; }          // a > b: link the larger root under the smaller
+        if (atomicCAS(const_cast<int*>(par) + a, a, b) == a) return;
+    }
+}
+
+__device__ __forceinline__ bool exact_adjacent(const float* sx, const float* sy, const float* sz, int i, int j, double eps2) {
+    const double dx = __dsub_rn((double)sx[i], (double)sx[j]), dy = __dsub_rn((double)sy[i], (double)sy[j]),
+                 dz = __dsub_rn((double)sz[i], (double)sz[j]);
+    return __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz)) < eps2;
+}
+
+__global__ void __launch_bounds__(kThreads)
+largest_cluster_kernel(int n, int total_pts, double eps2, float lo, float hi, int min_points,
+                       const float* __restrict__ pts, float* __restrict__ out, int* __restrict__ out_count) {
     extern __shared__ __align__(16) unsigned char s_raw[];
-    const int nw = (n + 31) >> 5;
+    const int n4 = (n + 3) & ~3;
     float* sx = reinterpret_cast<float*>(s_raw);
-    float* sy = sx + kMaxN;
-    float* sz = sy + kMaxN;
-    int* lab = reinterpret_cast<int*>(sz + kMaxN);
-    int* size = lab + kMaxN;
-    int* list = size + kMaxN;
-    unsigned* adj = reinterpret_cast<unsigned*>(list + kMaxN);   // n rows x nw words
-    __shared__ int s_best, s_bestsize, s_members;
-    __shared__ int s_warp_cnt[32];
+    float* sy = sx + n4;
+    float* sz = sy + n4;
+    int* par = reinterpret_cast<int*>(sz + n4);
+    int* size = par + n4;
+    int* list = size + n4;
+    __shared__ int s_best, s_bestsize, s_run;
+    __shared__ int s_warp_cnt[kThreads / 32];
 
-    const int b = blockIdx.x, i = threadIdx.x;
+    const int b = blockIdx.x, t = threadIdx.x;
     const float* p = pts + (size_t)b * n * 3;
-    for (int f = i; f < n * 3; f += kThreads) {
+    for (int f = t; f < n * 3; f += kThreads) {
         const float v = p[f]; const int k = f / 3, c = f - 3 * k;
         (c == 0 ? sx : c == 1 ? sy : sz)[k] = v;
     }
-    if (i == 0) { s_best = -1; s_bestsize = 0; }
-    __syncthreads();
-
-    // 1. adjacency row i
-    int deg = 0;
-    if (i < n) {
-        const double xi = sx[i], yi = sy[i], zi = sz[i];
-        for (int w = 0; w < nw; ++w) {
-            unsigned bits = 0;
-            const int jend = min(32, n - w * 32);
-            for (int t = 0; t < jend; ++t) {
-                const int j = w * 32 + t;
-                const double dx = __dsub_rn(xi, (double)sx[j]), dy = __dsub_rn(yi, (double)sy[j]), dz = __dsub_rn(zi, (double)sz[j]);
-                const double d2 = __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz));
-                if (d2 < eps2) bits |= 1u << t;
-            }
-            adj[(size_t)i * nw + w] = bits;
-            deg += __popc(bits);
-        }
+    for (int i = t; i < n4; i += kThreads) {
+        par[i] = i; size[i] = 0;
+        if (i >= n) { sx[i] = 1e30f; sy[i] = 1e30f; sz[i] = 1e30f; }   // padding: infinitely far from everything
     }
-    const bool core = i < n && deg >= min_points;   // deg counts the point itself
-    if (i < kMaxN) { lab[i] = core ? i : 0x7fffffff; size[i] = 0; }
+    if (t == 0) { s_best = -1; s_bestsize = 0; s_run = 0; }
     __syncthreads();
 
-    // 2. min-label propagation + pointer jumping
-    while (true) {
-        bool changed = false;
-        if (core) {
-            int m = lab[i];
-            for (int w = 0; w < nw; ++w) {
-                unsigned bits = adj[(size_t)i * nw + w];
-                while (bits) {
-                    const int t = __ffs(bits) - 1;
-                    bits &= bits - 1;
-                    m = min(m, lab[w * 32 + t]);
+    // 1 + 2. pair tests (fp32 screen, float64 in the guard band) + union-find
+    auto scan_row = [&](int i) {
+        const float xi = sx[i], yi = sy[i], zi = sz[i];
+        for (int j0 = (i + 1) & ~3; j0 < n; j0 += 4) {
+            const float4 X = *reinterpret_cast<const float4*>(sx + j0);
+            const float4 Y = *reinterpret_cast<const float4*>(sy + j0);
+            const float4 Z = *reinterpret_cast<const float4*>(sz + j0);
+            const float xs[4] = {X.x, X.y, X.z, X.w}, ys[4] = {Y.x, Y.y, Y.z, Y.w}, zs[4] = {Z.x, Z.y, Z.z, Z.w};
+            float d2[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const float dx = xi - xs[u], dy = yi - ys[u], dz = zi - zs[u];
+                d2[u] = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
+            }
+            const float dmin = fminf(fminf(d2[0], d2[1]), fminf(d2[2], d2[3]));
+            if (dmin < hi) {
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int j = j0 + u;
+                    if (j > i && d2[u] < hi && (d2[u] < lo || exact_adjacent(sx, sy, sz, i, j, eps2))) {
+                        const int a = const_cast<volatile int*>(par)[i], c = const_cast<volatile int*>(par)[j];
+                        if (a != c) uf_union(par, a, c);
+                    }
                 }
             }
-            if (m < lab[i]) { lab[i] = m; changed = true; }
         }
-        __syncthreads();
-        if (core) {
-            int l = lab[i];
-            for (int hop = 0; hop < 4; ++hop) l = lab[l];   // monotone: racing readers only see smaller labels
-            if (l < lab[i]) { lab[i] = l; changed = true; }
-        }
-        if (!__syncthreads_or(changed)) break;
+    };
+    for (int i = t; 2 * i < n; i += kThreads) {
+        scan_row(i);
+        const int i2 = n - 1 - i;
+        if (i2 != i) scan_row(i2);
     }
+    __syncthreads();
 
     // 3. sizes -> best root (largest, ties -> smallest root) -> member list in ascending order
-    if (core) atomicAdd(&size[lab[i]], 1);
+    for (int i = t; i < n; i += kThreads) atomicAdd(&size[uf_find(par, i)], 1);
     __syncthreads();
-    if (core && lab[i] == i) {
-        const int packed_self = size[i];
-        atomicMax(&s_bestsize, packed_self);
-    }
+    // after this barrier every par[] chain is only read (uf_find may still halve paths: benign)
+    for (int i = t; i < n; i += kThreads)
+        if (const_cast<volatile int*>(par)[i] == i && size[i] >= min_points) atomicMax(&s_bestsize, size[i]);
     __syncthreads();
-    if (core && lab[i] == i && size[i] == s_bestsize) atomicMin(reinterpret_cast<unsigned*>(&s_best), (unsigned)i);
+    for (int i = t; i < n; i += kThreads)
+        if (const_cast<volatile int*>(par)[i] == i && size[i] >= min_points && size[i] == s_bestsize)
+            atomicMin(reinterpret_cast<unsigned*>(&s_best), (unsigned)i);
     __syncthreads();
     const int best = s_best;
-    const bool member = core && best >= 0 && lab[i] == best;
-    const unsigned bal = __ballot_sync(0xffffffffu, member);
-    if (lane_id() == 0) s_warp_cnt[warp_id()] = __popc(bal);
-    __syncthreads();
-    if (warp_id() == 0) {
-        int c = s_warp_cnt[lane_id()];
-        int inc = c;
+    for (int i0 = 0; i0 < n; i0 += kThreads) {
+        const int i = i0 + t;
+        const bool member = best >= 0 && i < n && uf_find(par, i) == best;
+        const unsigned bal = __ballot_sync(0xffffffffu, member);
+        if (lane_id() == 0) s_warp_cnt[warp_id()] = __popc(bal);
+        __syncthreads();
+        if (warp_id() == 0) {
+            const int c = lane_id() < kThreads / 32 ? s_warp_cnt[lane_id()] : 0;
+            int inc = c;
 #pragma unroll
-        for (int off = 1; off < 32; off <<= 1) {
-            const int t = __shfl_up_sync(0xffffffffu, inc, off);
-            if (lane_id() >= off) inc += t;
+            for (int off = 1; off < 32; off <<= 1) {
+                const int v = __shfl_up_sync(0xffffffffu, inc, off);
+                if (lane_id() >= off) inc += v;
+            }
+            if (lane_id() < kThreads / 32) s_warp_cnt[lane_id()] = s_run + inc - c;
+            __syncwarp();
+            if (lane_id() == 31) s_run += inc;
         }
-        s_warp_cnt[lane_id()] = inc - c;
-        if (lane_id() == 31) s_members = inc;
+        __syncthreads();
+        if (member) list[s_warp_cnt[warp_id()] + __popc(bal & ((1u << lane_id()) - 1))] = i;
+        __syncthreads();
     }
-    __syncthreads();
-    if (member) list[s_warp_cnt[warp_id()] + __popc(bal & ((1u << lane_id()) - 1))] = i;
-    __syncthreads();
-    const int m = best >= 0 ? s_members : 0;
-    if (i == 0) out_count[b] = m;
+    const int m = best >= 0 ? s_run : 0;
+    if (t == 0) out_count[b] = m;
     float* o = out + (size_t)b * total_pts * 3;
-    for (int j = i; j < total_pts; j += kThreads) {
-        float x = 0.f, y = 0.f, z = 0.f;
-        if (m > 0) { const int s = list[j % m]; x = sx[s]; y = sy[s]; z = sz[s]; }
-        o[j * 3 + 0] = x; o[j * 3 + 1] = y; o[j * 3 + 2] = z;
+    for (int f = t; f < total_pts * 3; f += kThreads) {
+        float v = 0.f;
+        if (m > 0) {
+            const int j = f / 3, c = f - 3 * j;
+            const int s = list[j % m];
+            v = (c == 0 ? sx : c == 1 ? sy : sz)[s];
+        }
+        o[f] = v;
     }
 }
 
@@ -140,15 +171,19 @@ extern "C" int seevcn_largest_cluster(int b, int n, int total_pts, double eps, i
                    "largest_cluster: min_points=%d; only 1 or 2 (connected components) are supported", min_points);
     if (b == 0) return SEEVCN_OK;
     SEEVCN_REQUIRE(pts && out && out_count, "largest_cluster: null pointer");
-    const int nw = (n + 31) / 32;
-    const size_t smem = (size_t)kMaxN * 4 * 6 + (size_t)n * nw * 4 + 16;
+    const int n4 = (n + 3) & ~3;
+    const size_t smem = (size_t)n4 * 24 + 16;
     static bool attr = false;
     if (!attr) {
-        SEEVCN_CUDA_CHECK(cudaFuncSetAttribute(largest_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        SEEVCN_CUDA_CHECK(cudaFuncSetAttribute(largest_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                               kMaxN * 24 + 16));
         attr = true;
     }
-    const double e = eps;
-    largest_cluster_kernel<<<b, kThreads, smem, as_stream(stream)>>>(n, total_pts, e * e, min_points, pts, out, out_count);
+    const double e2 = eps * eps;
+    // fp32 screen: below `lo` certainly adjacent, at or above `hi` certainly not (fp32 error of the
+    // distance <= ~4 ulp = 2.4e-7 relative); in between the float64 test decides
+    const float lo = (float)(e2 * (1.0 - 1e-5)), hi = (float)(e2 * (1.0 + 1e-5));
+    largest_cluster_kernel<<<b, kThreads, smem, as_stream(stream)>>>(n, total_pts, e2, lo, hi, min_points, pts, out, out_count);
     SEEVCN_LAUNCH_CHECK();
     return SEEVCN_OK;
 }
