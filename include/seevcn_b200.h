@@ -152,6 +152,12 @@ int seevcn_knn_surface_select(int b, int n_partial, int r, int k, int surface_pt
 int seevcn_largest_cluster(int b, int n, int total_pts, double eps, int min_points, const float* pts,
                            float* out, int* out_count, seevcn_stream_t stream);
 
+/* Same result, for clouds the caller knows to be tiled: period (B) int32 DEVICE, pts[b][r] == pts[b][r % period[b]]
+ * (the output of seevcn_knn_surface_select with period = sel_count).  Only the period[b] distinct rows are
+ * clustered, each weighted by its multiplicity; eps > 0. */
+int seevcn_largest_cluster_periodic(int b, int n, int total_pts, double eps, int min_points, const float* pts,
+                                    const int* period, float* out, int* out_count, seevcn_stream_t stream);
+
 /* ------------------------------------------- stages 2+5: VCN forward (canonicalise+MLP) */
 
 /* Folded fp32 parameters, all DEVICE pointers, row-major (out,in) like torch Linear /

@@ -47,6 +47,7 @@ SIGNATURES = {
     "seevcn_knn": (I, [I, I, I, I, P, P, P, P, P]),
     "seevcn_knn_surface_select": (I, [I, I, I, I, I, P, P, P, P, P]),
     "seevcn_largest_cluster": (I, [I, I, I, ctypes.c_double, I, P, P, P, P]),
+    "seevcn_largest_cluster_periodic": (I, [I, I, I, ctypes.c_double, I, P, P, P, P, P]),
     "seevcn_vcn_create": (I, [POINTER(VcnParams), POINTER(c_void_p), P]),
     "seevcn_vcn_destroy": (None, [P]),
     "seevcn_vcn_workspace_bytes": (c_size_t, [P, I, I]),

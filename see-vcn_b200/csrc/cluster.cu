@@ -54,35 +54,43 @@ __device__ __forceinline__ bool exact_adjacent(const float* sx, const float* sy,
 
 __global__ void __launch_bounds__(kThreads)
 largest_cluster_kernel(int n, int total_pts, double eps2, float lo, float hi, int min_points,
-                       const float* __restrict__ pts, float* __restrict__ out, int* __restrict__ out_count) {
+                       const float* __restrict__ pts, const int* __restrict__ period,
+                       float* __restrict__ out, int* __restrict__ out_count) {
     extern __shared__ __align__(16) unsigned char s_raw[];
-    const int n4 = (n + 3) & ~3;
+    const int b = blockIdx.x, t = threadIdx.x;
+    // rows repeat with period m (pts[r] == pts[r % m], the tiling of the kNN surface selection): cluster the
+    // m distinct rows, row u standing for w(u) = #{r < n : r % m == u} rows.  No hint: m = n, w = 1.
+    int m = n;
+    if (period) { m = period[b]; m = m < 1 ? (n > 0 ? 1 : 0) : (m > n ? n : m); }
+    const int m4 = (m + 3) & ~3;
     float* sx = reinterpret_cast<float*>(s_raw);
-    float* sy = sx + n4;
-    float* sz = sy + n4;
-    int* par = reinterpret_cast<int*>(sz + n4);
-    int* size = par + n4;
-    int* list = size + n4;
+    float* sy = sx + m4;
+    float* sz = sy + m4;
+    int* par = reinterpret_cast<int*>(sz + m4);
+    int* size = par + m4;
+    int* list = size + m4;
     __shared__ int s_best, s_bestsize, s_run;
     __shared__ int s_warp_cnt[kThreads / 32];
 
-    const int b = blockIdx.x, t = threadIdx.x;
     const float* p = pts + (size_t)b * n * 3;
-    for (int f = t; f < n * 3; f += kThreads) {
+    for (int f = t; f < m * 3; f += kThreads) {
         const float v = p[f]; const int k = f / 3, c = f - 3 * k;
         (c == 0 ? sx : c == 1 ? sy : sz)[k] = v;
     }
-    for (int i = t; i < n4; i += kThreads) {
+    for (int i = t; i < m4; i += kThreads) {
         par[i] = i; size[i] = 0;
-        if (i >= n) { sx[i] = 1e30f; sy[i] = 1e30f; sz[i] = 1e30f; }   // padding: infinitely far from everything
+        if (i >= m) { sx[i] = 1e30f; sy[i] = 1e30f; sz[i] = 1e30f; }   // padding: infinitely far from everything
     }
     if (t == 0) { s_best = -1; s_bestsize = 0; s_run = 0; }
     __syncthreads();
+    volatile int* vpar = par;
 
-    // 1 + 2. pair tests (fp32 screen, float64 in the guard band) + union-find
+    // 1 + 2. pair tests (fp32 screen, float64 in the guard band) + union-find.  `root` caches the row's
+    // root: once a component has formed, a neighbour costs one compare of its parent against it.
     auto scan_row = [&](int i) {
         const float xi = sx[i], yi = sy[i], zi = sz[i];
-        for (int j0 = (i + 1) & ~3; j0 < n; j0 += 4) {
+        int root = uf_find(vpar, i);
+        for (int j0 = (i + 1) & ~3; j0 < m; j0 += 4) {
             const float4 X = *reinterpret_cast<const float4*>(sx + j0);
             const float4 Y = *reinterpret_cast<const float4*>(sy + j0);
             const float4 Z = *reinterpret_cast<const float4*>(sz + j0);
@@ -95,39 +103,41 @@ largest_cluster_kernel(int n, int total_pts, double eps2, float lo, float hi, in
             }
             const float dmin = fminf(fminf(d2[0], d2[1]), fminf(d2[2], d2[3]));
             if (dmin < hi) {
+                const int4 P = *reinterpret_cast<const int4*>(par + j0);   // may be stale: only a shortcut
+                const int ps[4] = {P.x, P.y, P.z, P.w};
 #pragma unroll
                 for (int u = 0; u < 4; ++u) {
                     const int j = j0 + u;
-                    if (j > i && d2[u] < hi && (d2[u] < lo || exact_adjacent(sx, sy, sz, i, j, eps2))) {
-                        const int a = const_cast<volatile int*>(par)[i], c = const_cast<volatile int*>(par)[j];
-                        if (a != c) uf_union(par, a, c);
+                    if (ps[u] != root && j > i && d2[u] < hi && (d2[u] < lo || exact_adjacent(sx, sy, sz, i, j, eps2))) {
+                        uf_union(vpar, root, j);
+                        root = uf_find(vpar, i);
                     }
                 }
             }
         }
     };
-    for (int i = t; 2 * i < n; i += kThreads) {
+    for (int i = t; 2 * i < m; i += kThreads) {
         scan_row(i);
-        const int i2 = n - 1 - i;
+        const int i2 = m - 1 - i;
         if (i2 != i) scan_row(i2);
     }
     __syncthreads();
 
-    // 3. sizes -> best root (largest, ties -> smallest root) -> member list in ascending order
-    for (int i = t; i < n; i += kThreads) atomicAdd(&size[uf_find(par, i)], 1);
+    // 3. weighted sizes -> best root (largest, ties -> smallest root) -> member list in ascending order
+    for (int i = t; i < m; i += kThreads) atomicAdd(&size[uf_find(vpar, i)], (n - i + m - 1) / m);
     __syncthreads();
-    // after this barrier every par[] chain is only read (uf_find may still halve paths: benign)
-    for (int i = t; i < n; i += kThreads)
-        if (const_cast<volatile int*>(par)[i] == i && size[i] >= min_points) atomicMax(&s_bestsize, size[i]);
+    // from here on par[] is only read (uf_find may still halve paths: benign)
+    for (int i = t; i < m; i += kThreads)
+        if (vpar[i] == i && size[i] >= min_points) atomicMax(&s_bestsize, size[i]);
     __syncthreads();
-    for (int i = t; i < n; i += kThreads)
-        if (const_cast<volatile int*>(par)[i] == i && size[i] >= min_points && size[i] == s_bestsize)
+    for (int i = t; i < m; i += kThreads)
+        if (vpar[i] == i && size[i] >= min_points && size[i] == s_bestsize)
             atomicMin(reinterpret_cast<unsigned*>(&s_best), (unsigned)i);
     __syncthreads();
     const int best = s_best;
-    for (int i0 = 0; i0 < n; i0 += kThreads) {
+    for (int i0 = 0; i0 < m; i0 += kThreads) {
         const int i = i0 + t;
-        const bool member = best >= 0 && i < n && uf_find(par, i) == best;
+        const bool member = best >= 0 && i < m && uf_find(vpar, i) == best;
         const unsigned bal = __ballot_sync(0xffffffffu, member);
         if (lane_id() == 0) s_warp_cnt[warp_id()] = __popc(bal);
         __syncthreads();
@@ -147,15 +157,18 @@ largest_cluster_kernel(int n, int total_pts, double eps2, float lo, float hi, in
         if (member) list[s_warp_cnt[warp_id()] + __popc(bal & ((1u << lane_id()) - 1))] = i;
         __syncthreads();
     }
-    const int m = best >= 0 ? s_run : 0;
-    if (t == 0) out_count[b] = m;
+    // member ROWS in ascending order: period q holds rows q*m + list[k] (k ascending); the last, partial
+    // period keeps a prefix of the list, so rank -> (q, k) = (rank / c, rank % c) for every rank < count
+    const int c = best >= 0 ? s_run : 0;
+    const int count = best >= 0 ? s_bestsize : 0;
+    if (t == 0) out_count[b] = count;
     float* o = out + (size_t)b * total_pts * 3;
     for (int f = t; f < total_pts * 3; f += kThreads) {
         float v = 0.f;
-        if (m > 0) {
-            const int j = f / 3, c = f - 3 * j;
-            const int s = list[j % m];
-            v = (c == 0 ? sx : c == 1 ? sy : sz)[s];
+        if (count > 0) {
+            const int j = f / 3, ch = f - 3 * j;
+            const int s = list[(j % count) % c];
+            v = (ch == 0 ? sx : ch == 1 ? sy : sz)[s];
         }
         o[f] = v;
     }
@@ -163,8 +176,8 @@ largest_cluster_kernel(int n, int total_pts, double eps2, float lo, float hi, in
 
 }  // namespace
 
-extern "C" int seevcn_largest_cluster(int b, int n, int total_pts, double eps, int min_points, const float* pts,
-                                      float* out, int* out_count, seevcn_stream_t stream) {
+static int largest_cluster_launch(int b, int n, int total_pts, double eps, int min_points, const float* pts,
+                                  const int* period, float* out, int* out_count, seevcn_stream_t stream) {
     SEEVCN_REQUIRE(b >= 0 && n >= 0 && total_pts >= 0, "largest_cluster: negative size");
     SEEVCN_REQUIRE(n <= kMaxN, "largest_cluster: n=%d > %d points per object", n, kMaxN);
     SEEVCN_REQUIRE(min_points >= 1 && min_points <= 2,
@@ -183,7 +196,20 @@ extern "C" int seevcn_largest_cluster(int b, int n, int total_pts, double eps, i
     // fp32 screen: below `lo` certainly adjacent, at or above `hi` certainly not (fp32 error of the
     // distance <= ~4 ulp = 2.4e-7 relative); in between the float64 test decides
     const float lo = (float)(e2 * (1.0 - 1e-5)), hi = (float)(e2 * (1.0 + 1e-5));
-    largest_cluster_kernel<<<b, kThreads, smem, as_stream(stream)>>>(n, total_pts, e2, lo, hi, min_points, pts, out, out_count);
+    largest_cluster_kernel<<<b, kThreads, smem, as_stream(stream)>>>(n, total_pts, e2, lo, hi, min_points, pts, period, out,
+                                                                    out_count);
     SEEVCN_LAUNCH_CHECK();
     return SEEVCN_OK;
+}
+
+extern "C" int seevcn_largest_cluster(int b, int n, int total_pts, double eps, int min_points, const float* pts,
+                                      float* out, int* out_count, seevcn_stream_t stream) {
+    return largest_cluster_launch(b, n, total_pts, eps, min_points, pts, nullptr, out, out_count, stream);
+}
+
+extern "C" int seevcn_largest_cluster_periodic(int b, int n, int total_pts, double eps, int min_points, const float* pts,
+                                               const int* period, float* out, int* out_count, seevcn_stream_t stream) {
+    SEEVCN_REQUIRE(period || b == 0, "largest_cluster_periodic: null period");
+    SEEVCN_REQUIRE(eps > 0.0, "largest_cluster_periodic: eps must be > 0 (duplicate rows are merged)");
+    return largest_cluster_launch(b, n, total_pts, eps, min_points, pts, period, out, out_count, stream);
 }

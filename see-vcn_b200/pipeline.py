@@ -72,11 +72,12 @@ class CompletionPipeline:
         if self.model_name == "VCN_CN":
             in_dict["gt_boxes"] = boxes[obj_frame.long(), obj_box.long()].contiguous()
         coarse = self.model(in_dict)["coarse"]
-        surface = get_partial_mesh_batch(inp, coarse, k=self.sel_k, surface_pts=self.resample_num)
-        out.update(input=inp, coarse=coarse, surface=surface, obj_frame_dev=obj_frame)
+        surface, sel_count = get_partial_mesh_batch(inp, coarse, k=self.sel_k, surface_pts=self.resample_num,
+                                                    return_count=True)
+        out.update(input=inp, coarse=coarse, surface=surface, surface_count=sel_count, obj_frame_dev=obj_frame)
         if self.cluster_eps is not None:   # models/VCN.py:95-98
             out["clustered"] = get_largest_cluster_batch(surface, eps=self.cluster_eps, min_points=2,
-                                                         total_pts=coarse.shape[1])
+                                                         total_pts=coarse.shape[1], period=sel_count)
         return out
 
     @torch.no_grad()
@@ -95,3 +96,93 @@ class CompletionPipeline:
         coords, feats, nums = dynamic_voxelize(vox_pts, *self.voxel_cfg, sort=True, batch_size=F)
         out.update(voxel_points=vox_pts, voxel_coords=coords, voxel_features=feats, voxel_num_points=nums)
         return out
+
+
+class HostStream:
+    """The public host-buffer entry of the path: pinned HOST frames in, pinned HOST results out.
+
+    The reference's driver (``sc_multiproc.py:60-94``) reads a frame from disk, completes its objects and
+    writes a .pcd; here a batch of frames arrives in pinned memory and the completed clouds + voxel tensors
+    leave in pinned memory.  Three CUDA streams: the H2D copy of batch i+1 and the D2H copy of batch i-1
+    overlap the kernels of batch i (the copy engines are otherwise idle; every batch still pays its own
+    copies inside the caller's timed region).
+
+        hs = HostStream(pipe, frames, pts_per_frame, boxes_per_frame)
+        for res in hs.run(batches):      # batches: iterable of (points_pinned (F,P,3), boxes_pinned (F,T,7))
+            res["clustered"], res["voxel_coords"], ...   # pinned host views, valid until `depth` batches later
+    """
+    KEYS = ("clustered", "voxel_coords", "voxel_features", "voxel_num_points")
+
+    def __init__(self, pipe, frames, pts_per_frame, boxes_per_frame, depth=2):
+        self.pipe, self.depth = pipe, depth
+        dev = pipe.device
+        self.dev = dev
+        F, P, T, S = frames, pts_per_frame, boxes_per_frame, pipe.resample_num
+        max_obj, max_rows = F * T, F * P + F * T * S
+        self.d_pts = [torch.empty((F, P, 3), dtype=torch.float32, device=dev) for _ in range(depth)]
+        self.d_boxes = [torch.empty((F, T, 7), dtype=torch.float32, device=dev) for _ in range(depth)]
+        pin = lambda shape, dt: torch.empty(shape, dtype=dt).pin_memory()   # noqa: E731
+        self.h_out = [{"clustered": pin((max_obj, S, 3), torch.float32), "voxel_coords": pin((max_rows, 4), torch.int32),
+                       "voxel_features": pin((max_rows, 3), torch.float32), "voxel_num_points": pin((max_rows,), torch.int32)}
+                      for _ in range(depth)]
+        self.s_h2d, self.s_d2h = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
+        self.ev_in = [torch.cuda.Event() for _ in range(depth)]       # H2D of the slot landed
+        self.ev_free = [torch.cuda.Event() for _ in range(depth)]     # kernels finished reading the slot's inputs
+        self.ev_out = [torch.cuda.Event() for _ in range(depth)]      # D2H of the slot's results landed
+        self.h2d_bytes = self.d2h_bytes = 0
+
+    def _upload(self, slot, pts_pin, boxes_pin):
+        with torch.cuda.stream(self.s_h2d):
+            self.s_h2d.wait_event(self.ev_free[slot])
+            self.d_pts[slot].copy_(pts_pin, non_blocking=True)
+            self.d_boxes[slot].copy_(boxes_pin, non_blocking=True)
+            self.ev_in[slot].record(self.s_h2d)
+        self.h2d_bytes += pts_pin.numel() * 4 + boxes_pin.numel() * 4
+
+    def _download(self, slot, out):
+        views = {}
+        compute = torch.cuda.current_stream(self.dev)
+        done = torch.cuda.Event(); done.record(compute)
+        with torch.cuda.stream(self.s_d2h):
+            self.s_d2h.wait_event(done)
+            for k in self.KEYS:
+                src = out.get(k)
+                if src is None:
+                    src = out["surface"] if k == "clustered" else None
+                n = src.shape[0]
+                dst = self.h_out[slot][k][:n]
+                dst.copy_(src, non_blocking=True)
+                views[k] = dst
+                self.d2h_bytes += src.numel() * src.element_size()
+            self.ev_out[slot].record(self.s_d2h)
+        views["_keepalive"] = out      # device tensors stay referenced until the copy has landed
+        return views
+
+    def run(self, batches, seed=0):
+        compute = torch.cuda.current_stream(self.dev)
+        it = iter(batches)
+        nxt = next(it, None)
+        if nxt is None:
+            return
+        for e in self.ev_free:
+            e.record(compute)
+        self._upload(0, *nxt)
+        i, pending = 0, None
+        while nxt is not None:
+            slot = i % self.depth
+            nxt = next(it, None)
+            if nxt is not None:
+                self._upload((i + 1) % self.depth, *nxt)         # overlaps the kernels below
+            compute.wait_event(self.ev_in[slot])
+            out = self.pipe.run(self.d_pts[slot], self.d_boxes[slot], seed=seed)
+            self.ev_free[slot].record(compute)
+            res = self._download(slot, out)                       # overlaps the next batch's kernels
+            if pending is not None:
+                self.ev_out[pending[0]].synchronize()
+                pending[1].pop("_keepalive", None)
+                yield pending[1]
+            pending = (slot, res)
+            i += 1
+        self.ev_out[pending[0]].synchronize()
+        pending[1].pop("_keepalive", None)
+        yield pending[1]

@@ -256,6 +256,29 @@ def test_largest_cluster_vs_oracle(cuda):
     assert wcnt.max() < 1024 and wcnt.min() >= 1
 
 
+@pytest.mark.parametrize("scale", [1.0, 0.05])
+def test_largest_cluster_periodic_vs_oracle(cuda, scale):
+    """tiled clouds (the kNN surface selection's output) with the period hint: same result as clustering all rows.
+    scale 0.05 squeezes the cloud so that every pair is adjacent (what a random-init VCN produces)."""
+    _, dense, _ = synth.make_object_clouds(52, 6, 64, 1024)
+    dense = (dense - dense.mean(axis=1, keepdims=True)) * scale + dense.mean(axis=1, keepdims=True)
+    periods = np.array([1, 7, 178, 512, 1000, 1024], dtype=np.int32)
+    pc = np.stack([np.tile(dense[b, :m], (1024 // m + 1, 1))[:1024] for b, m in enumerate(periods)]).astype(np.float32)
+    pc[2, 100:130] += 40.0       # a second blob and some isolated rows inside the period
+    pc[2] = np.tile(pc[2, :178], (6, 1))[:1024]
+    pc[4, 990:1000] = 500.0 + 3.0 * np.arange(10, dtype=np.float32)[:, None]
+    pc[4] = np.tile(pc[4, :1000], (2, 1))[:1024]
+    for eps, mp, total in ((0.3, 2, 1024), (0.2, 1, 1024), (0.3, 2, 2500)):
+        out, cnt = get_largest_cluster_batch(dev(pc, cuda), eps=eps, min_points=mp, total_pts=total, return_count=True,
+                                             period=dev(periods, cuda))
+        plain, pcnt = get_largest_cluster_batch(dev(pc, cuda), eps=eps, min_points=mp, total_pts=total, return_count=True)
+        want, wcnt = oracle.get_largest_cluster_batch(pc, eps=eps, min_points=mp, total_pts=total)
+        np.testing.assert_array_equal(pcnt.cpu().numpy(), wcnt)
+        np.testing.assert_array_equal(plain.cpu().numpy(), want)
+        np.testing.assert_array_equal(cnt.cpu().numpy(), wcnt)
+        np.testing.assert_array_equal(out.cpu().numpy(), want)
+
+
 def test_vcn_inference_wrapper(cuda, golden):
     """host numpy in / out through the reference-shaped VCN.inference"""
     from seevcn_b200.see.surface_completion.models.VCN import VCN
