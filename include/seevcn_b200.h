@@ -209,6 +209,11 @@ int seevcn_vcn_forward(const seevcn_vcn_model* model, int num_obj, int n_pts,
                        void* workspace, size_t workspace_bytes, int precision,
                        seevcn_stream_t stream);
 
+/* Selects how the bf16 path (precision 0) runs the per-point shared-MLP chains: 1 (default) = fused tcgen05
+ * chains with the activations kept in tensor memory (vcn_chain.cu); 0 = one tcgen05 GEMM launch per layer
+ * (vcn_tc.cu).  Both compute the same layers; returns the previous setting.  Process-wide, not thread-safe. */
+int seevcn_set_fused_chains(int on);
+
 /* One shared-MLP layer on the tcgen05 path, standalone (the building block of seevcn_vcn_forward;
  * ref: nn.Conv1d(k=1) / nn.Linear as used in VCN_VC.py:116-131):
  *   Y[r, c] = act(sum_k bf16(X[r,k]) * bf16(W[c,k]) + bias[c] + obj_bias[r / rows_per_obj, c])   (fp32 accumulate)

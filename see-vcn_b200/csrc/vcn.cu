@@ -16,12 +16,23 @@
 //    activations of pose_encoder.4 / mlp_conv2.3 are never written;
 //  * rotate/centre/canonicalise are fused into the kernels that read or write the points.
 #include <vector>
+#include <stdlib.h>
 #include "vcn_common.cuh"
 
 int vcn_linear_tc(const LinearW& L, int rows, const __nv_bfloat16* X, int ldx, const float* obj_bias,
                   int rows_per_obj, int act, __nv_bfloat16* Y, int ldy, float* Yf32, float* colmax,
                   cudaStream_t st);   // vcn_tc.cu
 int vcn_pointwise3(const LinearW& L, size_t rows, const float* X, int act, __nv_bfloat16* Y, int ldy, cudaStream_t st);
+size_t vcn_fc_part_bytes(int rows, int cout, int cin);
+int vcn_fc_tc(const LinearW& L, int rows, const __nv_bfloat16* X, int ldx, int act, float* Yf32, __nv_bfloat16* Yb16, int ldb,
+              float* part, cudaStream_t st);
+// vcn_chain.cu: fused per-point chains (tcgen05, activations kept in TMEM)
+int vcn_chain_pose(const seevcn_vcn_model* M, int num_obj, int n, const float* input, const VcnFrame* frames,
+                   float* pose_feat, cudaStream_t st);
+int vcn_chain_enc1(const seevcn_vcn_model* M, int num_obj, int n, const float* input, const VcnFrame* frames,
+                   const VcnPose* poses, __nv_bfloat16* F, float* g256, cudaStream_t st);
+int vcn_chain_enc2(const seevcn_vcn_model* M, int num_obj, int n, const __nv_bfloat16* F, const float* obj_bias,
+                   float* feat, cudaStream_t st);
 
 namespace {
 
@@ -73,7 +84,7 @@ vcn_frame_kernel(int n, int viewer_centred, const float* __restrict__ input, con
             fr.mean[0] = m0; fr.mean[1] = m1; fr.mean[2] = m2; fr.pad = 0.f;
             frames[o] = fr;
         }
-        for (int i = threadIdx.x; i < n; i += 256) {
+        if (out) for (int i = threadIdx.x; i < n; i += 256) {
             const float x = p[i * 3 + 0], y = p[i * 3 + 1], z = p[i * 3 + 2];
             q[i * 3 + 0] = (x * ca - y * sa) - m0;
             q[i * 3 + 1] = (x * sa + y * ca) - m1;
@@ -88,7 +99,7 @@ vcn_frame_kernel(int n, int viewer_centred, const float* __restrict__ input, con
             fr.mean[0] = c0; fr.mean[1] = c1; fr.mean[2] = c2; fr.pad = 0.f;
             frames[o] = fr;
         }
-        for (int i = threadIdx.x; i < n; i += 256) {
+        if (out) for (int i = threadIdx.x; i < n; i += 256) {
             const float x = p[i * 3 + 0] - c0, y = p[i * 3 + 1] - c1, z = p[i * 3 + 2] - c2;
             q[i * 3 + 0] = (x * ca - y * sa) / len;
             q[i * 3 + 1] = (x * sa + y * ca) / len;
@@ -183,6 +194,11 @@ vcn_output_kernel(int m, int viewer_centred, const float* __restrict__ coarse_cn
 __global__ void fill_kernel(size_t n, float v, float* p) {
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) p[i] = v;
+}
+
+__global__ void bf16_to_f32_kernel(size_t n, const __nv_bfloat16* __restrict__ src, float* __restrict__ dst) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) dst[i] = __bfloat162float(src[i]);
 }
 
 __global__ void f32_to_bf16_kernel(size_t rows, int cols, const float* __restrict__ src, int lds,
@@ -302,11 +318,11 @@ int fill(float* p, size_t n, float v, cudaStream_t st) {
 
 // ----------------------------------------------------------------- workspace layout --
 constexpr int kChunkObjF32 = 16;   // objects per pass of the fp32 path (activations 2 x 32 MB at N=1024)
-constexpr int kChunkObjTC = 64;    // bf16 path: 64 x 1024 x 512 x 2 B = 64 MB per activation buffer (L2-sized)
+constexpr int kChunkObjTC = 128;   // bf16 path: 128 x 1024 x 256 x 2 B = 64 MB of enc1 output per pass (L2-sized)
 
 struct VcnWs {
     size_t frames, poses, pts3, pose_feat, h512, rel, g256, objbias, feat, fc_a, fc_b, coarse_cn, act_a, act_b,
-        fcx_a, fcx_b, total;
+        fcx_a, fcx_b, fc_part, total;
     int chunk;
 };
 
@@ -335,6 +351,12 @@ VcnWs vcn_ws(int num_obj, int n, int num_coarse, int precision) {
     w.act_b = take(rows * 512 * esz);
     w.fcx_a = take(B * 1024 * 2);    // bf16 path: bf16 copies of the per-object feature vectors
     w.fcx_b = take(B * 1024 * 2);
+    {   // split-K partial sums of the per-object FC layers: the largest of the layers that use them
+        size_t pb = vcn_fc_part_bytes((int)B, 1024, 1024);
+        const size_t p4 = vcn_fc_part_bytes((int)B, 3 * num_coarse, 1024), p5 = vcn_fc_part_bytes((int)B, 512, 1024);
+        pb = p4 > pb ? p4 : pb; pb = p5 > pb ? p5 : pb;
+        w.fc_part = take(pb);
+    }
     w.total = o;
     return w;
 }
@@ -417,6 +439,18 @@ extern "C" size_t seevcn_vcn_workspace_bytes(const seevcn_vcn_model* model, int 
     return a > b ? a : b;
 }
 
+// SEEVCN_FUSED_CHAINS=0 selects the layer-by-layer tcgen05 kernels (vcn_tc.cu) instead of the fused chains
+static int g_fused_chains = -1;
+static bool fused_chains_enabled() {
+    if (g_fused_chains < 0) { const char* e = getenv("SEEVCN_FUSED_CHAINS"); g_fused_chains = (e && e[0] == '0') ? 0 : 1; }
+    return g_fused_chains == 1;
+}
+extern "C" int seevcn_set_fused_chains(int on) {
+    const int prev = fused_chains_enabled() ? 1 : 0;
+    g_fused_chains = on ? 1 : 0;
+    return prev;
+}
+
 #define TRY(expr) do { int _rc = (expr); if (_rc != SEEVCN_OK) return _rc; } while (0)
 
 extern "C" int seevcn_vcn_forward(const seevcn_vcn_model* M, int num_obj, int n, const float* input,
@@ -477,12 +511,60 @@ extern "C" int seevcn_vcn_forward(const seevcn_vcn_model* M, int num_obj, int n,
     auto fc_layer = [&](const LinearW& L, const float* X, int act, float* Y, __nv_bfloat16* xb) -> int {
         return fc_rows(L, num_obj, X, act, Y, xb);
     };
+    float* fc_part = reinterpret_cast<float*>(ws + w.fc_part);
+    auto to_bf16 = [&](const float* X, int rows, int cols, __nv_bfloat16* xb) -> int {
+        const size_t tot = (size_t)rows * cols;
+        f32_to_bf16_kernel<<<(unsigned)div_up(tot, (size_t)256), 256, 0, st>>>(rows, cols, X, cols, xb, cols);
+        SEEVCN_LAUNCH_CHECK();
+        return SEEVCN_OK;
+    };
+    // num_coarse with 3*num_coarse not a multiple of 128: last FC on CUDA cores from the fp32 copy of its input
+    auto linear_f32_from_bf16 = [&](const LinearW& L, int rows, const __nv_bfloat16* xb, float* Y) -> int {
+        bf16_to_f32_kernel<<<(unsigned)div_up((size_t)rows * L.cin, (size_t)256), 256, 0, st>>>((size_t)rows * L.cin, xb, fc_b);
+        SEEVCN_LAUNCH_CHECK();
+        return linear_f32(L, rows, fc_b, L.cin, nullptr, 1, ACT_NONE, Y, L.cout, nullptr, st);
+    };
     auto pts_in = [&](int) -> int { return SEEVCN_OK; };
     const void* ptsX = pts3;
     const int ptsLd = 3;
     void* A = tc ? static_cast<void*>(actA16) : static_cast<void*>(actA);
     void* Bf = tc ? static_cast<void*>(actB16) : static_cast<void*>(actB);
 
+    if (tc && fused_chains_enabled()) {
+        // ---- fused tcgen05 chains (vcn_chain.cu): one launch per chain, activations stay in TMEM ----
+        if (M->viewer_centred) {
+            vcn_frame_kernel<<<num_obj, 256, 0, st>>>(n, 1, input, nullptr, frames, nullptr);
+            SEEVCN_LAUNCH_CHECK();
+            TRY(fill(pose_feat, (size_t)num_obj * 1024, NEG_INF, st));
+            TRY(vcn_chain_pose(M, num_obj, n, input, frames, pose_feat, st));
+            TRY(to_bf16(pose_feat, num_obj, 1024, fcxA));
+            TRY(vcn_fc_tc(M->pose_fc0, num_obj, fcxA, 1024, ACT_LEAKY, h512, nullptr, 0, fc_part, st));
+            TRY(linear_f32(M->pose_fc2, num_obj, h512, 512, nullptr, 1, ACT_NONE, rel, 16, nullptr, st));
+            vcn_pose_kernel<<<div_up(num_obj, 128), 128, 0, st>>>(num_obj, rel, 16, frames, poses, reg_rot, reg_centre);
+            SEEVCN_LAUNCH_CHECK();
+        } else {
+            vcn_frame_kernel<<<num_obj, 256, 0, st>>>(n, 0, input, gt_boxes, frames, nullptr);
+            SEEVCN_LAUNCH_CHECK();
+        }
+        TRY(fill(g256, (size_t)num_obj * 256, NEG_INF, st));
+        TRY(fill(feat, (size_t)num_obj * 1024, NEG_INF, st));
+        for (int o0 = 0; o0 < num_obj; o0 += w.chunk) {
+            const int nb = std::min(w.chunk, num_obj - o0);
+            TRY(vcn_chain_enc1(M, nb, n, input + (size_t)o0 * n * 3, frames + o0, poses + o0, actA16, g256 + (size_t)o0 * 256, st));
+            TRY(to_bf16(g256 + (size_t)o0 * 256, nb, 256, fcxA));
+            TRY(vcn_fc_tc(M->enc2_0_global, nb, fcxA, 256, ACT_NONE, objbias + (size_t)o0 * 512, nullptr, 0, fc_part, st));
+            TRY(vcn_chain_enc2(M, nb, n, actA16, objbias + (size_t)o0 * 512, feat + (size_t)o0 * 1024, st));
+        }
+        TRY(to_bf16(feat, num_obj, 1024, fcxA));
+        TRY(vcn_fc_tc(M->fc0, num_obj, fcxA, 1024, ACT_RELU, nullptr, fcxB, 1024, fc_part, st));
+        TRY(vcn_fc_tc(M->fc2, num_obj, fcxB, 1024, ACT_RELU, nullptr, fcxA, 1024, fc_part, st));
+        if ((3 * M->num_coarse) % 128 == 0) TRY(vcn_fc_tc(M->fc4, num_obj, fcxA, 1024, ACT_NONE, coarse_cn, nullptr, 0, fc_part, st));
+        else TRY(linear_f32_from_bf16(M->fc4, num_obj, fcxA, coarse_cn));
+        vcn_output_kernel<<<dim3(div_up(M->num_coarse, 256), num_obj), 256, 0, st>>>(M->num_coarse, M->viewer_centred,
+                                                                                     coarse_cn, frames, poses, coarse);
+        SEEVCN_LAUNCH_CHECK();
+        return SEEVCN_OK;
+    }
     if (M->viewer_centred) {
         TRY(fill(pose_feat, (size_t)num_obj * 1024, NEG_INF, st));
         for (int o0 = 0; o0 < num_obj; o0 += w.chunk) {

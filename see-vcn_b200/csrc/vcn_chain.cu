@@ -1,0 +1,588 @@
+// Stage 5 — the VCN per-point MLP chains, FUSED: one persistent kernel runs a whole chain of shared-MLP
+// layers on a tile of 128 points without the activations ever leaving the SM.
+//
+//   pose chain  (VCN_VC.py:116-123,191)   xyz -> 64 -> 128 -> 1024, max over points      -> pose_feat
+//   enc1 chain  (VCN_VC.py:86-89,96-98)   xyz -> 128 -> 256, store f (bf16) + max        -> global feature
+//   enc2 chain  (VCN_VC.py:90-93,100-102) f(256) -> 512 (+ per-object bias) -> 1024, max -> shape feature
+//
+// Orientation: a TILE is 128 points = the 128 TMEM lanes (UMMA M); output channels are the UMMA N
+// dimension, 128 per accumulator.  That makes a layer's output — one TMEM lane per point, channels along
+// the columns — exactly the A operand of the next layer once it is rounded to bf16 and packed two per
+// column, so layer l+1 is issued as tcgen05.mma with A FROM TENSOR MEMORY (".ts" form): activations go
+// accumulator -> registers (bias, activation, bf16 pack) -> TMEM and never touch shared memory or HBM.
+// Only the weights stream through shared memory (TMA, SWIZZLE_128B, mbarrier ring), so the shared-memory
+// operand traffic per MMA is half that of the smem x smem form.
+//
+// The K = 3 input layer is CUDA-core work: the 8 point warps compute it straight from the raw points
+// (canonicalisation fused, VCN_VC.py:185-200) and store it to TMEM as the first A operand.
+//
+// Max-pool over points = max over TMEM lanes: a transposing shuffle butterfly inside each warp (31
+// shuffles per 32x32 block), then shared-memory atomics across the 4 lane quadrants and the tiles of one
+// object that a CTA owns (tiles are dealt out in contiguous runs), then one global atomic per channel.
+//
+// Warp roles (640 threads, one CTA per SM, persistent):
+//   warp 0      TMA producer (weight k-blocks; enc2: also the 128 x 256 input tile)
+//   warps 1, 3  MMA issuers (one elected thread each).  A single thread sustains one tcgen05.mma per ~94-120
+//               cycles whatever N is, and an M128 x N128 x K16 MMA only occupies the tensor pipe for 64
+//               (tools/microbench/mma_rate.cu: 2230 MAC/clk/SM with one issuer, 3710 with two), so the two
+//               accumulators are driven by two issuers: warp 1 owns accumulator 0 (even chunks), warp 3
+//               accumulator 1 (odd chunks); the weight ring interleaves the k-blocks of the two chunks in flight
+//   warp 2      TMEM allocator (512 columns: 2 accumulators x 128 | activations up to 256 | input 32)
+//   warps 4-19  point warps: lane quadrant q = warp % 4, column quarter cq = (warp - 4) / 4 (32 of the 128
+//               accumulator columns): 4 warps per scheduler keep the latency-bound producer / epilogue code busy
+#include <cuda.h>
+#include <stdlib.h>
+#include <vector>
+#include "vcn_common.cuh"
+#include "tc_ptx.cuh"
+
+using namespace tcptx;
+
+namespace {
+
+constexpr int TM = 128;                    // points per tile (UMMA M)
+constexpr int TN = 128;                    // channels per accumulator (UMMA N)
+constexpr int BK = 64;                     // K elements per weight stage (128 B = one swizzle row)
+constexpr int UMMA_K = 16;
+constexpr int W_STAGE_BYTES = TN * BK * 2; // 16 KB
+constexpr int NUM_POINT_WARPS = 16;         // 4 lane quadrants x 4 column quarters of a 128-column accumulator
+constexpr int NUM_POINT_THREADS = NUM_POINT_WARPS * 32;
+constexpr int NUM_THREADS = 128 + NUM_POINT_THREADS;
+constexpr int TMEM_COLS = 512;
+constexpr uint32_t ACC_COL = 0;            // 2 x 128 fp32 accumulator columns
+constexpr uint32_t H_COL = 256;            // activations (A operand of the last layer), KH / 2 columns
+
+// Instruction descriptor: c F32, a/b BF16, K-major, N = 128, M = 128
+constexpr uint32_t kIdesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(TN >> 3) << 17) | ((uint32_t)(TM >> 4) << 24);
+
+enum { CHAIN_POSE = 0, CHAIN_ENC1 = 1, CHAIN_ENC2 = 2 };
+enum { XF_VIEW = 0, XF_CANON = 1, XF_GT = 2 };   // producer transform of the raw points
+
+template <int MODE> struct Cfg;
+template <> struct Cfg<CHAIN_POSE> {
+    static constexpr int K0 = 64, C1 = 128, C2 = 1024, KH = 128, STAGES = 8;
+    static constexpr bool PRODUCER = true, HAS_L1 = true, X_SMEM = false, STORE = false;
+};
+template <> struct Cfg<CHAIN_ENC1> {
+    static constexpr int K0 = 128, C1 = 0, C2 = 256, KH = 128, STAGES = 8;
+    static constexpr bool PRODUCER = true, HAS_L1 = false, X_SMEM = false, STORE = true;
+};
+template <> struct Cfg<CHAIN_ENC2> {
+    static constexpr int K0 = 256, C1 = 512, C2 = 1024, KH = 512, STAGES = 8;
+    static constexpr bool PRODUCER = false, HAS_L1 = true, X_SMEM = true, STORE = false;
+};
+
+struct ChainArgs {
+    int num_obj, n, tiles_per_obj, num_tiles;
+    const float* input;            // (num_obj, n, 3) raw points (producer chains)
+    const float* gt_boxes;         // unused (frames carry the GT transform)
+    const VcnFrame* frames;
+    const VcnPose* poses;
+    int xform;
+    const float* w0; const float* b0; int act0;     // producer layer (K0, 3), (K0)
+    const float* b1; const float* obj_bias; int act1;   // first GEMM: bias (C1), per-object bias (num_obj, C1)
+    const float* b2;               // last GEMM bias (C2)
+    __nv_bfloat16* F; int ldf;     // STORE: last GEMM output, bf16 (rows, ldf)
+    float* colmax;                 // (num_obj, C2), pre-filled with -inf
+    long long* prof;               // dbg & 4: per-CTA cycle counters of issuer 0 [total, wait_a, wait_acc, wait_w, wait_h]
+    int dbg;                       // timing experiments only (SEEVCN_CHAIN_DBG): 1 = no weight reloads, 2 = no max epilogue math
+};
+
+template <int MODE>
+constexpr int chain_smem_bytes() {
+    using C = Cfg<MODE>;
+    return 1024 /*align*/ + (C::X_SMEM ? TM * C::K0 * 2 : 0) + C::STAGES * W_STAGE_BYTES + C::C2 * 4 /*tilemax*/ +
+           C::C2 * 4 /*bias2*/ + (C::HAS_L1 ? C::C1 * 4 : 0) /*bias1*/ + (C::PRODUCER ? C::K0 * 16 : 0) /*w0*/ + 768 /*barriers*/;
+}
+
+__device__ __forceinline__ uint32_t fkey(float f) {      // order-preserving float -> uint
+    const uint32_t b = __float_as_uint(f);
+    return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+}
+__device__ __forceinline__ float fkey_inv(uint32_t k) {
+    return __uint_as_float((k & 0x80000000u) ? (k ^ 0x80000000u) : ~k);
+}
+__device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
+    __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);    // .x = lo (low 16 bits)
+    return *reinterpret_cast<uint32_t*>(&v);
+}
+__device__ __forceinline__ float act_apply(float v, float slope) { return fmaxf(v, slope * v); }
+__device__ __forceinline__ float act_slope(int act) { return act == ACT_RELU ? 0.f : act == ACT_LEAKY ? 0.01f : 1.f; }
+
+// max over the 32 lanes of a warp of 16 packed bf16x2 registers (32 channels); lane l ends up with register
+// l & 15, i.e. channels 2(l & 15) and 2(l & 15) + 1.  Rounding to bf16 BEFORE the max is exact for every consumer of the pooled
+// features: they are all rounded to bf16 for the next tensor-core layer, and rounding is monotone.
+__device__ __forceinline__ uint32_t hmax2_u32(uint32_t x, uint32_t y) {
+    __nv_bfloat162 r = __hmax2(*reinterpret_cast<__nv_bfloat162*>(&x), *reinterpret_cast<__nv_bfloat162*>(&y));
+    return *reinterpret_cast<uint32_t*>(&r);
+}
+__device__ __forceinline__ uint32_t warp_transpose_max2(uint32_t (&r)[16], int lane) {
+    // 16 registers x 32 lanes: butterfly over lane bits 3..0 leaves register (lane & 15) reduced over the 16 lanes that
+    // share lane bit 4; one more exchange across bit 4 completes it (lanes l and l ^ 16 then hold the same value)
+#pragma unroll
+    for (int off = 8; off >= 1; off >>= 1) {
+        const bool up = (lane & off) != 0;
+#pragma unroll
+        for (int i = 0; i < off; ++i) {
+            const uint32_t keep = up ? r[i + off] : r[i];
+            const uint32_t send = up ? r[i] : r[i + off];
+            r[i] = hmax2_u32(keep, __shfl_xor_sync(0xffffffffu, send, off));
+        }
+    }
+    return hmax2_u32(r[0], __shfl_xor_sync(0xffffffffu, r[0], 16));
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+vcn_chain_kernel(const __grid_constant__ CUtensorMap tmap_w1, const __grid_constant__ CUtensorMap tmap_w2,
+                 const __grid_constant__ CUtensorMap tmap_x, const ChainArgs a) {
+    using C = Cfg<MODE>;
+    constexpr int STAGES = C::STAGES;
+    constexpr int N1 = C::HAS_L1 ? C::C1 / TN : 0;     // accumulator chunks of the first GEMM
+    constexpr int N2 = C::C2 / TN;                     // ... of the last GEMM
+    constexpr int KB1 = C::K0 / BK, KB2 = C::KH / BK;  // weight k-blocks per chunk
+    constexpr uint32_t HA_COL = H_COL + C::KH / 2;     // producer output when a first GEMM follows (pose chain), 2 buffers
+    // The point warps run the producer one tile AHEAD of the epilogues (software pipeline), so its target is
+    // double buffered: pose -> two input buffers at HA_COL, enc1 -> two activation buffers at H_COL.
+    constexpr bool HA_DOUBLE = C::PRODUCER && C::HAS_L1, H_DOUBLE = C::PRODUCER && !C::HAS_L1;
+
+    extern __shared__ uint8_t smem_raw[];
+    // 1024-byte alignment (SWIZZLE_128B) by OFFSET, so the compiler still knows these pointers are shared memory
+    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    uint8_t* smem_x = smem;                                                    // [KB1][128 rows][64] bf16 (enc2)
+    uint8_t* smem_w = smem + (C::X_SMEM ? TM * C::K0 * 2 : 0);                 // ring
+    uint32_t* tilemax = reinterpret_cast<uint32_t*>(smem_w + STAGES * W_STAGE_BYTES);
+    float* s_bias2 = reinterpret_cast<float*>(tilemax + C::C2);
+    float* s_bias1 = s_bias2 + C::C2;
+    float4* s_w0 = reinterpret_cast<float4*>(s_bias1 + (C::HAS_L1 ? C::C1 : 0));
+    uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(s_w0) + (C::PRODUCER ? C::K0 * 16 : 0));
+    uint64_t* w_full = bars;                    // [STAGES]
+    uint64_t* w_empty = bars + STAGES;          // [STAGES]
+    uint64_t* acc_full = bars + 2 * STAGES;     // [2]
+    uint64_t* acc_empty = acc_full + 2;         // [2]
+    uint64_t* x_full = acc_empty + 2;           // input tile landed in smem (enc2)
+    uint64_t* x_empty = x_full + 1;             // first GEMM finished reading it
+    uint64_t* ha_full = x_empty + 1;            // [2] producer output in TMEM (pose), double buffered
+    uint64_t* ha_free = ha_full + 2;            // [2]
+    uint64_t* h_full = ha_free + 2;             // [2] A operand of the last GEMM in TMEM (double buffered in the enc1 chain)
+    uint64_t* h_free = h_full + 2;              // [2]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(h_free + 2);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    // contiguous run of tiles per CTA: consecutive tiles of an object share the shared-memory max
+    const int t_begin = (int)((long long)a.num_tiles * blockIdx.x / gridDim.x);
+    const int t_end = (int)((long long)a.num_tiles * (blockIdx.x + 1) / gridDim.x);
+
+    if (warp == 0 && lane == 0) {
+        if (C::HAS_L1) asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_w1) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_w2) : "memory");
+        if (C::X_SMEM) asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_x) : "memory");
+    }
+    if (warp == 1 && lane == 0) {
+        for (int s = 0; s < STAGES; ++s) { mbar_init(&w_full[s], 1); mbar_init(&w_empty[s], 1); }
+        for (int s = 0; s < 2; ++s) { mbar_init(&acc_full[s], 1); mbar_init(&acc_empty[s], NUM_POINT_WARPS); }
+        mbar_init(x_full, 1); mbar_init(x_empty, 2);      // "free" barriers: one commit per MMA issuer
+        for (int s = 0; s < 2; ++s) {
+            mbar_init(&ha_full[s], NUM_POINT_WARPS); mbar_init(&ha_free[s], 2);
+            mbar_init(&h_full[s], NUM_POINT_WARPS); mbar_init(&h_free[s], 2);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 2) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(TMEM_COLS) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    // constants staged once per CTA
+    for (int i = threadIdx.x; i < C::C2; i += NUM_THREADS) { tilemax[i] = 0u; s_bias2[i] = a.b2 ? a.b2[i] : 0.f; }
+    if (C::PRODUCER)
+        for (int i = threadIdx.x; i < C::K0; i += NUM_THREADS)
+            s_w0[i] = make_float4(a.w0[i * 3 + 0], a.w0[i * 3 + 1], a.w0[i * 3 + 2], a.b0 ? a.b0[i] : 0.f);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ================================================================== TMA producer ==
+        // Ring order inside a phase: chunks go in groups of two (one per issuer); a group's k-blocks alternate
+        // between its two chunks so that both issuers advance together.
+        if (lane == 0) {
+            uint32_t pos = 0;     // ring position; stage = pos % STAGES, phase = (pos / STAGES) & 1
+            int ti = 0;
+            auto produce = [&](const CUtensorMap* tm, int n_chunks, int kbs) {
+                for (int g = 0; g < n_chunks; g += 2) {
+                    const int members = min(2, n_chunks - g);
+                    for (int kb = 0; kb < kbs; ++kb)
+                        for (int m = 0; m < members; ++m, ++pos) {
+                            const uint32_t stage = pos % STAGES, phase = (pos / STAGES) & 1;
+                            mbar_wait(&w_empty[stage], phase ^ 1);
+                            if ((a.dbg & 1) && pos >= (uint32_t)STAGES) { mbar_arrive(&w_full[stage]); continue; }
+                            mbar_expect_tx(&w_full[stage], W_STAGE_BYTES);
+                            tma_load_2d(smem_w + stage * W_STAGE_BYTES, tm, kb * BK, (g + m) * TN, &w_full[stage]);
+                        }
+                }
+            };
+            for (int tile = t_begin; tile < t_end; ++tile, ++ti) {
+                if (C::X_SMEM) {
+                    const int obj = tile / a.tiles_per_obj;
+                    const int row0 = obj * a.n + (tile - obj * a.tiles_per_obj) * TM;
+                    mbar_wait(x_empty, (ti & 1) ^ 1);
+                    mbar_expect_tx(x_full, TM * C::K0 * 2);
+#pragma unroll
+                    for (int kb = 0; kb < KB1; ++kb) tma_load_2d(smem_x + kb * (TM * BK * 2), &tmap_x, kb * BK, row0, x_full);
+                }
+                if (C::HAS_L1) produce(&tmap_w1, N1, KB1);
+                produce(&tmap_w2, N2, KB2);
+            }
+        }
+    } else if (warp == 1 || warp == 3) {
+        // =================================================================== MMA issuers ==
+        {   // the whole warp runs the loop (uniform control flow); one elected lane issues
+            const uint32_t me = warp == 1 ? 0u : 1u;        // accumulator owned by this issuer
+            const uint32_t d_tmem = tmem_base + ACC_COL + me * TN;
+            const uint64_t desc_w0 = make_desc(smem_u32(smem_w));
+            const uint64_t desc_x0 = make_desc(smem_u32(smem_x));
+            uint32_t pos = 0, ai = 0;                        // same sequences as the producer / the point warps
+            int ti = 0;
+            long long c_tot = 0, c_a = 0, c_acc = 0, c_w = 0, c_h = 0, t_;
+            const bool prof = (a.dbg & 4) != 0;
+#define PROF_WAIT(ctr, stmt) do { if (prof) { t_ = clock64(); stmt; ctr += clock64() - t_; } else { stmt; } } while (0)
+            if (prof) c_tot = -clock64();
+            // one phase (= one GEMM of the chain) of the current tile; a_tmem < 0 selects the smem A operand
+            auto issue = [&](int n_chunks, int kbs, bool a_from_smem, uint32_t a_tmem) {
+                for (int g = 0; g < n_chunks; g += 2) {
+                    const int members = min(2, n_chunks - g);
+                    const int mine = (int)((me - ai) & 1u);          // member index of the chunk on my accumulator
+                    if (mine < members) {
+                        const uint32_t use = (ai + mine) >> 1;        // how often my accumulator has been used
+                        PROF_WAIT(c_acc, mbar_wait(&acc_empty[me], (use & 1) ^ 1));
+                        tc_fence_after();
+                        for (int kb = 0; kb < kbs; ++kb) {
+                            const uint32_t p = pos + kb * members + mine;
+                            const uint32_t stage = p % STAGES, phase = (p / STAGES) & 1;
+                            PROF_WAIT(c_w, mbar_wait(&w_full[stage], phase));
+                            tc_fence_after();
+                            const uint64_t db = desc_w0 + (uint64_t)((stage * W_STAGE_BYTES) >> 4);
+                            if (elect_one()) {
+                                if (a_from_smem) {
+                                    const uint64_t da = desc_x0 + (uint64_t)((kb * (TM * BK * 2)) >> 4);
+#pragma unroll
+                                    for (int k = 0; k < BK / UMMA_K; ++k)
+                                        tc_mma(d_tmem, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), kIdesc, (kb | k) != 0);
+                                } else {
+                                    const uint32_t ta = a_tmem + kb * (BK / 2);
+#pragma unroll
+                                    for (int k = 0; k < BK / UMMA_K; ++k)
+                                        tc_mma_ts(d_tmem, ta + k * (UMMA_K / 2), db + (uint64_t)(k * 2), kIdesc, (kb | k) != 0);
+                                }
+                                tc_commit(&w_empty[stage]);
+                                if (kb == kbs - 1) tc_commit(&acc_full[me]);
+                            }
+                            __syncwarp();
+                        }
+                    }
+                    pos += members * kbs;
+                    ai += members;
+                }
+            };
+            for (int tile = t_begin; tile < t_end; ++tile, ++ti) {
+                const uint32_t tpar = ti & 1;
+                if (C::HAS_L1) {
+                    const uint32_t ab = HA_DOUBLE ? tpar : 0u, apar = HA_DOUBLE ? ((ti >> 1) & 1) : tpar;
+                    if (C::X_SMEM) PROF_WAIT(c_a, mbar_wait(x_full, tpar)); else PROF_WAIT(c_a, mbar_wait(&ha_full[ab], apar));
+                    tc_fence_after();
+                    issue(N1, KB1, C::X_SMEM, tmem_base + HA_COL + ab * (C::K0 / 2));
+                    if (elect_one()) { if (C::X_SMEM) tc_commit(x_empty); else tc_commit(&ha_free[ab]); }   // my MMAs of this GEMM are done reading A
+                    __syncwarp();
+                }
+                const uint32_t hb = H_DOUBLE ? tpar : 0u, hpar = H_DOUBLE ? ((ti >> 1) & 1) : tpar;
+                PROF_WAIT(c_h, mbar_wait(&h_full[hb], hpar));
+                tc_fence_after();
+                issue(N2, KB2, false, tmem_base + H_COL + hb * (C::KH / 2));
+                if (elect_one()) tc_commit(&h_free[hb]);
+                __syncwarp();
+            }
+            if (prof && me == 0 && lane == 0) {
+                long long* o = a.prof + (size_t)blockIdx.x * 8;
+                o[0] = c_tot + clock64(); o[1] = c_a; o[2] = c_acc; o[3] = c_w; o[4] = c_h; o[5] = t_end - t_begin;
+            }
+#undef PROF_WAIT
+        }
+    } else if (warp >= 4) {
+        // =================================================================== point warps ==
+        const int q = warp & 3, cq = (warp - 4) >> 2;
+        const int pt = q * 32 + lane;                         // point of the tile = TMEM lane
+        const int ptid = threadIdx.x - 128;                   // 0..511 among the point threads
+        const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16);
+        const float slope0 = act_slope(a.act0), slope1 = act_slope(a.act1);
+        // ---- K = 3 input layer on CUDA cores, canonicalisation fused; output -> TMEM A operand (buffer pti & 1) ----
+        auto produce = [&](int ptile, int pti) {
+            if constexpr (C::PRODUCER) {
+                const int obj = ptile / a.tiles_per_obj;
+                const int p0 = (ptile - obj * a.tiles_per_obj) * TM;
+                const bool valid = pt < min(TM, a.n - p0);
+                const size_t row = (size_t)obj * a.n + p0 + pt;
+                const uint32_t pb = pti & 1, ppar = (pti >> 1) & 1;
+                float x = 0.f, y = 0.f, z = 0.f;
+                if (valid) { const float* p = a.input + row * 3; x = p[0]; y = p[1]; z = p[2]; }
+                const VcnFrame f = a.frames[obj];
+                float u0, u1, u2;
+                if (a.xform == XF_VIEW) {            // (p . R(-theta)) - mean            VCN_VC.py:185-190
+                    u0 = (x * f.ca - y * f.sa) - f.mean[0]; u1 = (x * f.sa + y * f.ca) - f.mean[1]; u2 = z - f.mean[2];
+                } else if (a.xform == XF_CANON) {    // ((p . R(-theta)) - centre) . rot^T  VCN_VC.py:200
+                    const VcnPose P = a.poses[obj];
+                    const float d0 = (x * f.ca - y * f.sa) - P.centre[0], d1 = (x * f.sa + y * f.ca) - P.centre[1], d2 = z - P.centre[2];
+                    u0 = d0 * P.rot[0] + d1 * P.rot[1] + d2 * P.rot[2];
+                    u1 = d0 * P.rot[3] + d1 * P.rot[4] + d2 * P.rot[5];
+                    u2 = d0 * P.rot[6] + d1 * P.rot[7] + d2 * P.rot[8];
+                } else {                              // rotate(p - centre, -heading) / length  VCN_CN.py:146-147
+                    const float e0 = x - f.mean[0], e1 = y - f.mean[1], e2 = z - f.mean[2];
+                    u0 = (e0 * f.ca - e1 * f.sa) / f.scale; u1 = (e0 * f.sa + e1 * f.ca) / f.scale; u2 = e2 / f.scale;
+                }
+                // this buffer was read by the MMAs of tile pti - 2
+                if (C::HAS_L1) mbar_wait(&ha_free[pb], ppar ^ 1); else mbar_wait(&h_free[pb], ppar ^ 1);
+                tc_fence_after();
+                constexpr int CH = C::K0 / 4;                 // channels per thread (column quarter cq): 16 or 32
+                const uint32_t dst = lane_base + (C::HAS_L1 ? HA_COL : H_COL) + pb * (C::K0 / 2) + cq * (CH / 2);
+                uint32_t pk[CH / 2];
+#pragma unroll
+                for (int i = 0; i < CH / 2; ++i) {
+                    const float4 wa = s_w0[cq * CH + 2 * i], wb = s_w0[cq * CH + 2 * i + 1];
+                    const float va = act_apply(fmaf(wa.z, u2, fmaf(wa.y, u1, fmaf(wa.x, u0, wa.w))), slope0);
+                    const float vb = act_apply(fmaf(wb.z, u2, fmaf(wb.y, u1, fmaf(wb.x, u0, wb.w))), slope0);
+                    pk[i] = pack_bf16(va, vb);
+                }
+                if constexpr (CH == 16) tc_st8(dst, pk); else tc_st16(dst, pk);
+                tc_wait_st();
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(C::HAS_L1 ? &ha_full[pb] : &h_full[pb]);
+            }
+        };
+
+        if (C::PRODUCER && t_begin < t_end) produce(t_begin, 0);
+        uint32_t ai = 0;
+        int ti = 0;
+        for (int tile = t_begin; tile < t_end; ++tile, ++ti) {
+            const uint32_t tpar = ti & 1;
+            const int obj = tile / a.tiles_per_obj;
+            const int p0 = (tile - obj * a.tiles_per_obj) * TM;       // first point of the tile inside the object
+            const int nvalid = min(TM, a.n - p0);
+            const bool valid = pt < nvalid;
+            const size_t row = (size_t)obj * a.n + p0 + pt;            // global point row (valid lanes)
+
+            if (C::HAS_L1) {   // bias of the first GEMM for this object: b1 + per-object bias
+                for (int c = ptid; c < C::C1; c += NUM_POINT_THREADS)
+                    s_bias1[c] = (a.b1 ? a.b1[c] : 0.f) + (a.obj_bias ? a.obj_bias[(size_t)obj * C::C1 + c] : 0.f);
+            }
+
+            if (C::PRODUCER && tile + 1 < t_end) produce(tile + 1, ti + 1);   // one tile ahead of the epilogues
+
+            if (C::HAS_L1) {
+                named_bar_sync(1, NUM_POINT_THREADS);          // s_bias1 complete
+                // ---- first GEMM epilogue: bias + act -> bf16 -> TMEM (A operand of the last GEMM) ----
+                for (int j = 0; j < N1; ++j, ++ai) {
+                    const uint32_t acc = ai & 1;
+                    mbar_wait(&acc_full[acc], (ai >> 1) & 1);
+                    tc_fence_after();
+                    if (j == 0) { mbar_wait(&h_free[0], tpar ^ 1); tc_fence_after(); }
+                    uint32_t r0[32];
+                    tc_ld32(lane_base + ACC_COL + acc * TN + cq * 32, r0);
+                    // accumulator quarter drained into registers: hand it back before the stores
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&acc_empty[acc]);
+                    const float* bj = s_bias1 + j * TN + cq * 32;
+                    uint32_t pk[16];
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) {
+                        const float2 b = *reinterpret_cast<const float2*>(bj + 2 * i);
+                        pk[i] = pack_bf16(act_apply(__uint_as_float(r0[2 * i]) + b.x, slope1),
+                                          act_apply(__uint_as_float(r0[2 * i + 1]) + b.y, slope1));
+                    }
+                    tc_st16(lane_base + H_COL + j * (TN / 2) + cq * 16, pk);
+                }
+                tc_wait_st();
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&h_full[0]);
+            }
+
+            // ---- last GEMM epilogue: bias, optional bf16 store, max over the tile's points ----
+            for (int j = 0; j < N2; ++j, ++ai) {
+                const uint32_t acc = ai & 1;
+                mbar_wait(&acc_full[acc], (ai >> 1) & 1);
+                tc_fence_after();
+                uint32_t r0[32];
+                tc_ld32(lane_base + ACC_COL + acc * TN + cq * 32, r0);
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&acc_empty[acc]);
+                if (a.dbg & 2) continue;
+                const int cbase = j * TN + cq * 32;
+                const float* bj = s_bias2 + cbase;
+                uint32_t pk[16];                      // 32 channels as bf16x2: register i = channels 2i, 2i+1
+#pragma unroll
+                for (int i = 0; i < 16; ++i) {
+                    if constexpr (C::STORE) {
+                        const float2 b = *reinterpret_cast<const float2*>(bj + 2 * i);
+                        pk[i] = pack_bf16(__uint_as_float(r0[2 * i]) + b.x, __uint_as_float(r0[2 * i + 1]) + b.y);
+                    } else {      // max-only chains: the bias commutes with the max and is added once per object at the flush
+                        pk[i] = pack_bf16(__uint_as_float(r0[2 * i]), __uint_as_float(r0[2 * i + 1]));
+                    }
+                }
+                if (C::STORE) {
+                    if (valid) {
+                        uint4* dst = reinterpret_cast<uint4*>(a.F + row * a.ldf + cbase);
+#pragma unroll
+                        for (int g = 0; g < 4; ++g) dst[g] = make_uint4(pk[4 * g], pk[4 * g + 1], pk[4 * g + 2], pk[4 * g + 3]);
+                    }
+                }
+                if (!valid) {
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) pk[i] = 0xff80ff80u;     // (-inf, -inf)
+                }
+                const uint32_t m2 = warp_transpose_max2(pk, lane);        // channels cbase + 2*(lane & 15), + 1
+                if (lane < 16) {
+                    atomicMax(&tilemax[cbase + 2 * lane], fkey(__uint_as_float(m2 << 16)));
+                    atomicMax(&tilemax[cbase + 2 * lane + 1], fkey(__uint_as_float(m2 & 0xffff0000u)));
+                }
+            }
+
+            // ---- object finished on this CTA: publish the max ----
+            const bool last_of_obj = (tile + 1 == t_end) || ((tile + 1) / a.tiles_per_obj != obj);
+            if (last_of_obj) {
+                named_bar_sync(1, NUM_POINT_THREADS);
+                for (int c = ptid; c < C::C2; c += NUM_POINT_THREADS) {
+                    const uint32_t k = tilemax[c];
+                    tilemax[c] = 0u;
+                    if (k != 0u) atomic_max_float(&a.colmax[(size_t)obj * C::C2 + c], fkey_inv(k) + (C::STORE ? 0.f : s_bias2[c]));
+                }
+                named_bar_sync(1, NUM_POINT_THREADS);
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TMEM_COLS) : "memory");
+    }
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode() {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(p);
+    }
+    return fn;
+}
+
+// 2-D bf16 row-major (rows, kpad) tensor, box = 64 elements (128 B) x 128 rows, SWIZZLE_128B, zero OOB fill
+int make_tmap(CUtensorMap* m, const void* base, uint64_t rows, uint64_t kpad, uint64_t ld_elems) {
+    EncodeTiledFn enc = get_encode();
+    if (!enc) { seevcn_set_error("cuTensorMapEncodeTiled not available from the driver"); return SEEVCN_E_CUDA; }
+    cuuint64_t dims[2] = {kpad, rows};
+    cuuint64_t strides[1] = {ld_elems * 2};
+    cuuint32_t box[2] = {BK, TM};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { seevcn_set_error("cuTensorMapEncodeTiled failed (%d)", (int)r); return SEEVCN_E_CUDA; }
+    return SEEVCN_OK;
+}
+
+template <int MODE>
+int launch_chain(const CUtensorMap& tw1, const CUtensorMap& tw2, const CUtensorMap& tx, const ChainArgs& a, cudaStream_t st) {
+    constexpr int smem = chain_smem_bytes<MODE>();
+    static bool attr_set = false;
+    if (!attr_set) {
+        SEEVCN_CUDA_CHECK(cudaFuncSetAttribute(vcn_chain_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        attr_set = true;
+    }
+    const int grid = a.num_tiles < SEEVCN_NUM_SMS ? a.num_tiles : SEEVCN_NUM_SMS;
+    ChainArgs b = a;
+    static int dbg = -1;
+    if (dbg < 0) { const char* e = getenv("SEEVCN_CHAIN_DBG"); dbg = e ? atoi(e) : 0; }
+    b.dbg = dbg;
+    b.prof = nullptr;
+    if (dbg & 4) SEEVCN_CUDA_CHECK(cudaMalloc(&b.prof, (size_t)grid * 8 * sizeof(long long)));
+    vcn_chain_kernel<MODE><<<grid, NUM_THREADS, smem, st>>>(tw1, tw2, tx, b);
+    SEEVCN_LAUNCH_CHECK();
+    if (dbg & 4) {   // timing experiment: issuer-0 wait breakdown, averaged over CTAs
+        std::vector<long long> h((size_t)grid * 8);
+        SEEVCN_CUDA_CHECK(cudaStreamSynchronize(st));
+        SEEVCN_CUDA_CHECK(cudaMemcpy(h.data(), b.prof, h.size() * sizeof(long long), cudaMemcpyDeviceToHost));
+        cudaFree(b.prof);
+        double s[6] = {0, 0, 0, 0, 0, 0};
+        for (int i = 0; i < grid; ++i) for (int j = 0; j < 6; ++j) s[j] += (double)h[(size_t)i * 8 + j] / grid;
+        fprintf(stderr, "chain<%d> tiles/CTA %.1f: issuer0 cycles total %.0f | wait A %.0f | acc_empty %.0f | w_full %.0f | h_full %.0f  (per tile: %.0f)\n",
+                MODE, s[5], s[0], s[1], s[2], s[3], s[4], s[0] / (s[5] > 0 ? s[5] : 1));
+    }
+    return SEEVCN_OK;
+}
+
+}  // namespace
+
+// pose chain: raw points -> pose_enc0 (CUDA cores) -> pose_enc2 -> pose_enc4, max -> pose_feat (num_obj, 1024)
+int vcn_chain_pose(const seevcn_vcn_model* M, int num_obj, int n, const float* input, const VcnFrame* frames,
+                   float* pose_feat, cudaStream_t st) {
+    if (num_obj == 0) return SEEVCN_OK;
+    CUtensorMap tw1, tw2;
+    int rc = make_tmap(&tw1, M->pose_enc2.w16, 128, 64, 64);
+    if (rc != SEEVCN_OK) return rc;
+    rc = make_tmap(&tw2, M->pose_enc4.w16, 1024, 128, 128);
+    if (rc != SEEVCN_OK) return rc;
+    ChainArgs a{};
+    a.num_obj = num_obj; a.n = n; a.tiles_per_obj = div_up(n, TM); a.num_tiles = num_obj * a.tiles_per_obj;
+    a.input = input; a.frames = frames; a.poses = nullptr; a.xform = XF_VIEW;
+    a.w0 = M->pose_enc0.w; a.b0 = M->pose_enc0.b; a.act0 = ACT_LEAKY;
+    a.b1 = M->pose_enc2.b; a.obj_bias = nullptr; a.act1 = ACT_LEAKY;
+    a.b2 = M->pose_enc4.b; a.F = nullptr; a.ldf = 0; a.colmax = pose_feat;
+    return launch_chain<CHAIN_POSE>(tw1, tw2, tw2, a, st);
+}
+
+// enc1 chain: raw points -> canonicalise -> mlp_conv1.0 (CUDA cores) -> mlp_conv1.3; stores f (rows, 256) bf16, max -> g256
+int vcn_chain_enc1(const seevcn_vcn_model* M, int num_obj, int n, const float* input, const VcnFrame* frames,
+                   const VcnPose* poses, __nv_bfloat16* F, float* g256, cudaStream_t st) {
+    if (num_obj == 0) return SEEVCN_OK;
+    CUtensorMap tw2;
+    int rc = make_tmap(&tw2, M->enc1_3.w16, 256, 128, 128);
+    if (rc != SEEVCN_OK) return rc;
+    ChainArgs a{};
+    a.num_obj = num_obj; a.n = n; a.tiles_per_obj = div_up(n, TM); a.num_tiles = num_obj * a.tiles_per_obj;
+    a.input = input; a.frames = frames; a.poses = poses; a.xform = M->viewer_centred ? XF_CANON : XF_GT;
+    a.w0 = M->enc1_0.w; a.b0 = M->enc1_0.b; a.act0 = ACT_RELU;
+    a.b1 = nullptr; a.obj_bias = nullptr; a.act1 = ACT_NONE;
+    a.b2 = M->enc1_3.b; a.F = F; a.ldf = 256; a.colmax = g256;
+    return launch_chain<CHAIN_ENC1>(tw2, tw2, tw2, a, st);
+}
+
+// enc2 chain: f (rows, 256) bf16 -> mlp_conv2.0 (local half, + per-object bias) -> mlp_conv2.3, max -> feat (num_obj, 1024)
+int vcn_chain_enc2(const seevcn_vcn_model* M, int num_obj, int n, const __nv_bfloat16* F, const float* obj_bias,
+                   float* feat, cudaStream_t st) {
+    if (num_obj == 0) return SEEVCN_OK;
+    CUtensorMap tw1, tw2, tx;
+    int rc = make_tmap(&tw1, M->enc2_0_local.w16, 512, 256, 256);
+    if (rc != SEEVCN_OK) return rc;
+    rc = make_tmap(&tw2, M->enc2_3.w16, 1024, 512, 512);
+    if (rc != SEEVCN_OK) return rc;
+    rc = make_tmap(&tx, F, (uint64_t)num_obj * n, 256, 256);
+    if (rc != SEEVCN_OK) return rc;
+    ChainArgs a{};
+    a.num_obj = num_obj; a.n = n; a.tiles_per_obj = div_up(n, TM); a.num_tiles = num_obj * a.tiles_per_obj;
+    a.input = nullptr; a.frames = nullptr; a.poses = nullptr; a.xform = 0;
+    a.w0 = nullptr; a.b0 = nullptr; a.act0 = ACT_NONE;
+    a.b1 = nullptr /* folded into obj_bias by the caller */; a.obj_bias = obj_bias; a.act1 = ACT_RELU;
+    a.b2 = M->enc2_3.b; a.F = nullptr; a.ldf = 0; a.colmax = feat;
+    return launch_chain<CHAIN_ENC2>(tw1, tw2, tx, a, st);
+}

@@ -22,6 +22,7 @@
 // for the other cout/128 - 1 channel tiles.
 #include <cuda.h>
 #include "vcn_common.cuh"
+#include "tc_ptx.cuh"
 
 namespace {
 
@@ -44,72 +45,12 @@ struct TcArgs {
     __nv_bfloat16* Y; int ldy;
     float* Yf32; int ldyf;
     float* colmax;           // (rows / rows_per_obj, cout) or null; pre-filled with -inf
+    int ksplit, kb_per_split; // split-K (FC layers, few rows): tile t covers k-blocks [ks*kb_per_split, ...) of K
+    float* part;             // split-K partial sums (ksplit, rows, cout) fp32, raw accumulators (no bias / act)
 };
 
-// ------------------------------------------------------------------------- PTX wrappers --
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+using namespace tcptx;
 
-__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "WAIT_LOOP:\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
-        "@p bra DONE;\n\t"
-        "bra WAIT_LOOP;\n\t"
-        "DONE:\n\t}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
-}
-__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, int c0, int c1, uint64_t* bar) {
-    asm volatile(
-        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
-        ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1) : "memory");
-}
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_commit(uint64_t* bar) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-// D[tmem] (+)= A[smem] . B[smem]^T, bf16 operands, fp32 accumulate
-__device__ __forceinline__ void tc_mma(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-        ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate) : "memory");
-}
-// 32 lanes x 32 consecutive fp32 columns -> 32 registers per thread
-__device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t (&r)[32]) {
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-        "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
-        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
-          "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
-          "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-        : "r"(taddr));
-    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-}
-
-// UMMA shared-memory descriptor, K-major operand, SWIZZLE_128B (cute::UMMA::SmemDescriptor layout):
-//   [0,14) start address >> 4 | [16,30) leading byte offset >> 4 (unused for swizzled K-major) |
-//   [32,46) stride byte offset >> 4 (8 rows x 128 B = 1024) | [46,48) version = 1 | [61,64) layout = 2 (SW128)
-__device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr) {
-    uint64_t d = 0;
-    d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
-    d |= (uint64_t)1 << 16;
-    d |= (uint64_t)(1024 >> 4) << 32;
-    d |= (uint64_t)1 << 46;
-    d |= (uint64_t)2 << 61;
-    return d;
-}
 // Instruction descriptor (cute::UMMA::InstrDescriptor): c_format F32 (1<<4), a/b format BF16 (1<<7, 1<<10),
 // both K-major, N>>3 at bit 17, M>>4 at bit 24.
 constexpr uint32_t kIdesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
@@ -117,7 +58,7 @@ constexpr uint32_t kIdesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN 
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 vcn_linear_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant__ CUtensorMap tmap_x, const TcArgs a) {
     extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // keeps the shared address space
     uint8_t* smem_a = smem;
     uint8_t* smem_b = smem + STAGES * A_BYTES;
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * (A_BYTES + B_BYTES));
@@ -151,8 +92,10 @@ vcn_linear_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_co
         if (lane == 0) {
             int stage = 0; uint32_t phase = 0;
             for (int tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x) {
-                const int m_tile = tile % a.num_m_tiles, n_tile = tile / a.num_m_tiles;
-                for (int kb = 0; kb < a.kblocks; ++kb) {
+                const int ks = tile % a.ksplit, mn = tile / a.ksplit;
+                const int m_tile = mn % a.num_m_tiles, n_tile = mn / a.num_m_tiles;
+                const int kb0 = ks * a.kb_per_split, kb1 = min(a.kblocks, kb0 + a.kb_per_split);
+                for (int kb = kb0; kb < kb1; ++kb) {
                     mbar_wait(&empty[stage], phase ^ 1);
                     mbar_expect_tx(&full[stage], A_BYTES + B_BYTES);
                     tma_load_2d(smem_a + stage * A_BYTES, &tmap_w, kb * BK, m_tile * BM, &full[stage]);
@@ -171,7 +114,9 @@ vcn_linear_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_co
                 mbar_wait(&tempty[acc], acc_phase ^ 1);
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + acc * BN;
-                for (int kb = 0; kb < a.kblocks; ++kb) {
+                const int ks = tile % a.ksplit;
+                const int kb0 = ks * a.kb_per_split, kb1 = min(a.kblocks, kb0 + a.kb_per_split);
+                for (int kb = kb0; kb < kb1; ++kb) {
                     mbar_wait(&full[stage], phase);
                     tc_fence_after();
                     const uint32_t a_addr = smem_u32(smem_a + stage * A_BYTES);
@@ -180,7 +125,7 @@ vcn_linear_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_co
                     for (int k = 0; k < BK / UMMA_K; ++k) {
                         const uint64_t da = make_desc(a_addr + k * UMMA_K * 2);
                         const uint64_t db = make_desc(b_addr + k * UMMA_K * 2);
-                        tc_mma(d_tmem, da, db, kIdesc, (kb | k) != 0);
+                        tc_mma(d_tmem, da, db, kIdesc, (kb != kb0 || k != 0) ? 1u : 0u);
                     }
                     tc_commit(&empty[stage]);   // frees the smem slot when these MMAs have read it
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
@@ -197,13 +142,14 @@ vcn_linear_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_co
         for (int tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x, ++it) {
             const int acc = it & 1;
             const uint32_t acc_phase = (it >> 1) & 1;
-            const int m_tile = tile % a.num_m_tiles, n_tile = tile / a.num_m_tiles;
+            const int ks = tile % a.ksplit, mn = tile / a.ksplit;
+            const int m_tile = mn % a.num_m_tiles, n_tile = mn / a.num_m_tiles;
             const int c = m_tile * BM + q * 32 + lane;
             const int row0 = n_tile * BN;
             const int nvalid = min(BN, a.rows - row0);
             const bool c_ok = c < a.cout;
             const int obj_first = row0 / a.rows_per_obj, obj_last = (row0 + nvalid - 1) / a.rows_per_obj;
-            const bool one_obj = obj_first == obj_last;
+            const bool one_obj = obj_first == obj_last && !a.part;   // split-K always takes the generic path
             float bt = (a.bias && c_ok) ? a.bias[c] : 0.f;            // bias (+ per-object bias when the tile is one object)
             if (one_obj && a.obj_bias && c_ok) bt += a.obj_bias[(size_t)obj_first * a.cout + c];
             mbar_wait(&tfull[acc], acc_phase);
@@ -253,6 +199,7 @@ vcn_linear_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_co
                         if (p >= nvalid) continue;
                         const int row = row0 + p;
                         const int o = row / a.rows_per_obj;
+                        if (a.part) { a.part[((size_t)ks * a.rows + row) * a.cout + c] = __uint_as_float(r[j]); continue; }
                         float v = __uint_as_float(r[j]) + bt;
                         if (!one_obj && a.obj_bias) v += a.obj_bias[(size_t)o * a.cout + c];
                         v = fmaxf(v, slope * v);
@@ -370,6 +317,7 @@ int vcn_linear_tc(const LinearW& L, int rows, const __nv_bfloat16* X, int ldx, c
     a.num_m_tiles = div_up(L.cout, BM);
     a.num_tiles = a.num_m_tiles * div_up(rows, BN);
     a.bias = L.b; a.obj_bias = obj_bias; a.Y = Y; a.ldy = ldy; a.Yf32 = Yf32; a.ldyf = L.cout; a.colmax = colmax;
+    a.ksplit = 1; a.kb_per_split = a.kblocks; a.part = nullptr;
     const int grid = a.num_tiles < SEEVCN_NUM_SMS ? a.num_tiles : SEEVCN_NUM_SMS;
     vcn_linear_tc_kernel<<<grid, NUM_THREADS, SMEM_BYTES, st>>>(tw, tx, a);
     SEEVCN_LAUNCH_CHECK();
@@ -381,6 +329,78 @@ int vcn_pointwise3(const LinearW& L, size_t rows, const float* X, int act, __nv_
     SEEVCN_REQUIRE(L.cin == 3 && L.cout % 8 == 0 && ldy % 8 == 0, "vcn_pointwise3: needs cin == 3, cout %% 8 == 0");
     const size_t total = rows * (size_t)(L.cout / 8);
     pointwise3_kernel<<<(unsigned)div_up(total, (size_t)256), 256, L.cout * 16 + (L.cout / 8) * 16, st>>>(rows, L.cout, X, L.w, L.b, act, Y, ldy);
+    SEEVCN_LAUNCH_CHECK();
+    return SEEVCN_OK;
+}
+
+
+// ---- per-object FC layers (few rows, K up to 1024): split-K over the SMs + a deterministic reduce ----
+namespace {
+// Y = act(sum_ks part[ks] + bias); writes fp32 (optional) and a bf16 copy padded to ldb (the next layer's X)
+__global__ void __launch_bounds__(256)
+fc_reduce_kernel(int rows, int cout, int ksplit, const float* __restrict__ part, const float* __restrict__ bias, int act,
+                 float* __restrict__ Yf32, __nv_bfloat16* __restrict__ Yb16, int ldb) {
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    const int groups = cout / 4;
+    if (e >= rows * groups) return;
+    const int r = e / groups, c = (e - r * groups) * 4;
+    float4 s = *reinterpret_cast<const float4*>(part + (size_t)r * cout + c);
+    for (int k = 1; k < ksplit; ++k) {      // fixed order: bitwise reproducible
+        const float4 t = *reinterpret_cast<const float4*>(part + ((size_t)k * rows + r) * cout + c);
+        s.x += t.x; s.y += t.y; s.z += t.z; s.w += t.w;
+    }
+    if (bias) { const float4 b = *reinterpret_cast<const float4*>(bias + c); s.x += b.x; s.y += b.y; s.z += b.z; s.w += b.w; }
+    s.x = apply_act(s.x, act); s.y = apply_act(s.y, act); s.z = apply_act(s.z, act); s.w = apply_act(s.w, act);
+    if (Yf32) *reinterpret_cast<float4*>(Yf32 + (size_t)r * cout + c) = s;
+    if (Yb16) {
+        __nv_bfloat162 lo = __floats2bfloat162_rn(s.x, s.y), hi = __floats2bfloat162_rn(s.z, s.w);
+        uint2 v; v.x = *reinterpret_cast<uint32_t*>(&lo); v.y = *reinterpret_cast<uint32_t*>(&hi);
+        *reinterpret_cast<uint2*>(Yb16 + (size_t)r * ldb + c) = v;
+    }
+}
+}  // namespace
+
+static int fc_ksplit(int rows, int cout, int kblocks, int* kb_per_split) {
+    const int mn = div_up(cout, BM) * div_up(rows, BN);
+    int ksplit = SEEVCN_NUM_SMS / mn;                       // fill the machine once
+    ksplit = ksplit < 1 ? 1 : ksplit > 16 ? 16 : ksplit;
+    ksplit = ksplit > kblocks ? kblocks : ksplit;
+    *kb_per_split = div_up(kblocks, ksplit);
+    return div_up(kblocks, *kb_per_split);
+}
+size_t vcn_fc_part_bytes(int rows, int cout, int cin) {
+    int kbps;
+    const int ks = fc_ksplit(rows, cout, (int)align_up((size_t)cin, BK) / BK, &kbps);
+    return (size_t)ks * rows * cout * 4;
+}
+
+// X bf16 (rows, ldx >= kpad, zero padded).  part: >= vcn_fc_part_bytes(rows, cout, cin).  cout % 128 == 0.
+int vcn_fc_tc(const LinearW& L, int rows, const __nv_bfloat16* X, int ldx, int act, float* Yf32, __nv_bfloat16* Yb16, int ldb,
+              float* part, cudaStream_t st) {
+    if (rows == 0) return SEEVCN_OK;
+    SEEVCN_REQUIRE(L.kpad % BK == 0 && ldx >= L.kpad && L.cout % 4 == 0, "vcn_fc_tc: bad layer shape");
+    static bool attr_set = false;
+    if (!attr_set) {
+        SEEVCN_CUDA_CHECK(cudaFuncSetAttribute(vcn_linear_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+        attr_set = true;
+    }
+    CUtensorMap tw, tx;
+    int rc = make_tmap(&tw, L.w16, (uint64_t)L.cout, (uint64_t)L.kpad, (uint64_t)L.kpad, BM);
+    if (rc != SEEVCN_OK) return rc;
+    rc = make_tmap(&tx, X, (uint64_t)rows, (uint64_t)L.kpad, (uint64_t)ldx, BN);
+    if (rc != SEEVCN_OK) return rc;
+    TcArgs a{};
+    a.rows = rows; a.cout = L.cout; a.kblocks = L.kpad / BK; a.rows_per_obj = 1; a.act = ACT_NONE;
+    a.num_m_tiles = div_up(L.cout, BM);
+    const int mn = a.num_m_tiles * div_up(rows, BN);
+    a.ksplit = fc_ksplit(rows, L.cout, a.kblocks, &a.kb_per_split);
+    a.num_tiles = mn * a.ksplit;
+    a.part = part;
+    const int grid = a.num_tiles < SEEVCN_NUM_SMS ? a.num_tiles : SEEVCN_NUM_SMS;
+    vcn_linear_tc_kernel<<<grid, NUM_THREADS, SMEM_BYTES, st>>>(tw, tx, a);
+    SEEVCN_LAUNCH_CHECK();
+    const int total = rows * (L.cout / 4);
+    fc_reduce_kernel<<<div_up(total, 256), 256, 0, st>>>(rows, L.cout, a.ksplit, part, L.b, act, Yf32, Yb16, ldb);
     SEEVCN_LAUNCH_CHECK();
     return SEEVCN_OK;
 }

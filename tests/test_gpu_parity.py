@@ -362,6 +362,37 @@ def test_vcn_forward_many_objects_vs_oracle(cuda, precision):
     assert (rel_chamfer(got, want, part) < 1e-3).all()
 
 
+@pytest.mark.parametrize("name,nobj,n", [("VCN_VC", 5, 1024), ("VCN_VC", 150, 1024), ("VCN_CN", 3, 1024), ("VCN_VC", 3, 1000),
+                                         ("VCN_VC", 2, 2048)])
+def test_vcn_fused_chains_vs_layerwise_and_oracle(cuda, name, nobj, n):
+    """the fused tcgen05 chains (activations in TMEM, A operand from tensor memory) against the layer-by-layer
+    tcgen05 path and the fp32 restatement; ragged tiles (n = 1000), several objects per CTA, chunk boundary (150)"""
+    from seevcn_b200 import _abi
+    part, _, boxes = synth.make_object_clouds(91, nobj, n, 0)
+    sd = oracle.make_state_dict(name, seed=5)
+    model = MODELS.build({"NAME": name}, precision="bf16")
+    model.load_state_dict(sd)
+    model.to(cuda).eval()
+    in_dict = {"input": dev(part, cuda)}
+    if name == "VCN_CN":
+        in_dict["gt_boxes"] = dev(boxes[:, :7].astype(np.float32), cuda)
+    L = _abi.lib()
+    prev = L.seevcn_set_fused_chains(1)
+    try:
+        fused = model(in_dict)["coarse"].cpu().numpy()
+        L.seevcn_set_fused_chains(0)
+        layer = model(in_dict)["coarse"].cpu().numpy()
+    finally:
+        L.seevcn_set_fused_chains(prev)
+    want = oracle.vcn_forward_ref(sd, part, boxes[:, :7].astype(np.float32) if name == "VCN_CN" else None, name)["coarse"].numpy()
+    assert np.isfinite(fused).all()
+    assert (rel_chamfer(fused, want, part) < 1e-3).all(), rel_chamfer(fused, want, part).max()
+    assert (rel_chamfer(fused, layer, part) < 1e-3).all()
+    # same bf16 roundings in both paths up to accumulation order: point-wise agreement, not just Chamfer
+    scale = np.abs(want - want.mean(axis=1, keepdims=True)).max()
+    assert np.abs(fused - layer).max() < 2e-2 * scale, (np.abs(fused - layer).max(), scale)
+
+
 # ------------------------------------------------------------------ stage 6: voxelization --
 WAYMO = ([-75.2, -75.2, -2, 75.2, 75.2, 4], [0.1, 0.1, 0.15], [1504, 1504, 40])
 
