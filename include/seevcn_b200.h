@@ -137,10 +137,13 @@ int seevcn_knn(int b, int r, int q, int k, const float* ref_pts, const float* qu
  * For every object: S = union of the k nearest `complete` points of every `partial`
  * point; out = complete[sorted(S)] repeated cyclically to surface_pts rows.
  * partial (B,Np,3), complete (B,R,3) -> out (B,surface_pts,3), sel_count (B) int32 = |S|.
- * R <= 16384. */
+ * R <= 16384.  workspace: seevcn_knn_surface_select_workspace_bytes(b, r) bytes of device scratch (the union
+ * bit masks the CTAs of one object share). */
+size_t seevcn_knn_surface_select_workspace_bytes(int b, int r);
 int seevcn_knn_surface_select(int b, int n_partial, int r, int k, int surface_pts,
                               const float* partial, const float* complete,
-                              float* out, int* sel_count, seevcn_stream_t stream);
+                              float* out, int* sel_count,
+                              void* workspace, size_t workspace_bytes, seevcn_stream_t stream);
 
 /* ref: get_largest_cluster(_batch)  see/surface_completion/models/vcn/utils/sampling.py:83-109
  * (open3d cluster_dbscan(eps, min_points) -> largest cluster -> tiled to total_pts rows), called with

@@ -45,7 +45,8 @@ SIGNATURES = {
     "seevcn_gather_points": (I, [I, I, I, I, P, P, P, P]),
     "seevcn_group_points": (I, [I, I, I, I, I, P, P, P, P]),
     "seevcn_knn": (I, [I, I, I, I, P, P, P, P, P]),
-    "seevcn_knn_surface_select": (I, [I, I, I, I, I, P, P, P, P, P]),
+    "seevcn_knn_surface_select_workspace_bytes": (c_size_t, [I, I]),
+    "seevcn_knn_surface_select": (I, [I, I, I, I, I, P, P, P, P, P, c_size_t, P]),
     "seevcn_largest_cluster": (I, [I, I, I, ctypes.c_double, I, P, P, P, P]),
     "seevcn_largest_cluster_periodic": (I, [I, I, I, ctypes.c_double, I, P, P, P, P, P]),
     "seevcn_vcn_create": (I, [POINTER(VcnParams), POINTER(c_void_p), P]),

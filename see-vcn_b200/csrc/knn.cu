@@ -132,14 +132,21 @@ __device__ __forceinline__ unsigned hash3(float x, float y, float z) {
     return h ^ (h >> 15);
 }
 
-// One CTA of T threads per object.  Dynamic smem:
+// Surface selection: grid (chunks, objects), T threads per CTA.  Every CTA of an object stages the completed
+// cloud, de-duplicates the object's queries DETERMINISTICALLY (representative = lowest index of equal
+// coordinates, unique list in index order) and takes the chunk-th slice of T unique queries: objects with
+// 1024 distinct queries spread over 4 CTAs, objects with few are done in one and the others exit at once —
+// without this split the kernel time is set by the largest object while half the SMs idle.  Neighbour sets
+// are OR-ed into a global bit mask; the last CTA of an object to arrive (global counter) emits the output.
+// Dynamic smem:
 //   complete float4[R] | list k*T u64 | buf kBuf*T u64 | partial SoA 3*Np f32 | hash table H i32 |
 //   unique list Np i32 | bitmask nw u32 | prefix (nw+1) i32
 template <int T>
 __global__ void __launch_bounds__(T)
 knn_surface_select_kernel(int np, int r, int k, int surface_pts, int hash_size,
                           const float* __restrict__ partial, const float* __restrict__ complete,
-                          float* __restrict__ out, int* __restrict__ sel_count) {
+                          float* __restrict__ out, int* __restrict__ sel_count,
+                          unsigned* __restrict__ g_mask, unsigned* __restrict__ g_arrive) {
     extern __shared__ __align__(16) unsigned char s_raw[];
     const int nwords = (r + 31) >> 5;
     float4* cref = reinterpret_cast<float4*>(s_raw);
@@ -151,9 +158,10 @@ knn_surface_select_kernel(int np, int r, int k, int surface_pts, int hash_size,
     int* uq = tab + hash_size;
     unsigned* mask = reinterpret_cast<unsigned*>(uq + np);
     int* prefix = reinterpret_cast<int*>(mask + nwords);
-    __shared__ int s_total, s_nuniq;
+    __shared__ int s_total, s_run, s_last;
+    __shared__ int s_warp_cnt[T / 32];
 
-    const int b = blockIdx.x;
+    const int b = blockIdx.y, chunk = blockIdx.x;
     const float* cp = complete + (size_t)b * r * 3;
     const float* pp = partial + (size_t)b * np * 3;
     for (int p = threadIdx.x; p < r; p += T) cref[p] = make_float4(cp[p * 3 + 0], cp[p * 3 + 1], cp[p * 3 + 2], 0.f);
@@ -163,25 +171,58 @@ knn_surface_select_kernel(int np, int r, int k, int surface_pts, int hash_size,
     }
     for (int i = threadIdx.x; i < hash_size; i += T) tab[i] = -1;
     for (int i = threadIdx.x; i < nwords; i += T) mask[i] = 0u;
-    if (threadIdx.x == 0) s_nuniq = 0;
+    if (threadIdx.x == 0) s_run = 0;
     __syncthreads();
 
-    // hash-set insert: the first thread to claim a slot for these exact coordinates keeps the query
+    // hash-set insert keyed by the exact coordinates; a slot ends up holding the LOWEST query index of its key
     for (int qi = threadIdx.x; qi < np; qi += T) {
         const float x = qx[qi], y = qy[qi], z = qz[qi];
         unsigned h = hash3(x, y, z) & (hash_size - 1);
         while (true) {
             const int prev = atomicCAS(&tab[h], -1, qi);
-            if (prev == -1) { uq[atomicAdd(&s_nuniq, 1)] = qi; break; }
-            if (qx[prev] == x && qy[prev] == y && qz[prev] == z) break;   // duplicate query
+            if (prev == -1) break;
+            if (qx[prev] == x && qy[prev] == y && qz[prev] == z) { atomicMin(&tab[h], qi); break; }   // duplicate query
             h = (h + 1) & (hash_size - 1);
         }
     }
     __syncthreads();
-    const int nuniq = s_nuniq;
-    for (int u0 = 0; u0 < nuniq; u0 += T) {
-        if (u0 + (int)(threadIdx.x & ~31u) >= nuniq) break;     // whole warp idle (warp-uniform)
-        const int u = u0 + threadIdx.x;
+    // unique list in ascending index order (block scan over the representative flags)
+    for (int q0 = 0; q0 < np; q0 += T) {
+        const int qi = q0 + threadIdx.x;
+        bool rep = false;
+        if (qi < np) {
+            const float x = qx[qi], y = qy[qi], z = qz[qi];
+            unsigned h = hash3(x, y, z) & (hash_size - 1);
+            while (true) {
+                const int cur = tab[h];
+                if (qx[cur] == x && qy[cur] == y && qz[cur] == z) { rep = cur == qi; break; }
+                h = (h + 1) & (hash_size - 1);
+            }
+        }
+        const unsigned bal = __ballot_sync(0xffffffffu, rep);
+        if (lane_id() == 0) s_warp_cnt[warp_id()] = __popc(bal);
+        __syncthreads();
+        if (warp_id() == 0) {
+            const int c = lane_id() < T / 32 ? s_warp_cnt[lane_id()] : 0;
+            int inc = c;
+#pragma unroll
+            for (int off = 1; off < 32; off <<= 1) {
+                const int t = __shfl_up_sync(0xffffffffu, inc, off);
+                if (lane_id() >= off) inc += t;
+            }
+            if (lane_id() < T / 32) s_warp_cnt[lane_id()] = s_run + inc - c;
+            __syncwarp();
+            if (lane_id() == 31) s_run += inc;
+        }
+        __syncthreads();
+        if (rep) uq[s_warp_cnt[warp_id()] + __popc(bal & ((1u << lane_id()) - 1))] = qi;
+        __syncthreads();
+    }
+    const int nuniq = s_run;
+
+    // this CTA's slice of the unique queries
+    const int u = chunk * T + threadIdx.x;
+    if (chunk * T + (int)(threadIdx.x & ~31u) < nuniq) {            // warp-uniform
         const bool active = u < nuniq;
         float x = 0.f, y = 0.f, z = 0.f;
         if (active) { const int qi = uq[u]; x = qx[qi]; y = qy[qi]; z = qz[qi]; }
@@ -194,6 +235,17 @@ knn_surface_select_kernel(int np, int r, int k, int surface_pts, int hash_size,
                 if (key != kInfKey) { const unsigned i = (unsigned)key; atomicOr(&mask[i >> 5], 1u << (i & 31)); }
             }
     }
+    __syncthreads();
+    unsigned* gm = g_mask + (size_t)b * nwords;
+    for (int w = threadIdx.x; w < nwords; w += T)
+        if (mask[w]) atomicOr(&gm[w], mask[w]);
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) s_last = atomicAdd(&g_arrive[b], 1u) == gridDim.x - 1;
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    for (int w = threadIdx.x; w < nwords; w += T) mask[w] = __ldcg(&gm[w]);
     __syncthreads();
     // exclusive prefix of popcounts over mask words (nwords <= 512): one warp, serial chunks
     if (threadIdx.x < 32) {
@@ -215,17 +267,18 @@ knn_surface_select_kernel(int np, int r, int k, int surface_pts, int hash_size,
     __syncthreads();
     const int total = s_total;
     float* o = out + (size_t)b * surface_pts * 3;
-    for (int j = threadIdx.x; j < surface_pts; j += T) {
-        float x = 0.f, y = 0.f, z = 0.f;
+    for (int f = threadIdx.x; f < surface_pts * 3; f += T) {
+        float v = 0.f;
         if (total > 0) {
+            const int j = f / 3, c = f - 3 * j;
             const int rank = j % total;
             int lo = 0, hi = nwords;           // last w with prefix[w] <= rank
             while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (prefix[mid] <= rank) lo = mid; else hi = mid; }
             const int bit = __fns(mask[lo], 0, rank - prefix[lo] + 1);
             const float4 s = cref[(lo << 5) + bit];
-            x = s.x; y = s.y; z = s.z;
+            v = c == 0 ? s.x : c == 1 ? s.y : s.z;
         }
-        o[j * 3 + 0] = x; o[j * 3 + 1] = y; o[j * 3 + 2] = z;
+        o[f] = v;
     }
 }
 
@@ -239,11 +292,12 @@ size_t select_smem(int T, int np, int r, int k, int hash_size) {
 
 template <int T>
 int launch_select(int b, int np, int r, int k, int surface_pts, int hash_size, size_t smem, const float* partial,
-                  const float* complete, float* out, int* sel_count, cudaStream_t st) {
+                  const float* complete, float* out, int* sel_count, unsigned* g_mask, unsigned* g_arrive, cudaStream_t st) {
     auto kern = knn_surface_select_kernel<T>;
     if (smem > 40 * 1024)
         SEEVCN_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    kern<<<b, T, smem, st>>>(np, r, k, surface_pts, hash_size, partial, complete, out, sel_count);
+    const int chunks = np > 0 ? div_up(np, T) : 1;
+    kern<<<dim3(chunks, b), T, smem, st>>>(np, r, k, surface_pts, hash_size, partial, complete, out, sel_count, g_mask, g_arrive);
     SEEVCN_LAUNCH_CHECK();
     return SEEVCN_OK;
 }
@@ -267,25 +321,38 @@ extern "C" int seevcn_knn(int b, int r, int q, int k, const float* ref_pts, cons
     return SEEVCN_OK;
 }
 
+extern "C" size_t seevcn_knn_surface_select_workspace_bytes(int b, int r) {
+    return ((size_t)(b > 0 ? b : 0) * ((size_t)((r > 0 ? r : 0) + 31) / 32 + 1)) * 4 + 256;
+}
+
 extern "C" int seevcn_knn_surface_select(int b, int n_partial, int r, int k, int surface_pts, const float* partial,
                                          const float* complete, float* out, int* sel_count,
-                                         seevcn_stream_t stream) {
+                                         void* workspace, size_t workspace_bytes, seevcn_stream_t stream) {
     SEEVCN_REQUIRE(b >= 0 && n_partial >= 0 && r >= 0 && surface_pts >= 0, "knn_surface_select: negative size");
     SEEVCN_REQUIRE(k >= 1 && k <= 64, "knn_surface_select: k=%d outside [1,64]", k);
     if (b == 0) return SEEVCN_OK;
     SEEVCN_REQUIRE(k <= r, "knn_surface_select: k=%d > r=%d", k, r);
-    SEEVCN_REQUIRE(partial && complete && out && sel_count, "knn_surface_select: null pointer");
+    SEEVCN_REQUIRE(b <= 65535, "knn_surface_select: b > 65535");
+    SEEVCN_REQUIRE(partial && complete && out && sel_count && workspace, "knn_surface_select: null pointer");
+    if (workspace_bytes < seevcn_knn_surface_select_workspace_bytes(b, r)) {
+        seevcn_set_error("knn_surface_select: workspace too small");
+        return SEEVCN_E_WORKSPACE;
+    }
     cudaStream_t st = as_stream(stream);
+    const int nwords = (r + 31) / 32;
+    unsigned* g_mask = static_cast<unsigned*>(workspace);
+    unsigned* g_arrive = g_mask + (size_t)b * nwords;
+    SEEVCN_CUDA_CHECK(cudaMemsetAsync(workspace, 0, ((size_t)b * (nwords + 1)) * 4, st));
     const int hash_size = next_pow2(2 * (n_partial > 0 ? n_partial : 1));
     // widest block whose per-thread lists still fit next to the staged clouds
     const size_t lim = 227 * 1024;
     if (select_smem(256, n_partial, r, k, hash_size) <= lim / 2)   // two CTAs per SM
         return launch_select<256>(b, n_partial, r, k, surface_pts, hash_size, select_smem(256, n_partial, r, k, hash_size),
-                                  partial, complete, out, sel_count, st);
+                                  partial, complete, out, sel_count, g_mask, g_arrive, st);
     if (select_smem(128, n_partial, r, k, hash_size) <= lim)
         return launch_select<128>(b, n_partial, r, k, surface_pts, hash_size, select_smem(128, n_partial, r, k, hash_size),
-                                  partial, complete, out, sel_count, st);
+                                  partial, complete, out, sel_count, g_mask, g_arrive, st);
     const size_t need = select_smem(32, n_partial, r, k, hash_size);
     SEEVCN_REQUIRE(need <= lim, "knn_surface_select: r=%d np=%d k=%d needs %zu B of shared memory (> 227 KB)", r, n_partial, k, need);
-    return launch_select<32>(b, n_partial, r, k, surface_pts, hash_size, need, partial, complete, out, sel_count, st);
+    return launch_select<32>(b, n_partial, r, k, surface_pts, hash_size, need, partial, complete, out, sel_count, g_mask, g_arrive, st);
 }

@@ -20,10 +20,12 @@ def get_partial_mesh_batch(batch_partial, batch_complete, k=20, surface_pts=1024
     R = batch_complete.shape[1]
     out = torch.empty((B, surface_pts, 3), dtype=torch.float32, device=batch_partial.device)
     cnt = torch.empty((B,), dtype=torch.int32, device=batch_partial.device)
+    L = _abi.lib()
+    ws = torch.empty(L.seevcn_knn_surface_select_workspace_bytes(B, R), dtype=torch.uint8, device=batch_partial.device)
     with torch.cuda.device(batch_partial.device):
-        _abi.check(_abi.lib().seevcn_knn_surface_select(B, Np, R, k, surface_pts, _abi.ptr(batch_partial),
-                                                        _abi.ptr(batch_complete), _abi.ptr(out), _abi.ptr(cnt),
-                                                        _abi.stream()))
+        _abi.check(L.seevcn_knn_surface_select(B, Np, R, k, surface_pts, _abi.ptr(batch_partial),
+                                               _abi.ptr(batch_complete), _abi.ptr(out), _abi.ptr(cnt),
+                                               _abi.ptr(ws), ws.numel(), _abi.stream()))
     return (out, cnt) if return_count else out
 
 
