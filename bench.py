@@ -11,8 +11,9 @@ step stands for "collect for the detector" when N > 1 (weak scaling: F frames pe
 
 Prints ONE JSON line (rank 0).  `value` = completed objects/s with inputs resident in HBM;
 `e2e` = same through the public API from pinned HOST buffers (H2D + D2H inside the timed region);
-`roofline` = the dominant kernel group (VCN forward: bf16 tcgen05 GEMMs) against the measured
-bf16 peak; `cpu_baseline` = the oracle port of the same path timed on the host cores.
+`roofline` = the dominant kernel (vcn_chain_kernel<2>, the enc2 tcgen05 chain) timed by the library's
+CUDA-event scopes inside the timed region, against the measured bf16 peak; `stages` = every launch
+group the same way; `cpu_baseline` = the oracle port of the same path timed on the host cores.
 """
 import argparse
 import json
@@ -32,6 +33,8 @@ SEL_K = 20               # SURFACE_COMPLETION.VCN.SEL_K_NEAREST (see/surface_com
 CLUSTER_EPS = 0.3        # SURFACE_COMPLETION.VCN.CLUSTER_EPS   (WAY-GT_VCN-VC.yaml:14)
 RESAMPLE = 1024
 FLOP_PER_OBJ = 2.0 * (959040 * 1024 + 5771776)   # VCN_VC, N = 1024 -> 1.976 GFLOP
+FLOP_ENC2_REF = 2.0 * (512 * 512 + 512 * 1024) * 1024    # enc2 as the reference graph states it
+FLOP_ENC2_EXEC = 2.0 * (256 * 512 + 512 * 1024) * 1024   # enc2 as executed: the global half folded into a per-object bias
 
 
 def peaks():
@@ -206,29 +209,66 @@ def run_ours(args):
     pts_d, boxes_d = pts_pin.to(dev), boxes_pin.to(dev)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)   # > 126 MB L2
 
-    def step_resident():
-        out = pipe.run(pts_d, boxes_d, seed=0)
-        if world > 1:
-            sdist.all_gather_v(out["clustered"])
-        return out
-
     from seevcn_b200.pipeline import HostStream
     hs = HostStream(pipe, F, pts_h.shape[1], boxes_h.shape[1])
 
-    def e2e_batches(n):
+    def resident_batches(n):
         for _ in range(n):
             flush.fill_(1)                                   # L2 flush before every batch (on the compute stream, timed)
+            yield pts_d, boxes_d
+
+    def e2e_batches(n):
+        for _ in range(n):
+            flush.fill_(1)
             yield pts_pin, boxes_pin
+
+    def sync_all():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def reduce_max_sum(ms, count):
+        t = torch.tensor([ms], device=dev, dtype=torch.float64)
+        c = torch.tensor([float(count)], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)         # max over ranks
+            dist.all_reduce(c)
+        return t.item(), c.item()
+
+    def timed_resident(steps, warmup):
+        """K batches streamed through pipe.run_stream with the inputs resident in HBM; the timed region holds the
+        K L2 flushes too.  The library's event scopes (seevcn_prof_*) time each launch group on the launching stream."""
+        for out in pipe.run_stream(resident_batches(warmup)):
+            pass
+        sync_all()
+        l0 = _abi.lib().seevcn_launch_count()
+        _abi.prof_enable(True)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        n_obj = n_pts = 0
+        last = None
+        e0.record()
+        for out in pipe.run_stream(resident_batches(steps)):
+            if world > 1:
+                sdist.all_gather_v(out.get("clustered", out["surface"]))   # "collect for the detector"
+            n_obj += out["input"].shape[0]; n_pts += out["num_voxel_points"]
+            last = out
+        e1.record()
+        e1.synchronize()
+        _abi.prof_enable(False)
+        prof = _abi.prof_report()
+        launches = _abi.lib().seevcn_launch_count() - l0
+        sync_all()
+        ms, objs = reduce_max_sum(e0.elapsed_time(e1), n_obj)
+        _, pts = reduce_max_sum(0.0, n_pts)
+        return ms, objs, pts, last, launches, prof
 
     def timed_e2e(steps, warmup):
         """Public host-buffer API: pinned host frames in, pinned host results out, every batch's H2D and D2H
         inside the timed region (copies of neighbouring batches overlap the kernels, see HostStream)."""
         for _ in hs.run(e2e_batches(warmup)):
             pass
-        torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
+        sync_all()
         hs.h2d_bytes = hs.d2h_bytes = 0
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         n_obj = 0
@@ -237,92 +277,80 @@ def run_ours(args):
             n_obj += res["clustered"].shape[0]
         e1.record()                                          # after the last D2H has landed on the host
         e1.synchronize()
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-        t = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
-        c = torch.tensor([float(n_obj)], device=dev, dtype=torch.float64)
-        if world > 1:
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            dist.all_reduce(c)
-        return t.item(), c.item(), hs.h2d_bytes // steps, hs.d2h_bytes // steps
-
-    def timed(fn, steps, warmup):
-        for _ in range(warmup):
-            fn()
-        torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-        ms, last = 0.0, None
-        l0 = _abi.lib().seevcn_launch_count()
-        for _ in range(steps):
-            flush.fill_(1)                                   # L2 flush between timed iterations (not timed)
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record()
-            last = fn()
-            e1.record()
-            e1.synchronize()
-            ms += e0.elapsed_time(e1)
-        launches = _abi.lib().seevcn_launch_count() - l0
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-        t = torch.tensor([ms], device=dev, dtype=torch.float64)
-        if world > 1:
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)         # max over ranks
-        return t.item(), last, launches
+        sync_all()
+        ms, objs = reduce_max_sum(e0.elapsed_time(e1), n_obj)
+        return ms, objs, hs.h2d_bytes // steps, hs.d2h_bytes // steps
 
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
-    ms_res, out, launches = timed(step_resident, args.steps, args.warmup)
-    n_obj = torch.tensor([out["input"].shape[0]], device=dev, dtype=torch.float64)
-    n_vox_pts = torch.tensor([out["voxel_points"].shape[0]], device=dev, dtype=torch.float64)
+    ms_res, n_obj_res, n_vox_pts, out, launches, prof = timed_resident(args.steps, args.warmup)
     n_voxels = out["voxel_coords"].shape[0]
-    if world > 1:
-        dist.all_reduce(n_obj); dist.all_reduce(n_vox_pts)
+    obj_rank0 = out["input"].shape[0]
     ms_e2e, n_obj_e2e, h2d, d2h = timed_e2e(args.steps, max(args.warmup, 3))
-
-    # dominant kernel group: the VCN forward on this rank's objects, timed alone with CUDA events
-    inp = out["input"]
-    for _ in range(3):
-        pipe.model({"input": inp})
-    torch.cuda.synchronize()
-    vms = 0.0
-    reps = max(args.steps, 5)
-    for _ in range(reps):
-        flush.fill_(1)
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record(); pipe.model({"input": inp}); e1.record(); e1.synchronize()
-        vms += e0.elapsed_time(e1)
-    vms /= reps
     clocks = sampler.summary() if rank == 0 else None
 
     if rank == 0:
         pk = peaks()
         steps = args.steps
-        value = n_obj.item() * steps / (ms_res / 1e3)
+        value = n_obj_res / (ms_res / 1e3)
         e2e = n_obj_e2e / (ms_e2e / 1e3)
-        achieved = FLOP_PER_OBJ * inp.shape[0] / (vms / 1e3) / 1e12
+        step_ms = ms_res / steps
+        # per launch group, from the library's CUDA events inside the timed region (rank 0)
+        P_pts = pts_h.shape[1]
+        alg = {   # algorithmic work per STEP on this rank (SURVEY.md §8d per-unit figures x units), and the bound
+            "points_in_boxes_kernel": ("hbm", 16.0 * F * P_pts + 28.0 * F * boxes_h.shape[1]),
+            "vcn_chain_pose": ("tensor", 2.0 * (64 * 128 + 128 * 1024) * RESAMPLE * obj_rank0),
+            "vcn_chain_enc1": ("tensor", 2.0 * (128 * 256) * RESAMPLE * obj_rank0),
+            "vcn_chain_enc2": ("tensor", FLOP_ENC2_EXEC * obj_rank0),
+            "vcn_forward": ("tensor", FLOP_PER_OBJ * obj_rank0),
+            "dynamic_voxelize": ("hbm", 16.0 * out["num_voxel_points"] + 32.0 * n_voxels),
+            "knn_surface_select": ("alu", None), "knn_prepare_kernel": ("alu", None), "knn_sweep_select_kernel": ("alu", None),
+            "largest_cluster": ("alu", None), "crop": ("hbm", None),
+        }
+        stages = []
+        for name, (cnt, tot_ms) in prof.items():
+            bound, work = alg.get(name, (None, None))
+            row = {"group": name, "launches_per_step": cnt / steps, "ms_per_step": tot_ms / steps, "share_of_step": tot_ms / ms_res,
+                   "bound": bound}
+            if work is not None and tot_ms > 0:
+                rate = work * steps / (tot_ms / 1e3)
+                if bound == "hbm":
+                    row.update(achieved=rate / 1e9, unit="GB/s", frac=rate / 1e9 / pk["hbm_gbs"])
+                else:
+                    row.update(achieved=rate / 1e12, unit="TFLOP/s", frac=rate / 1e12 / pk["bf16_tflops"])
+            stages.append(row)
+        cnt2, ms2 = prof.get("vcn_chain_enc2", (0, 0.0))
+        achieved = FLOP_ENC2_EXEC * obj_rank0 * steps / (ms2 / 1e3) / 1e12 if ms2 > 0 else None
         peak = pk["bf16_tflops"]
+        traffic = None
+        tpath = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+        if os.path.exists(tpath):
+            traffic = json.load(open(tpath)).get("vcn_chain_kernel<2>", {}).get("dram_bytes_per_launch")
         import oracle   # cpu_baseline leg only (rank 0, N = 1)
         cpu = cpu_baseline(2, oracle.make_state_dict("VCN_VC", 0), os.cpu_count() or 1) if world == 1 and not args.no_cpu else None
         line = {
             "metric": METRIC, "value": value, "unit": "objects/s", "n_gpus": world, "steps": steps, "warmup": args.warmup,
-            "ms_per_step": ms_res / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "ms_per_step": step_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "bf16" if args.precision == "bf16" else "f32", "data": "synthetic",
             "config": {"workload": "C2: synthetic Waymo-like 64-beam frame (180k pts, 50 car boxes, 1024 pts/object), random-init VCN_VC",
-                       "frames_per_step_per_gpu": F, "objects_per_step": int(n_obj.item()), "sel_k": SEL_K, "cluster_eps": CLUSTER_EPS,
-                       "l2": "flushed (256 MB write) between timed iterations", "parallelism": f"frame-sharded x{world}"},
-            "voxelized_mpts_per_sec": n_vox_pts.item() * steps / (ms_res / 1e3) / 1e6, "voxels_per_step_rank0": int(n_voxels),
+                       "frames_per_step_per_gpu": F, "objects_per_step": int(round(n_obj_res / steps)), "sel_k": SEL_K,
+                       "cluster_eps": CLUSTER_EPS, "l2": "flushed (256 MB write) before every step, inside the timed region",
+                       "parallelism": f"frame-sharded x{world}"},
+            "voxelized_mpts_per_sec": n_vox_pts / (ms_res / 1e3) / 1e6, "voxels_per_step_rank0": int(n_voxels),
             "e2e": {"value": e2e, "unit": "objects/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                     "ms_per_step": ms_e2e / steps},
             "gpu_launches": int(launches),
-            "roofline": {"kernel": "VCN forward (vcn_linear_tc tcgen05 GEMMs + per-object kernels)" if args.precision == "bf16" else "VCN forward fp32 SIMT",
-                         "bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
-                         "traffic": None, "peak_source": pk["source"] + " burst bf16 (kernel group timed alone)",
-                         "ms_per_launch_group": vms, "objects": int(inp.shape[0])},
+            "roofline": {"kernel": "vcn_chain_kernel<2> (enc2: mlp_conv2.0 local half + mlp_conv2.3 + max-pool, tcgen05)",
+                         "bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
+                         "frac": achieved / peak if achieved else None, "traffic": traffic,
+                         "peak_source": pk["source"] + " burst bf16 (cuBLAS); sustained is %.0f" % pk["bf16_tflops_sustained"],
+                         "launches": cnt2, "us_per_launch": 1e3 * ms2 / cnt2 if cnt2 else None,
+                         "flop_per_object": FLOP_ENC2_EXEC,
+                         "note": "flops as executed (W_local x + per-object bias: 655,360 MAC/pt); the reference graph's "
+                                 "cat([global, local]) -> conv form is 786,432 MAC/pt (SURVEY.md §8a6)",
+                         "achieved_reference_graph": achieved * FLOP_ENC2_REF / FLOP_ENC2_EXEC if achieved else None},
+            "stages": stages,
             "cpu_baseline": cpu, "clocks": clocks,
         }
         print(json.dumps(line))

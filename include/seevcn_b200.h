@@ -35,6 +35,12 @@ int         seevcn_abi_version(void);
 const char* seevcn_last_error(void);
 /* Number of kernels this library has launched in this process (bench.py's gpu_launches). */
 unsigned long long seevcn_launch_count(void);
+/* Optional timing of the library's launch groups with CUDA events recorded on the stream each group is launched
+ * on (the reference has no profiling hooks).  seevcn_prof_enable(1) clears and starts recording,
+ * (0) stops; returns the previous state.  seevcn_prof_report synchronises the recorded events and writes one
+ * line per group name, "<name> <launch groups> <total ms>\n", into buf (NUL-terminated), then clears. */
+int         seevcn_prof_enable(int on);
+int         seevcn_prof_report(char* buf, size_t cap);
 /* Returns 0 when device `dev` is an sm_100 part this library was built for. */
 int         seevcn_check_device(int dev);
 
@@ -137,9 +143,9 @@ int seevcn_knn(int b, int r, int q, int k, const float* ref_pts, const float* qu
  * For every object: S = union of the k nearest `complete` points of every `partial`
  * point; out = complete[sorted(S)] repeated cyclically to surface_pts rows.
  * partial (B,Np,3), complete (B,R,3) -> out (B,surface_pts,3), sel_count (B) int32 = |S|.
- * R <= 16384.  workspace: seevcn_knn_surface_select_workspace_bytes(b, r) bytes of device scratch (the union
- * bit masks the CTAs of one object share). */
-size_t seevcn_knn_surface_select_workspace_bytes(int b, int r);
+ * R <= 16384, Np <= 4096.  workspace: seevcn_knn_surface_select_workspace_bytes(b, n_partial, r) bytes of
+ * 16-byte aligned device scratch (axis-sorted copies of the clouds, the union bit masks the CTAs of one object share). */
+size_t seevcn_knn_surface_select_workspace_bytes(int b, int n_partial, int r);
 int seevcn_knn_surface_select(int b, int n_partial, int r, int k, int surface_pts,
                               const float* partial, const float* complete,
                               float* out, int* sel_count,
@@ -258,6 +264,18 @@ int seevcn_dynamic_voxelize(int num_points, int num_features, const float* point
                             int* voxel_coords, float* voxel_features, int* voxel_counts,
                             int* num_voxels, void* workspace, size_t workspace_bytes,
                             seevcn_stream_t stream);
+
+/* The frame pipeline's form of the same op: rows come from two device arrays — the raw frames frame_pts (F,P,3),
+ * batch index = frame, and the completed object clouds obj_pts (O,S,3), batch index obj_frame[o] (O int32) — so the
+ * [batch_idx,x,y,z] matrix the reference concatenates on the host (detector3d/pcdet/datasets/dataset.py:187-192
+ * after SEE_VCN.py:247-265 merged the completed points into the frame) is never materialised.  C = 3.
+ * workspace: seevcn_dynamic_voxelize_workspace_bytes(F*P + O*S, 3, max_voxels). */
+int seevcn_dynamic_voxelize_frames(int num_frames, int pts_per_frame, const float* frame_pts,
+                                   int num_obj, int pts_per_obj, const float* obj_pts, const int* obj_frame,
+                                   const float* pc_range, const float* voxel_size, const int* grid_size,
+                                   int max_voxels, int sorted,
+                                   int* voxel_coords, float* voxel_features, int* voxel_counts, int* num_voxels,
+                                   void* workspace, size_t workspace_bytes, seevcn_stream_t stream);
 
 /* ref: VoxelGeneratorWrapper.generate  detector3d/pcdet/datasets/processor/data_processor.py:44-60
  * (spconv hard voxelization: first-seen voxel order, first max_points points per voxel in

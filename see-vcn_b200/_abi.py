@@ -33,6 +33,8 @@ SIGNATURES = {
     "seevcn_last_error": (c_char_p, []),
     "seevcn_launch_count": (ctypes.c_ulonglong, []),
     "seevcn_check_device": (I, [I]),
+    "seevcn_prof_enable": (I, [I]),
+    "seevcn_prof_report": (I, [c_char_p, c_size_t]),
     "seevcn_points_in_boxes": (I, [I, I, I, P, P, P, P]),
     "seevcn_points_in_boxes_dense": (I, [I, I, P, P, P, P]),
     "seevcn_points_in_boxes_dense_trig": (I, [I, I, P, P, P, P, P]),
@@ -45,7 +47,7 @@ SIGNATURES = {
     "seevcn_gather_points": (I, [I, I, I, I, P, P, P, P]),
     "seevcn_group_points": (I, [I, I, I, I, I, P, P, P, P]),
     "seevcn_knn": (I, [I, I, I, I, P, P, P, P, P]),
-    "seevcn_knn_surface_select_workspace_bytes": (c_size_t, [I, I]),
+    "seevcn_knn_surface_select_workspace_bytes": (c_size_t, [I, I, I]),
     "seevcn_knn_surface_select": (I, [I, I, I, I, I, P, P, P, P, P, c_size_t, P]),
     "seevcn_largest_cluster": (I, [I, I, I, ctypes.c_double, I, P, P, P, P]),
     "seevcn_largest_cluster_periodic": (I, [I, I, I, ctypes.c_double, I, P, P, P, P, P]),
@@ -60,6 +62,8 @@ SIGNATURES = {
     "seevcn_dynamic_voxelize_workspace_bytes": (c_size_t, [I, I, I]),
     "seevcn_dynamic_voxelize": (I, [I, I, P, POINTER(ctypes.c_float), POINTER(ctypes.c_float), POINTER(c_int),
                                     I, I, I, P, P, P, P, P, c_size_t, P]),
+    "seevcn_dynamic_voxelize_frames": (I, [I, I, P, I, I, P, P, POINTER(ctypes.c_float), POINTER(ctypes.c_float), POINTER(c_int),
+                                           I, I, P, P, P, P, P, c_size_t, P]),
     "seevcn_hard_voxelize_workspace_bytes": (c_size_t, [I, I, I]),
     "seevcn_hard_voxelize": (I, [I, I, P, POINTER(ctypes.c_float), POINTER(ctypes.c_float), POINTER(c_int),
                                  I, I, P, P, P, P, P, c_size_t, P]),
@@ -122,3 +126,19 @@ def farray(vals):
 
 def iarray(vals):
     return (ctypes.c_int * len(vals))(*[int(v) for v in vals])
+
+
+def prof_enable(on=True):
+    """Start/stop the library's CUDA-event timing of its launch groups (``seevcn_prof_enable``)."""
+    return lib().seevcn_prof_enable(1 if on else 0)
+
+
+def prof_report():
+    """-> {group name: (launch groups, total ms)} since ``prof_enable(True)``; synchronises the events."""
+    buf = ctypes.create_string_buffer(1 << 16)
+    check(lib().seevcn_prof_report(buf, len(buf)))
+    out = {}
+    for line in buf.value.decode().splitlines():
+        name, cnt, ms = line.rsplit(" ", 2)
+        out[name] = (int(cnt), float(ms))
+    return out

@@ -1,5 +1,9 @@
 // C-ABI plumbing: version, per-thread error message, device check.
 #include <atomic>
+#include <map>
+#include <mutex>
+#include <string>
+#include <vector>
 #include <stdarg.h>
 #include <string.h>
 #include "common.cuh"
@@ -26,6 +30,71 @@ extern "C" int seevcn_check_device(int dev) {
     if (prop.major != 10) {
         seevcn_set_error("device %d is sm_%d%d; this library is built for sm_100a only", dev, prop.major, prop.minor);
         return SEEVCN_E_UNSUPPORTED;
+    }
+    return SEEVCN_OK;
+}
+
+// ---- optional per-kernel timing with CUDA events on the launching stream (bench.py's roofline leg) ----
+// Off by default: a disabled scope costs one relaxed load.  Enabled, every scope records two events on the
+// stream its kernels are launched on; seevcn_prof_report() synchronises them and sums per name.
+namespace {
+struct ProfRec { const char* name; cudaEvent_t e0, e1; };
+std::atomic<int> g_prof_on{0};
+std::mutex g_prof_mu;
+std::vector<ProfRec> g_prof;
+std::vector<cudaEvent_t> g_prof_pool;
+cudaEvent_t prof_event() {
+    if (!g_prof_pool.empty()) { cudaEvent_t e = g_prof_pool.back(); g_prof_pool.pop_back(); return e; }
+    cudaEvent_t e = nullptr;
+    cudaEventCreate(&e);
+    return e;
+}
+}  // namespace
+
+SeevcnProfScope::SeevcnProfScope(const char* name, cudaStream_t st) : st_(st), slot_(-1) {
+    if (!g_prof_on.load(std::memory_order_relaxed)) return;
+    std::lock_guard<std::mutex> lk(g_prof_mu);
+    ProfRec r{name, prof_event(), prof_event()};
+    cudaEventRecord(r.e0, st_);
+    slot_ = (long)g_prof.size();
+    g_prof.push_back(r);
+}
+SeevcnProfScope::~SeevcnProfScope() {
+    if (slot_ < 0) return;
+    std::lock_guard<std::mutex> lk(g_prof_mu);
+    if ((size_t)slot_ < g_prof.size()) cudaEventRecord(g_prof[slot_].e1, st_);
+}
+
+extern "C" int seevcn_prof_enable(int on) {
+    std::lock_guard<std::mutex> lk(g_prof_mu);
+    const int prev = g_prof_on.exchange(on ? 1 : 0);
+    if (on) {
+        for (auto& r : g_prof) { g_prof_pool.push_back(r.e0); g_prof_pool.push_back(r.e1); }
+        g_prof.clear();
+    }
+    return prev;
+}
+
+extern "C" int seevcn_prof_report(char* buf, size_t cap) {
+    std::lock_guard<std::mutex> lk(g_prof_mu);
+    std::map<std::string, std::pair<long, double>> acc;
+    std::vector<std::string> order;
+    for (auto& r : g_prof) {
+        if (cudaEventSynchronize(r.e1) != cudaSuccess) { seevcn_set_error("prof_report: event sync failed"); return SEEVCN_E_CUDA; }
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, r.e0, r.e1);
+        if (!acc.count(r.name)) order.push_back(r.name);
+        auto& a = acc[r.name];
+        a.first += 1; a.second += ms;
+        g_prof_pool.push_back(r.e0); g_prof_pool.push_back(r.e1);
+    }
+    g_prof.clear();
+    size_t off = 0;
+    if (cap) buf[0] = 0;
+    for (auto& n : order) {
+        const int w = snprintf(buf + off, off < cap ? cap - off : 0, "%s %ld %.6f\n", n.c_str(), acc[n].first, acc[n].second);
+        if (w < 0 || off + (size_t)w >= cap) { seevcn_set_error("prof_report: buffer too small"); return SEEVCN_E_INVALID; }
+        off += (size_t)w;
     }
     return SEEVCN_OK;
 }

@@ -196,6 +196,7 @@ static int largest_cluster_launch(int b, int n, int total_pts, double eps, int m
     // fp32 screen: below `lo` certainly adjacent, at or above `hi` certainly not (fp32 error of the
     // distance <= ~4 ulp = 2.4e-7 relative); in between the float64 test decides
     const float lo = (float)(e2 * (1.0 - 1e-5)), hi = (float)(e2 * (1.0 + 1e-5));
+    SEEVCN_PROF("largest_cluster", as_stream(stream));
     largest_cluster_kernel<<<b, kThreads, smem, as_stream(stream)>>>(n, total_pts, e2, lo, hi, min_points, pts, period, out,
                                                                     out_count);
     SEEVCN_LAUNCH_CHECK();

@@ -35,6 +35,15 @@ void seevcn_count_launch();
         SEEVCN_CUDA_CHECK(cudaGetLastError());     \
     } while (0)
 
+// Optional CUDA-event timing of a launch group (see abi.cu; off unless seevcn_prof_enable(1)).
+struct SeevcnProfScope {
+    SeevcnProfScope(const char* name, cudaStream_t st);
+    ~SeevcnProfScope();
+    cudaStream_t st_;
+    long slot_;
+};
+#define SEEVCN_PROF(name, st) SeevcnProfScope _seevcn_prof_scope(name, st)
+
 static inline cudaStream_t as_stream(seevcn_stream_t s) { return reinterpret_cast<cudaStream_t>(s); }
 
 template <typename T>

@@ -448,8 +448,12 @@ extern "C" int seevcn_crop_points_in_boxes(int batch_size, int boxes_num, int pt
     int* tile_counts = static_cast<int*>(workspace);
     const int ntiles = div_up(pts_num, kTilePts);
     dim3 grid(ntiles, batch_size);
-    points_in_boxes_kernel<true><<<grid, kThreads, boxes_num * sizeof(int), st>>>(
-        boxes_num, pts_num, boxes, pts, box_idx_of_points, tile_counts);
+    SEEVCN_PROF("crop", st);
+    {
+        SEEVCN_PROF("points_in_boxes_kernel", st);
+        points_in_boxes_kernel<true><<<grid, kThreads, boxes_num * sizeof(int), st>>>(
+            boxes_num, pts_num, boxes, pts, box_idx_of_points, tile_counts);
+    }
     SEEVCN_LAUNCH_CHECK();
     crop_scan_kernel<<<batch_size, 256, boxes_num * sizeof(int), st>>>(boxes_num, ntiles, tile_counts,
                                                                        box_counts, box_offsets);

@@ -469,6 +469,7 @@ extern "C" int seevcn_vcn_forward(const seevcn_vcn_model* M, int num_obj, int n,
         return SEEVCN_E_WORKSPACE;
     }
     cudaStream_t st = as_stream(stream);
+    SEEVCN_PROF("vcn_forward", st);
     char* ws = static_cast<char*>(workspace);
     auto* frames = reinterpret_cast<VcnFrame*>(ws + w.frames);
     auto* poses = reinterpret_cast<VcnPose*>(ws + w.poses);

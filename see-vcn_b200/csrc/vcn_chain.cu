@@ -516,7 +516,10 @@ int launch_chain(const CUtensorMap& tw1, const CUtensorMap& tw2, const CUtensorM
     b.dbg = dbg;
     b.prof = nullptr;
     if (dbg & 4) SEEVCN_CUDA_CHECK(cudaMalloc(&b.prof, (size_t)grid * 8 * sizeof(long long)));
-    vcn_chain_kernel<MODE><<<grid, NUM_THREADS, smem, st>>>(tw1, tw2, tx, b);
+    {
+        SEEVCN_PROF(MODE == CHAIN_POSE ? "vcn_chain_pose" : MODE == CHAIN_ENC1 ? "vcn_chain_enc1" : "vcn_chain_enc2", st);
+        vcn_chain_kernel<MODE><<<grid, NUM_THREADS, smem, st>>>(tw1, tw2, tx, b);
+    }
     SEEVCN_LAUNCH_CHECK();
     if (dbg & 4) {   // timing experiment: issuer-0 wait breakdown, averaged over CTAs
         std::vector<long long> h((size_t)grid * 8);

@@ -48,6 +48,28 @@ __device__ __forceinline__ bool voxel_coord(const VoxGeom& g, float x, float y, 
 // acc layout per slot: [sum_0 .. sum_{C-1}, count] padded to ACCW floats (4 or 8) so one
 // slot is one 16/32-byte sector and C=3 uses a single red.global.add.v4.f32.
 template <int ACCW>
+__device__ __forceinline__ void dynvox_add(const VoxGeom& g, long long b, const float (&f)[kMaxFeat], unsigned long long hmask,
+                                           unsigned long long* __restrict__ keys, float* __restrict__ acc) {
+    int cx, cy, cz;
+    if (!voxel_coord(g, f[0], f[1], f[2], cx, cy, cz)) return;
+    const unsigned long long key =
+        (unsigned long long)(((b * g.g[0] + cx) * g.g[1] + cy) * (long long)g.g[2] + cz);
+    unsigned long long slot = mix64(key) & hmask;
+    while (true) {
+        const unsigned long long prev = atomicCAS(&keys[slot], kEmpty, key);
+        if (prev == kEmpty || prev == key) break;
+        slot = (slot + 1) & hmask;
+    }
+    float* a = acc + slot * ACCW;
+    if (ACCW == 4) {
+        asm volatile("red.global.add.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(a), "f"(f[0]), "f"(f[1]), "f"(f[2]), "f"(1.f) : "memory");
+    } else {
+        asm volatile("red.global.add.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(a), "f"(f[0]), "f"(f[1]), "f"(f[2]), "f"(f[3]) : "memory");
+        asm volatile("red.global.add.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(a + 4), "f"(f[4]), "f"(f[5]), "f"(f[6]), "f"(1.f) : "memory");
+    }
+}
+
+template <int ACCW>
 __global__ void __launch_bounds__(256)
 dynvox_insert_kernel(int n, int c, const float* __restrict__ points, VoxGeom g, unsigned long long hmask,
                      unsigned long long* __restrict__ keys, float* __restrict__ acc) {
@@ -58,24 +80,27 @@ dynvox_insert_kernel(int n, int c, const float* __restrict__ points, VoxGeom g, 
         const float bf = row[0];
 #pragma unroll
         for (int j = 0; j < kMaxFeat; ++j) f[j] = j < c ? row[1 + j] : 0.f;
-        int cx, cy, cz;
-        if (!voxel_coord(g, f[0], f[1], f[2], cx, cy, cz)) continue;
-        const long long b = (long long)(int)bf;   // points[:,0].int()
-        const unsigned long long key =
-            (unsigned long long)(((b * g.g[0] + cx) * g.g[1] + cy) * (long long)g.g[2] + cz);
-        unsigned long long slot = mix64(key) & hmask;
-        while (true) {
-            const unsigned long long prev = atomicCAS(&keys[slot], kEmpty, key);
-            if (prev == kEmpty || prev == key) break;
-            slot = (slot + 1) & hmask;
-        }
-        float* a = acc + slot * ACCW;
-        if (ACCW == 4) {
-            asm volatile("red.global.add.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(a), "f"(f[0]), "f"(f[1]), "f"(f[2]), "f"(1.f) : "memory");
-        } else {
-            asm volatile("red.global.add.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(a), "f"(f[0]), "f"(f[1]), "f"(f[2]), "f"(f[3]) : "memory");
-            asm volatile("red.global.add.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(a + 4), "f"(f[4]), "f"(f[5]), "f"(f[6]), "f"(1.f) : "memory");
-        }
+        dynvox_add<ACCW>(g, (long long)(int)bf /* points[:,0].int() */, f, hmask, keys, acc);
+    }
+}
+
+// The frame pipeline's rows without the concatenated (N,4) matrix: frame f's raw points carry batch index f,
+// object o's completed points carry obj_frame[o].
+__global__ void __launch_bounds__(256)
+dynvox_insert_frames_kernel(int n_frame_pts, int pts_per_frame, const float* __restrict__ frame_pts, int n_obj_pts,
+                            int pts_per_obj, const float* __restrict__ obj_pts, const int* __restrict__ obj_frame,
+                            VoxGeom g, unsigned long long hmask, unsigned long long* __restrict__ keys,
+                            float* __restrict__ acc) {
+    const int n = n_frame_pts + n_obj_pts;
+    for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < n; p += gridDim.x * blockDim.x) {
+        const float* row;
+        long long b;
+        if (p < n_frame_pts) { row = frame_pts + (size_t)p * 3; b = p / pts_per_frame; }
+        else { const int q = p - n_frame_pts; row = obj_pts + (size_t)q * 3; b = obj_frame[q / pts_per_obj]; }
+        float f[kMaxFeat];
+#pragma unroll
+        for (int j = 0; j < kMaxFeat; ++j) f[j] = j < 3 ? row[j] : 0.f;
+        dynvox_add<4>(g, b, f, hmask, keys, acc);
     }
 }
 
@@ -329,29 +354,27 @@ extern "C" size_t seevcn_dynamic_voxelize_workspace_bytes(int num_points, int nu
     return dyn_layout(num_points, num_features, max_voxels).total;
 }
 
-extern "C" int seevcn_dynamic_voxelize(int num_points, int num_features, const float* points, const float* pc_range,
-                                       const float* voxel_size, const int* grid_size, int max_voxels, int sorted,
-                                       int batch_hint, int* voxel_coords, float* voxel_features, int* voxel_counts, int* num_voxels,
-                                       void* workspace, size_t workspace_bytes, seevcn_stream_t stream) {
-    SEEVCN_REQUIRE(num_points >= 0 && max_voxels >= 0, "dynamic_voxelize: negative size");
-    if (batch_hint <= 0) batch_hint = 1 << 20;   // unknown batch size: sort on (almost) all key bits
-    SEEVCN_REQUIRE(num_features >= 3 && num_features < kMaxFeat, "dynamic_voxelize: num_features=%d outside [3,%d]",
-                   num_features, kMaxFeat - 1);
-    SEEVCN_REQUIRE(pc_range && voxel_size && grid_size && num_voxels, "dynamic_voxelize: null pointer");
-    cudaStream_t st = as_stream(stream);
-    SEEVCN_CUDA_CHECK(cudaMemsetAsync(num_voxels, 0, sizeof(int), st));
-    if (num_points == 0 || max_voxels == 0) return SEEVCN_OK;
-    SEEVCN_REQUIRE(points && voxel_coords && voxel_features && voxel_counts && workspace,
-                   "dynamic_voxelize: null pointer");
+namespace {
+struct DynSrc {   // either one (N,1+C) matrix, or frames + object clouds
+    const float* points;
+    int n_frame_pts, pts_per_frame; const float* frame_pts;
+    int n_obj_pts, pts_per_obj; const float* obj_pts; const int* obj_frame;
+};
+
+int dynvox_run(const char* what, int num_points, int num_features, const DynSrc& src, const float* pc_range,
+               const float* voxel_size, const int* grid_size, int max_voxels, int sorted, int batch_hint,
+               int* voxel_coords, float* voxel_features, int* voxel_counts, int* num_voxels, void* workspace,
+               size_t workspace_bytes, cudaStream_t st) {
+    SEEVCN_PROF("dynamic_voxelize", st);
     const DynWs w = dyn_layout(num_points, num_features, max_voxels);
     if (workspace_bytes < w.total) {
-        seevcn_set_error("dynamic_voxelize: workspace %zu < %zu", workspace_bytes, w.total);
+        seevcn_set_error("%s: workspace %zu < %zu", what, workspace_bytes, w.total);
         return SEEVCN_E_WORKSPACE;
     }
     VoxGeom g;
     for (int i = 0; i < 3; ++i) {
         g.lo[i] = pc_range[i]; g.vs[i] = voxel_size[i]; g.g[i] = grid_size[i];
-        SEEVCN_REQUIRE(grid_size[i] > 0 && voxel_size[i] > 0.f, "dynamic_voxelize: bad grid");
+        SEEVCN_REQUIRE(grid_size[i] > 0 && voxel_size[i] > 0.f, "%s: bad grid", what);
     }
     char* ws = static_cast<char*>(workspace);
     auto* keys = reinterpret_cast<unsigned long long*>(ws + w.off_keys);
@@ -369,13 +392,19 @@ extern "C" int seevcn_dynamic_voxelize(int num_points, int num_features, const f
         o_keys = reinterpret_cast<unsigned long long*>(ws + w.off_sort_keys_in);
         SEEVCN_CUDA_CHECK(cudaMemsetAsync(o_keys, 0xff, (size_t)max_voxels * 8, st));
     }
-    if (w.accw == 4) {
-        dynvox_insert_kernel<4><<<grid_ins, 256, 0, st>>>(num_points, num_features, points, g, w.nslots - 1, keys, acc);
+    if (!src.points) {
+        dynvox_insert_frames_kernel<<<grid_ins, 256, 0, st>>>(src.n_frame_pts, src.pts_per_frame, src.frame_pts, src.n_obj_pts,
+                                                             src.pts_per_obj, src.obj_pts, src.obj_frame, g, w.nslots - 1, keys, acc);
+        SEEVCN_LAUNCH_CHECK();
+        dynvox_finalize_kernel<4><<<grid_fin, 256, 0, st>>>(w.nslots, num_features, g, keys, acc, max_voxels, o_coords,
+                                                           o_feat, o_cnt, o_keys, num_voxels);
+    } else if (w.accw == 4) {
+        dynvox_insert_kernel<4><<<grid_ins, 256, 0, st>>>(num_points, num_features, src.points, g, w.nslots - 1, keys, acc);
         SEEVCN_LAUNCH_CHECK();
         dynvox_finalize_kernel<4><<<grid_fin, 256, 0, st>>>(w.nslots, num_features, g, keys, acc, max_voxels, o_coords,
                                                            o_feat, o_cnt, o_keys, num_voxels);
     } else {
-        dynvox_insert_kernel<8><<<grid_ins, 256, 0, st>>>(num_points, num_features, points, g, w.nslots - 1, keys, acc);
+        dynvox_insert_kernel<8><<<grid_ins, 256, 0, st>>>(num_points, num_features, src.points, g, w.nslots - 1, keys, acc);
         SEEVCN_LAUNCH_CHECK();
         dynvox_finalize_kernel<8><<<grid_fin, 256, 0, st>>>(w.nslots, num_features, g, keys, acc, max_voxels, o_coords,
                                                            o_feat, o_cnt, o_keys, num_voxels);
@@ -400,6 +429,51 @@ extern "C" int seevcn_dynamic_voxelize(int num_points, int num_features, const f
         SEEVCN_LAUNCH_CHECK();
     }
     return SEEVCN_OK;
+}
+}  // namespace
+
+extern "C" int seevcn_dynamic_voxelize(int num_points, int num_features, const float* points, const float* pc_range,
+                                       const float* voxel_size, const int* grid_size, int max_voxels, int sorted,
+                                       int batch_hint, int* voxel_coords, float* voxel_features, int* voxel_counts, int* num_voxels,
+                                       void* workspace, size_t workspace_bytes, seevcn_stream_t stream) {
+    SEEVCN_REQUIRE(num_points >= 0 && max_voxels >= 0, "dynamic_voxelize: negative size");
+    if (batch_hint <= 0) batch_hint = 1 << 20;   // unknown batch size: sort on (almost) all key bits
+    SEEVCN_REQUIRE(num_features >= 3 && num_features < kMaxFeat, "dynamic_voxelize: num_features=%d outside [3,%d]",
+                   num_features, kMaxFeat - 1);
+    SEEVCN_REQUIRE(pc_range && voxel_size && grid_size && num_voxels, "dynamic_voxelize: null pointer");
+    cudaStream_t st = as_stream(stream);
+    SEEVCN_CUDA_CHECK(cudaMemsetAsync(num_voxels, 0, sizeof(int), st));
+    if (num_points == 0 || max_voxels == 0) return SEEVCN_OK;
+    SEEVCN_REQUIRE(points && voxel_coords && voxel_features && voxel_counts && workspace,
+                   "dynamic_voxelize: null pointer");
+    DynSrc src{};
+    src.points = points;
+    return dynvox_run("dynamic_voxelize", num_points, num_features, src, pc_range, voxel_size, grid_size, max_voxels, sorted,
+                      batch_hint, voxel_coords, voxel_features, voxel_counts, num_voxels, workspace, workspace_bytes, st);
+}
+
+extern "C" int seevcn_dynamic_voxelize_frames(int num_frames, int pts_per_frame, const float* frame_pts, int num_obj,
+                                              int pts_per_obj, const float* obj_pts, const int* obj_frame,
+                                              const float* pc_range, const float* voxel_size, const int* grid_size,
+                                              int max_voxels, int sorted, int* voxel_coords, float* voxel_features,
+                                              int* voxel_counts, int* num_voxels, void* workspace, size_t workspace_bytes,
+                                              seevcn_stream_t stream) {
+    SEEVCN_REQUIRE(num_frames >= 0 && pts_per_frame >= 0 && num_obj >= 0 && pts_per_obj >= 0 && max_voxels >= 0,
+                   "dynamic_voxelize_frames: negative size");
+    const long long n_frame = (long long)num_frames * pts_per_frame, n_obj = (long long)num_obj * pts_per_obj;
+    SEEVCN_REQUIRE(n_frame + n_obj < (1ll << 31), "dynamic_voxelize_frames: more than 2^31 points");
+    SEEVCN_REQUIRE(pc_range && voxel_size && grid_size && num_voxels, "dynamic_voxelize_frames: null pointer");
+    cudaStream_t st = as_stream(stream);
+    SEEVCN_CUDA_CHECK(cudaMemsetAsync(num_voxels, 0, sizeof(int), st));
+    if (n_frame + n_obj == 0 || max_voxels == 0) return SEEVCN_OK;
+    SEEVCN_REQUIRE((n_frame == 0 || frame_pts) && (n_obj == 0 || (obj_pts && obj_frame)) && voxel_coords && voxel_features &&
+                   voxel_counts && workspace, "dynamic_voxelize_frames: null pointer");
+    DynSrc src{};
+    src.n_frame_pts = (int)n_frame; src.pts_per_frame = pts_per_frame > 0 ? pts_per_frame : 1; src.frame_pts = frame_pts;
+    src.n_obj_pts = (int)n_obj; src.pts_per_obj = pts_per_obj > 0 ? pts_per_obj : 1; src.obj_pts = obj_pts; src.obj_frame = obj_frame;
+    return dynvox_run("dynamic_voxelize_frames", (int)(n_frame + n_obj), 3, src, pc_range, voxel_size, grid_size, max_voxels,
+                      sorted, num_frames > 0 ? num_frames : 1, voxel_coords, voxel_features, voxel_counts, num_voxels, workspace,
+                      workspace_bytes, st);
 }
 
 extern "C" size_t seevcn_hard_voxelize_workspace_bytes(int num_points, int max_points, int max_voxels) {

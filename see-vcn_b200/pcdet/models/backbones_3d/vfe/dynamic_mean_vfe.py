@@ -38,6 +38,40 @@ def dynamic_voxelize(points, point_cloud_range, voxel_size, grid_size, max_voxel
     return coords[:m], feats[:m], counts[:m]
 
 
+def dynamic_voxelize_frames(frame_pts, obj_pts, obj_frame, point_cloud_range, voxel_size, grid_size, sort=True):
+    """The frame pipeline's form: frame_pts (F,P,3) rows carry batch index = frame, obj_pts (O,S,3) rows carry
+    obj_frame[o]; same result as ``dynamic_voxelize`` on the concatenated [batch_idx,x,y,z] matrix, which is never
+    built.  No host sync: returns FULL-capacity tensors plus the device scalar M —
+    (coords (N,4), feats (N,3), counts (N,), num_voxels (1,) int32 CUDA); rows >= M are undefined."""
+    frame_pts = frame_pts.contiguous()
+    _abi.require_cuda(frame_pts)
+    F, P, _ = frame_pts.shape
+    dev = frame_pts.device
+    if obj_pts is not None and obj_pts.shape[0] > 0:
+        obj_pts = obj_pts.contiguous(); obj_frame = obj_frame.contiguous()
+        _abi.require_cuda(obj_pts, obj_frame)
+        assert obj_frame.dtype == torch.int32 and obj_frame.shape[0] == obj_pts.shape[0]
+        O, S, _ = obj_pts.shape
+    else:
+        obj_pts = obj_frame = None
+        O = S = 0
+    N = F * P + O * S
+    L = _abi.lib()
+    cap = max(N, 1)
+    ws = torch.empty(L.seevcn_dynamic_voxelize_workspace_bytes(N, 3, cap), dtype=torch.uint8, device=dev)
+    coords = torch.empty((cap, 4), dtype=torch.int32, device=dev)
+    feats = torch.empty((cap, 3), dtype=torch.float32, device=dev)
+    counts = torch.empty((cap,), dtype=torch.int32, device=dev)
+    num = torch.empty((1,), dtype=torch.int32, device=dev)
+    with torch.cuda.device(dev):
+        _abi.check(L.seevcn_dynamic_voxelize_frames(F, P, _abi.ptr(frame_pts), O, S, _abi.ptr(obj_pts), _abi.ptr(obj_frame),
+                                                    _abi.farray(point_cloud_range), _abi.farray(voxel_size),
+                                                    _abi.iarray(grid_size), cap, 1 if sort else 0, _abi.ptr(coords),
+                                                    _abi.ptr(feats), _abi.ptr(counts), _abi.ptr(num), _abi.ptr(ws),
+                                                    ws.numel(), _abi.stream()))
+    return coords, feats, counts, num
+
+
 class DynamicMeanVFE(VFETemplate):
     def __init__(self, model_cfg, num_point_features, voxel_size, grid_size, point_cloud_range, **kwargs):
         super().__init__(model_cfg=model_cfg)

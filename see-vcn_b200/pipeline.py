@@ -10,7 +10,7 @@ import numpy as np
 import torch
 
 from .pcdet.ops.roiaware_pool3d import roiaware_pool3d_utils as roi
-from .pcdet.models.backbones_3d.vfe.dynamic_mean_vfe import dynamic_voxelize
+from .pcdet.models.backbones_3d.vfe.dynamic_mean_vfe import dynamic_voxelize, dynamic_voxelize_frames  # noqa: F401
 from .see.surface_completion.models.vcn.models.build import MODELS
 from .see.surface_completion.models.vcn.utils.sampling import get_partial_mesh_batch, get_largest_cluster_batch
 
@@ -21,6 +21,11 @@ def resample_choice(count, n_points, rng):
     """Indices into the tiled cloud, as ResamplePoints draws them (data_transforms.py:254-262)."""
     reps = int(np.ceil(n_points / count))
     return rng.permutation(reps * count)[:n_points].astype(np.int32)
+
+
+class _Crop:
+    """An issued crop: device outputs + the box counts on their way to pinned host memory."""
+    __slots__ = ("points", "boxes", "idx", "counts", "offsets", "lists", "h_counts", "done")
 
 
 class CompletionPipeline:
@@ -39,14 +44,48 @@ class CompletionPipeline:
         self.voxel_cfg = voxel_cfg
         self.host_rng = host_rng              # True: numpy permutation per object on the host (reference's draw)
         self.cluster_eps = cluster_eps        # SURFACE_COMPLETION.VCN.CLUSTER_EPS; None skips the largest-cluster filter
+        self._side = None                     # stream of the small D2H copies (box counts, number of voxels)
+
+    def _side_stream(self):
+        if self._side is None:
+            self._side = torch.cuda.Stream(self.device)
+        return self._side
+
+    def _to_host_async(self, t):
+        """Device tensor -> pinned host copy on the side stream, ordered after the work queued so far on the
+        current stream.  Returns (pinned tensor, event)."""
+        compute = torch.cuda.current_stream(self.device)
+        ev = torch.cuda.Event(); ev.record(compute)
+        host = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
+        side = self._side_stream()
+        done = torch.cuda.Event()
+        with torch.cuda.stream(side):
+            side.wait_event(ev)
+            host.copy_(t, non_blocking=True)
+            done.record(side)
+        return host, done
+
+    # ---- stage A: crop.  Its box counts decide how many objects stage B launches for, so they travel to the host;
+    # issuing the NEXT batch's crop before this batch's stage B (run_stream) takes that wait off the critical path.
+    @torch.no_grad()
+    def crop_async(self, points, boxes):
+        h = _Crop()
+        h.points, h.boxes = points, boxes
+        h.idx, h.counts, h.offsets, h.lists = roi.crop_points_in_boxes(points, boxes)
+        h.h_counts, h.done = self._to_host_async(h.counts)
+        return h
 
     @torch.no_grad()
     def complete(self, points, boxes, seed=0):
         """points (F,P,3), boxes (F,T,7) CUDA -> dict with the per-object clouds.  One host sync (box counts)."""
-        F, P, _ = points.shape
-        T = boxes.shape[1]
-        idx, counts, offsets, lists = roi.crop_points_in_boxes(points, boxes)
-        cnt = counts.cpu().numpy()                                   # F*T ints: the only D2H before the results
+        return self.complete_from(self.crop_async(points, boxes), seed)
+
+    @torch.no_grad()
+    def complete_from(self, h, seed=0):
+        points, boxes = h.points, h.boxes
+        idx, counts, offsets, lists = h.idx, h.counts, h.offsets, h.lists
+        h.done.synchronize()                                         # F*T ints: the only D2H before the results
+        cnt = h.h_counts.numpy()
         keep = np.argwhere(cnt >= self.min_lidar_pts)                # SEE_VCN.py:71
         out = {"box_idxs_of_pts": idx, "box_counts": counts, "obj_frame": keep[:, 0].astype(np.int32),
                "obj_box": keep[:, 1].astype(np.int32)}
@@ -59,8 +98,8 @@ class CompletionPipeline:
             # the reference's own draw (numpy permutation on the host), for bit-for-bit comparisons
             rng = np.random.default_rng(seed)
             choice = np.stack([resample_choice(int(cnt[f, k]), self.resample_num, rng) for f, k in keep])
-            h = torch.from_numpy(np.concatenate([keep.astype(np.int32).T.reshape(-1), choice.reshape(-1)])).pin_memory()
-            d = h.to(points.device, non_blocking=True)
+            hp = torch.from_numpy(np.concatenate([keep.astype(np.int32).T.reshape(-1), choice.reshape(-1)])).pin_memory()
+            d = hp.to(points.device, non_blocking=True)
             obj_frame, obj_box, d_choice = d[:O], d[O:2 * O], d[2 * O:].view(O, self.resample_num)
             inp = roi.resample_gather(points, counts, offsets, lists, obj_frame.contiguous(), obj_box.contiguous(),
                                       d_choice.contiguous())
@@ -80,10 +119,61 @@ class CompletionPipeline:
                                                          total_pts=coarse.shape[1], period=sel_count)
         return out
 
+    # ---- stage B: complete + voxelize.  The number of voxels M is data dependent; it travels to the host on the side
+    # stream and `finalize` slices the full-capacity outputs with it, so nothing here blocks the host.
+    @torch.no_grad()
+    def run_from(self, h, seed=0, defer=False):
+        out = self.complete_from(h, seed)
+        points = h.points
+        F, P, _ = points.shape
+        completed = out.get("clustered", out["surface"])
+        coords, feats, nums, num_dev = dynamic_voxelize_frames(points, completed, out.get("obj_frame_dev"), *self.voxel_cfg,
+                                                              sort=True)
+        out["num_voxel_points"] = F * P + completed.shape[0] * completed.shape[1]
+        out["_frame_points"] = points
+        out["_vox_full"] = (coords, feats, nums, num_dev)
+        out["_h_num"], out["_num_done"] = self._to_host_async(num_dev)
+        out["_done"] = torch.cuda.Event()
+        out["_done"].record(torch.cuda.current_stream(self.device))
+        return out if defer else self.finalize(out)
+
+    def finalize(self, out):
+        """Waits for M only (not for the stream) and exposes voxel_coords / voxel_features / voxel_num_points."""
+        if "_vox_full" in out:
+            coords, feats, nums, _ = out.pop("_vox_full")
+            out["_num_done"].synchronize()
+            m = min(int(out["_h_num"][0]), coords.shape[0])
+            out.update(voxel_coords=coords[:m], voxel_features=feats[:m], voxel_num_points=nums[:m])
+        return out
+
     @torch.no_grad()
     def run(self, points, boxes, seed=0):
         """complete() + dynamic voxelization of [frame points ++ completed surfaces] -> detector input."""
-        out = self.complete(points, boxes, seed)
+        return self.run_from(self.crop_async(points, boxes), seed)
+
+    @torch.no_grad()
+    def run_stream(self, batches, seed=0):
+        """Streams batches of frames: yields run()'s dict for every (points (F,P,3), boxes (F,T,7)) CUDA pair, in order.
+        Batch i+1's crop is queued ahead of batch i's stage B and M is collected one batch late, so the host never
+        waits on the kernels it has just launched and the stream never drains between batches."""
+        it = iter(batches)
+        cur = next(it, None)
+        if cur is None:
+            return
+        h, prev = self.crop_async(*cur), None
+        while h is not None:
+            nxt = next(it, None)
+            h_next = self.crop_async(*nxt) if nxt is not None else None
+            out = self.run_from(h, seed, defer=True)
+            if prev is not None:
+                yield self.finalize(prev)
+            prev, h = out, h_next
+        yield self.finalize(prev)
+
+    @staticmethod
+    def voxel_points(out):
+        """The [batch_idx, x, y, z] matrix run() voxelized (frame points ++ completed clouds), materialised for checks."""
+        points = out["_frame_points"]
         F, P, _ = points.shape
         fid = torch.arange(F, device=points.device, dtype=torch.float32).view(F, 1, 1).expand(F, P, 1)
         rows = [torch.cat((fid, points), dim=2).view(F * P, 4)]
@@ -92,10 +182,7 @@ class CompletionPipeline:
             O, S, _ = completed.shape
             ofid = out["obj_frame_dev"].to(torch.float32).view(O, 1, 1).expand(O, S, 1)
             rows.append(torch.cat((ofid, completed), dim=2).view(O * S, 4))
-        vox_pts = torch.cat(rows, dim=0).contiguous()
-        coords, feats, nums = dynamic_voxelize(vox_pts, *self.voxel_cfg, sort=True, batch_size=F)
-        out.update(voxel_points=vox_pts, voxel_coords=coords, voxel_features=feats, voxel_num_points=nums)
-        return out
+        return torch.cat(rows, dim=0).contiguous()
 
 
 class HostStream:
@@ -103,17 +190,19 @@ class HostStream:
 
     The reference's driver (``sc_multiproc.py:60-94``) reads a frame from disk, completes its objects and
     writes a .pcd; here a batch of frames arrives in pinned memory and the completed clouds + voxel tensors
-    leave in pinned memory.  Three CUDA streams: the H2D copy of batch i+1 and the D2H copy of batch i-1
+    leave in pinned memory.  Three CUDA streams: the H2D copy of batch i+2 and the D2H copy of batch i-1
     overlap the kernels of batch i (the copy engines are otherwise idle; every batch still pays its own
-    copies inside the caller's timed region).
+    copies inside the caller's timed region), and batch i+1's crop is queued ahead of batch i's completion
+    stage so its box counts are on the host by the time they are needed.
 
         hs = HostStream(pipe, frames, pts_per_frame, boxes_per_frame)
         for res in hs.run(batches):      # batches: iterable of (points_pinned (F,P,3), boxes_pinned (F,T,7))
-            res["clustered"], res["voxel_coords"], ...   # pinned host views, valid until `depth` batches later
+            res["clustered"], res["voxel_coords"], ...   # pinned host views, valid until `depth - 1` batches later
     """
     KEYS = ("clustered", "voxel_coords", "voxel_features", "voxel_num_points")
 
-    def __init__(self, pipe, frames, pts_per_frame, boxes_per_frame, depth=2):
+    def __init__(self, pipe, frames, pts_per_frame, boxes_per_frame, depth=3):
+        assert depth >= 3
         self.pipe, self.depth = pipe, depth
         dev = pipe.device
         self.dev = dev
@@ -141,10 +230,8 @@ class HostStream:
 
     def _download(self, slot, out):
         views = {}
-        compute = torch.cuda.current_stream(self.dev)
-        done = torch.cuda.Event(); done.record(compute)
         with torch.cuda.stream(self.s_d2h):
-            self.s_d2h.wait_event(done)
+            self.s_d2h.wait_event(out["_done"])
             for k in self.KEYS:
                 src = out.get(k)
                 if src is None:
@@ -158,31 +245,49 @@ class HostStream:
         views["_keepalive"] = out      # device tensors stay referenced until the copy has landed
         return views
 
+    def _collect(self, pending):
+        self.ev_out[pending[0]].synchronize()
+        pending[1].pop("_keepalive", None)
+        return pending[1]
+
     def run(self, batches, seed=0):
         compute = torch.cuda.current_stream(self.dev)
         it = iter(batches)
-        nxt = next(it, None)
-        if nxt is None:
-            return
+        D = self.depth
+        state = {"up": 0, "more": True}
+
+        def upload_next():
+            if state["more"]:
+                nxt = next(it, None)
+                if nxt is None:
+                    state["more"] = False
+                else:
+                    self._upload(state["up"] % D, *nxt)
+                    state["up"] += 1
+
+        def crop(i):
+            compute.wait_event(self.ev_in[i % D])
+            return self.pipe.crop_async(self.d_pts[i % D], self.d_boxes[i % D])
+
         for e in self.ev_free:
             e.record(compute)
-        self._upload(0, *nxt)
-        i, pending = 0, None
-        while nxt is not None:
-            slot = i % self.depth
-            nxt = next(it, None)
-            if nxt is not None:
-                self._upload((i + 1) % self.depth, *nxt)         # overlaps the kernels below
-            compute.wait_event(self.ev_in[slot])
-            out = self.pipe.run(self.d_pts[slot], self.d_boxes[slot], seed=seed)
-            self.ev_free[slot].record(compute)
-            res = self._download(slot, out)                       # overlaps the next batch's kernels
-            if pending is not None:
-                self.ev_out[pending[0]].synchronize()
-                pending[1].pop("_keepalive", None)
-                yield pending[1]
-            pending = (slot, res)
-            i += 1
-        self.ev_out[pending[0]].synchronize()
-        pending[1].pop("_keepalive", None)
-        yield pending[1]
+        upload_next(); upload_next()
+        if state["up"] == 0:
+            return
+        h, i = crop(0), 0
+        prev = pending = None          # prev: stage B queued, M not read yet; pending: D2H issued, not yet on the host
+        while h is not None:
+            upload_next()                                            # batch i+2: overlaps the kernels below
+            h_next = crop(i + 1) if i + 1 < state["up"] else None    # ahead of batch i's stage B
+            out = self.pipe.run_from(h, seed, defer=True)
+            self.ev_free[i % D].record(compute)
+            if prev is not None:
+                res = self._download(prev[0] % D, self.pipe.finalize(prev[1]))   # overlaps this batch's kernels
+                if pending is not None:
+                    yield self._collect(pending)
+                pending = (prev[0] % D, res)
+            prev, h, i = (i, out), h_next, i + 1
+        res = self._download(prev[0] % D, self.pipe.finalize(prev[1]))
+        if pending is not None:
+            yield self._collect(pending)
+        yield self._collect((prev[0] % D, res))

@@ -21,7 +21,7 @@ def get_partial_mesh_batch(batch_partial, batch_complete, k=20, surface_pts=1024
     out = torch.empty((B, surface_pts, 3), dtype=torch.float32, device=batch_partial.device)
     cnt = torch.empty((B,), dtype=torch.int32, device=batch_partial.device)
     L = _abi.lib()
-    ws = torch.empty(L.seevcn_knn_surface_select_workspace_bytes(B, R), dtype=torch.uint8, device=batch_partial.device)
+    ws = torch.empty(L.seevcn_knn_surface_select_workspace_bytes(B, Np, R), dtype=torch.uint8, device=batch_partial.device)
     with torch.cuda.device(batch_partial.device):
         _abi.check(L.seevcn_knn_surface_select(B, Np, R, k, surface_pts, _abi.ptr(batch_partial),
                                                _abi.ptr(batch_complete), _abi.ptr(out), _abi.ptr(cnt),

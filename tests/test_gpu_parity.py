@@ -242,6 +242,32 @@ def test_surface_select_with_duplicate_and_padded_objects(cuda):
     assert wcnt[2] == 20
 
 
+@pytest.mark.parametrize("cfg", [(2, 2048, 16384, 20), (2, 300, 5000, 16), (3, 1024, 4096, 64), (2, 37, 40, 5), (1, 1, 1, 1)])
+def test_surface_select_shapes_vs_oracle(cuda, cfg):
+    """C4 (2048 partial points against a 16,384-point completed cloud: sorted cloud read from global memory)
+    and ragged sizes; the sweep along the longest axis must give exactly the brute-force union."""
+    B, NP, R, k = cfg
+    part, dense, _ = synth.make_object_clouds(47, B, NP, R)
+    out, cnt = get_partial_mesh_batch(dev(part, cuda), dev(dense, cuda), k=k, surface_pts=1500, return_count=True)
+    want, wcnt = oracle.get_partial_mesh_batch(part, dense, k=k, surface_pts=1500)
+    np.testing.assert_array_equal(cnt.cpu().numpy(), wcnt)
+    np.testing.assert_array_equal(out.cpu().numpy(), want)
+
+
+def test_surface_select_degenerate_axis_and_exact_ties(cuda):
+    """A flat cloud (two axes constant) and a lattice full of equidistant neighbours: ties go to the lower index."""
+    rng = np.random.default_rng(5)
+    g = np.stack(np.meshgrid(np.arange(16), np.arange(16), np.arange(4), indexing="ij"), -1).reshape(1, -1, 3).astype(np.float32)
+    g = g[:, rng.permutation(g.shape[1])]
+    flat = np.zeros((1, 1024, 3), np.float32); flat[0, :, 1] = rng.permutation(1024) * 0.25
+    dense = np.concatenate([g, flat])
+    part = np.concatenate([g[:, :512] + np.float32(0.5), flat[:, ::2] + np.float32(0.125)])
+    out, cnt = get_partial_mesh_batch(dev(part, cuda), dev(dense, cuda), k=7, return_count=True)
+    want, wcnt = oracle.get_partial_mesh_batch(part, dense, k=7)
+    np.testing.assert_array_equal(cnt.cpu().numpy(), wcnt)
+    np.testing.assert_array_equal(out.cpu().numpy(), want)
+
+
 def test_largest_cluster_vs_oracle(cuda):
     _, dense, _ = synth.make_object_clouds(51, 4, 64, 1024)
     pc = dense.copy()
@@ -420,6 +446,49 @@ def test_dynamic_voxelize_vs_oracle(cuda, nframes):
     order = np.lexsort(c.cpu().numpy()[:, [1, 2, 3, 0]].T)   # lexsort: last key is primary -> b, x, y, z (coords are b,z,y,x)
     np.testing.assert_array_equal(c.cpu().numpy()[order], want_c)
     np.testing.assert_array_equal(n.cpu().numpy()[order], want_n)
+
+
+def test_dynamic_voxelize_frames_matches_concatenated_matrix(cuda):
+    """The two-source form (frames + object clouds, no [b,x,y,z] matrix) against the oracle on the concatenation."""
+    from seevcn_b200.pcdet.models.backbones_3d.vfe.dynamic_mean_vfe import dynamic_voxelize_frames
+    from seevcn_b200.pipeline import WAYMO_VOXEL_CFG
+    rng = np.random.default_rng(11)
+    F, P, O, S = 3, 5000, 7, 256
+    frames = (rng.standard_normal((F, P, 3)) * [30, 30, 1.5]).astype(np.float32)
+    objs = (rng.standard_normal((O, S, 3)) * [2, 1, 0.7] + rng.standard_normal((O, 1, 3)) * [20, 20, 0.3]).astype(np.float32)
+    obj_frame = rng.integers(0, F, O).astype(np.int32)
+    rows = [np.concatenate([np.full((P, 1), f, np.float32), frames[f]], 1) for f in range(F)]
+    rows += [np.concatenate([np.full((S, 1), obj_frame[o], np.float32), objs[o]], 1) for o in range(O)]
+    wc, wf, wn = oracle.dynamic_voxelize(np.concatenate(rows), *WAYMO_VOXEL_CFG)
+    for objs_d, of_d in ((dev(objs, cuda), dev(obj_frame, cuda)), (None, None)):
+        coords, feats, counts, num = dynamic_voxelize_frames(dev(frames, cuda), objs_d, of_d, *WAYMO_VOXEL_CFG)
+        m = int(num.item())
+        if objs_d is None:
+            wc, wf, wn = oracle.dynamic_voxelize(np.concatenate(rows[:F]), *WAYMO_VOXEL_CFG)
+        assert m == len(wc)
+        np.testing.assert_array_equal(coords[:m].cpu().numpy(), wc)
+        np.testing.assert_array_equal(counts[:m].cpu().numpy(), wn)
+        np.testing.assert_allclose(feats[:m].cpu().numpy(), wf, rtol=1e-5, atol=1e-5)
+
+
+def test_pipeline_stream_equals_single_runs(cuda):
+    """run_stream (crop look-ahead, deferred voxel count) and HostStream give what run() gives batch by batch."""
+    from seevcn_b200.pipeline import CompletionPipeline, HostStream
+    pipe = CompletionPipeline("VCN_VC", oracle.make_state_dict("VCN_VC", seed=0), cuda, sel_k=10, cluster_eps=0.3)
+    batches = [synth.make_stream(2, n_beams=32, n_az=1090, n_boxes=10, first_seed=300 + 2 * i) for i in range(4)]
+    dbat = [(dev(p, cuda), dev(b, cuda)) for p, b in batches]
+    singles = [pipe.run(p, b, seed=0) for p, b in dbat]
+    streamed = list(pipe.run_stream(iter(dbat), seed=0))
+    hs = HostStream(pipe, 2, batches[0][0].shape[1], batches[0][1].shape[1])
+    pinned = [(torch.from_numpy(p).pin_memory(), torch.from_numpy(b).pin_memory()) for p, b in batches]
+    hosted = [{k: v.clone() for k, v in res.items()} for res in hs.run(iter(pinned), seed=0)]
+    assert len(streamed) == len(hosted) == 4
+    for a, b, c in zip(singles, streamed, hosted):
+        assert a["input"].shape[0] > 0
+        for key in ("clustered", "voxel_coords", "voxel_num_points"):
+            np.testing.assert_array_equal(a[key].cpu().numpy(), b[key].cpu().numpy())
+            np.testing.assert_array_equal(a[key].cpu().numpy(), c[key].numpy())
+        np.testing.assert_allclose(a["voxel_features"].cpu().numpy(), c["voxel_features"].numpy(), rtol=1e-5, atol=1e-5)
 
 
 def test_dynamic_voxelize_extra_features_and_overflow_batch(cuda):
