@@ -53,6 +53,7 @@ def lib():
         L.orc_hard_voxelize.restype = _I
         L.orc_mean_vfe.argtypes = [_I, _I, _I, _f, _f, _f]
         L.orc_chamfer.argtypes = [_I, _I, _I, _f, _f, _f]
+        L.orc_nearest_dist.argtypes = [_I, _I, _f, _f, np.ctypeslib.ndpointer(dtype=np.float64, flags="C_CONTIGUOUS")]
         _LIB = L
     return _LIB
 
@@ -159,6 +160,46 @@ def get_largest_cluster_batch(pc, eps=0.4, min_points=1, total_pts=1024):
     cnt = np.empty((B,), np.int32)
     lib().orc_largest_cluster(B, N, total_pts, float(eps), int(min_points), pc, out, cnt)
     return out, cnt
+
+
+# --------------------------------------------------------------------------- splice --
+def nearest_dist(points, completed, brute=False):
+    """Distance (float64) from every row of points (P,3) to its nearest row of completed (K,3): what
+    open3d's compute_point_cloud_distance returns (SEE_VCN.py:258).  KD-tree (scipy) by default, the C
+    brute force with brute=True (small cases; the two are checked against each other in tests/test_oracle.py)."""
+    points, completed = _c(points), _c(completed)
+    if len(completed) == 0:
+        return np.full((len(points),), np.inf)
+    if brute:
+        d = np.empty((len(points),), np.float64)
+        lib().orc_nearest_dist(len(points), len(completed), points, completed, d)
+        return d
+    from scipy.spatial import cKDTree
+    return cKDTree(completed.astype(np.float64)).query(points.astype(np.float64), k=1)[0]
+
+
+def replace_with_completed_pts(points, sc_instances, point_dist_thresh=0.1, brute=False):
+    """ref: SEE_VCN.replace_with_completed_pts, see/surface_completion/SEE_VCN.py:247-265 — PARITY UNPINNED
+    (open3d absent).  points (P,3), sc_instances (K,3) or None -> (merged (K+kept,3) = vstack(sc_instances,
+    surviving originals in order), keep mask (P,) bool)."""
+    points = _c(points)
+    if sc_instances is None:
+        return points, np.ones((len(points),), bool)
+    sc_instances = _c(sc_instances)
+    keep = ~(nearest_dist(points, sc_instances, brute) < point_dist_thresh)
+    return np.vstack((sc_instances, points[keep])), keep
+
+
+def all_instances(clustered, counts=None):
+    """ref: SEE_VCN.py:244 — np.unique(np.vstack(sc_model_ret['clustered']), axis=0): the distinct completed points of
+    all objects of a frame, rows in lexicographic order.  counts (O,) limits object o to its first counts[o] rows
+    (objects whose every point was noise contribute nothing)."""
+    clustered = _c(clustered)
+    rows = [clustered[o][: (len(clustered[o]) if counts is None else int(counts[o]))] for o in range(len(clustered))]
+    rows = [r for r in rows if len(r)]
+    if not rows:
+        return np.zeros((0, 3), np.float32)
+    return np.unique(np.vstack(rows), axis=0)
 
 
 # ------------------------------------------------------------------------- voxelize --

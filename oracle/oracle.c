@@ -147,9 +147,10 @@ void orc_knn(int B, int R, int Q, int K, const float* ref, const float* query, f
                 const float* rp = ref + ((long long)b * R + r) * 3;
                 const double dx = (double)rp[0] - qp[0], dy = (double)rp[1] - qp[1], dz = (double)rp[2] - qp[2];
                 double d = dx * dx + dy * dy + dz * dz; int ci = r;
-                if (d < bd[K - 1]) {
-                    for (int j = 0; j < K; ++j)
-                        if (d < bd[j]) { const double td = bd[j]; bd[j] = d; d = td; const int ti = bi[j]; bi[j] = ci; ci = ti; }
+                if (d < bd[K - 1]) {   /* stable insertion: after the first strictly larger entry, shift the rest (ties keep the lower index) */
+                    int j = K - 1;
+                    while (j > 0 && d < bd[j - 1]) { bd[j] = bd[j - 1]; bi[j] = bi[j - 1]; --j; }
+                    bd[j] = d; bi[j] = ci;
                 }
             }
             for (int j = 0; j < K; ++j) {
@@ -343,4 +344,24 @@ void orc_chamfer(int B, int N, int M, const float* a, const float* b, float* d1)
             }
             d1[(long long)bi * N + i] = (float)best;
         }
+}
+
+/* ref: SEE_VCN.replace_with_completed_pts, see/surface_completion/SEE_VCN.py:247-265 (demo twin
+ * demo/see_vcn_dataset.py:127-135): dist = original_pcd.compute_point_cloud_distance(completed) — open3d,
+ * NOT vendored (setup.py:25 pins 0.14.1): per original point the Euclidean distance to its nearest completed
+ * point, evaluated on float64 copies of the points — PARITY UNPINNED.  Brute-force restatement: nearest
+ * distance (double) per original point; the caller drops the points with dist < thresh. */
+void orc_nearest_dist(int P, int K, const float* pts, const float* completed, double* dist) {
+#pragma omp parallel for schedule(static)
+    for (int i = 0; i < P; ++i) {
+        const float* p = pts + (long long)i * 3;
+        double best = INFINITY;
+        for (int j = 0; j < K; ++j) {
+            const float* q = completed + (long long)j * 3;
+            const double dx = (double)p[0] - (double)q[0], dy = (double)p[1] - (double)q[1], dz = (double)p[2] - (double)q[2];
+            const double d2 = (dx * dx + dy * dy) + dz * dz;
+            if (d2 < best) best = d2;
+        }
+        dist[i] = sqrt(best);
+    }
 }

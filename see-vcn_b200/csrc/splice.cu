@@ -1,0 +1,356 @@
+// Splice step — drop the raw frame points that the completed object clouds replace, then merge.
+//
+// Replaces SEE_VCN.replace_with_completed_pts (see/surface_completion/SEE_VCN.py:247-265; demo twin
+// demo/see_vcn_dataset.py:127-135): `dist = original.compute_point_cloud_distance(completed)` (open3d: nearest
+// completed point per original point, float64), `keep = !(dist < thresh)`, `vstack(completed, original[keep])`.
+// The reference builds a KD-tree over ~50 k completed points per frame on the host and queries 180 k points.
+//
+// Design (B200): HBM-bound — 12 B/point in + 1 B/point out for the mask, the completed clouds (<= 12 KB per object)
+// stay in L2.  The completed points of a frame come as per-object blocks, so the spatial index is free: one
+// thresh-expanded axis-aligned bound per object (splice_bounds_kernel, a warp per object).  splice_mask_kernel stages a
+// tile of 1024 points in shared memory (same 128-bit streaming loads as the crop), tests every point against the
+// bounds of its frame's objects from shared memory, and only the few points inside a bound (the object's own LiDAR
+// returns and their surroundings) pay for a distance scan: the warp takes such points one at a time, its 32 lanes
+// stride over the object's rows with an early exit as soon as one row is closer than thresh.
+//
+// Exactness: a squared distance is screened in fp32 (relative error < 1e-6 from exact fp32 inputs); pairs within a
+// 1e-5 relative band around thresh^2 are re-evaluated the way the reference does — float64 differences,
+// (dx*dx + dy*dy) + dz*dz, sqrt, `< thresh` — so the mask equals the float64 evaluation bit for bit.
+#include "common.cuh"
+
+namespace {
+
+constexpr int kThreads = 256;
+constexpr int kPtsPerThread = 4;
+constexpr int kTilePts = kThreads * kPtsPerThread;   // 1024 points = 12 KB
+constexpr int kObjChunk = 256;                       // object bounds staged per pass
+
+struct __align__(16) ObjBound {   // 32 B
+    float lo[3]; int count;
+    float hi[3]; int frame;
+};
+
+// One warp per object: bound of its first count rows, expanded by thresh and rounded outward.
+__global__ void __launch_bounds__(kThreads)
+splice_bounds_kernel(int num_obj, int pts_per_obj, const float* __restrict__ obj_pts, const int* __restrict__ obj_count,
+                     const int* __restrict__ obj_frame, float thresh, ObjBound* __restrict__ bounds) {
+    const int o = blockIdx.x * (kThreads / 32) + warp_id();
+    if (o >= num_obj) return;
+    const int cnt = obj_count ? min(max(obj_count[o], 0), pts_per_obj) : pts_per_obj;
+    const float* p = obj_pts + (size_t)o * pts_per_obj * 3;
+    float lo[3] = {INFINITY, INFINITY, INFINITY}, hi[3] = {-INFINITY, -INFINITY, -INFINITY};
+    for (int r = lane_id(); r < cnt; r += 32) {
+#pragma unroll
+        for (int a = 0; a < 3; ++a) { const float v = p[r * 3 + a]; lo[a] = fminf(lo[a], v); hi[a] = fmaxf(hi[a], v); }
+    }
+#pragma unroll
+    for (int a = 0; a < 3; ++a)
+        for (int s = 16; s > 0; s >>= 1) {
+            lo[a] = fminf(lo[a], __shfl_xor_sync(0xffffffffu, lo[a], s));
+            hi[a] = fmaxf(hi[a], __shfl_xor_sync(0xffffffffu, hi[a], s));
+        }
+    if (lane_id() == 0) {
+        ObjBound b;
+        // any point within thresh (float64) of a row lies inside [lo - t, hi + t]; directed rounding + one more
+        // ulp of slack keeps the float test conservative
+        const float t = __fmul_ru(thresh, 1.000001f);
+#pragma unroll
+        for (int a = 0; a < 3; ++a) { b.lo[a] = __fsub_rd(lo[a], t); b.hi[a] = __fadd_ru(hi[a], t); }
+        b.count = cnt; b.frame = obj_frame[o];
+        bounds[o] = b;
+    }
+}
+
+// first index in [0, n) with frame[idx] >= f   (obj_frame is non-decreasing)
+__device__ __forceinline__ int lower_bound_frame(const ObjBound* __restrict__ b, int n, int f) {
+    int lo = 0, hi = n;
+    while (lo < hi) { const int mid = (lo + hi) >> 1; if (b[mid].frame < f) lo = mid + 1; else hi = mid; }
+    return lo;
+}
+
+// Is any of the object's rows closer than thresh to (x, y, z)?  Whole warp, uniform arguments.
+__device__ __forceinline__ bool warp_near_object(float x, float y, float z, const float* __restrict__ rows, int count,
+                                                 float t2_in, float t2_out, double thresh) {
+    for (int r0 = 0; r0 < count; r0 += 128) {
+        bool hit = false;
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int r = r0 + u * 32 + lane_id();
+            if (r < count) {
+                const float qx = rows[r * 3], qy = rows[r * 3 + 1], qz = rows[r * 3 + 2];
+                const float dx = x - qx, dy = y - qy, dz = z - qz;
+                const float d2 = dx * dx + dy * dy + dz * dz;
+                if (d2 < t2_in) hit = true;
+                else if (d2 <= t2_out) {   // guard band: the reference's float64 evaluation
+                    const double ex = (double)x - (double)qx, ey = (double)y - (double)qy, ez = (double)z - (double)qz;
+                    const double e2 = __dadd_rn(__dadd_rn(__dmul_rn(ex, ex), __dmul_rn(ey, ey)), __dmul_rn(ez, ez));
+                    if (sqrt(e2) < thresh) hit = true;
+                }
+            }
+        }
+        if (__any_sync(0xffffffffu, hit)) return true;
+    }
+    return false;
+}
+
+// grid (ceil(P / 1024), F).  keep (F,P) u8: 1 = the point survives.  tile_kept (F, ntiles) or NULL.
+__global__ void __launch_bounds__(kThreads)
+splice_mask_kernel(int pts_per_frame, const float* __restrict__ frame_pts, int num_obj, int pts_per_obj,
+                   const float* __restrict__ obj_pts, const ObjBound* __restrict__ bounds, float thresh_f, double thresh,
+                   unsigned char* __restrict__ keep, int* __restrict__ tile_kept) {
+    __shared__ __align__(16) float s_pts[kTilePts * 3 + 8];
+    __shared__ ObjBound s_obj[kObjChunk];
+    __shared__ int s_range[2];
+    __shared__ int s_cnt[kThreads / 32];
+
+    const int f = blockIdx.y, tile = blockIdx.x;
+    const int p0 = tile * kTilePts;
+    const int npts = min(kTilePts, pts_per_frame - p0);
+    const float* src = frame_pts + ((size_t)f * pts_per_frame + p0) * 3;
+    const int mis = stage_floats(s_pts, src, npts * 3);
+    if (threadIdx.x == 0) s_range[0] = lower_bound_frame(bounds, num_obj, f);
+    if (threadIdx.x == 32) s_range[1] = lower_bound_frame(bounds, num_obj, f + 1);
+    __syncthreads();
+    const int obj_lo = s_range[0], obj_hi = s_range[1];
+
+    float px[kPtsPerThread], py[kPtsPerThread], pz[kPtsPerThread];
+    unsigned removed = 0;   // bit e: point e*256 + tid is replaced
+#pragma unroll
+    for (int e = 0; e < kPtsPerThread; ++e) {
+        const int i = e * kThreads + threadIdx.x;
+        const bool ok = i < npts;
+        px[e] = ok ? s_pts[mis + i * 3] : INFINITY;   // +inf fails every bound test
+        py[e] = ok ? s_pts[mis + i * 3 + 1] : INFINITY;
+        pz[e] = ok ? s_pts[mis + i * 3 + 2] : INFINITY;
+    }
+    const float t2 = thresh_f * thresh_f;
+    const float t2_in = t2 * (1.f - 1e-5f), t2_out = t2 * (1.f + 1e-5f);
+
+    for (int c0 = obj_lo; c0 < obj_hi; c0 += kObjChunk) {
+        const int nc = min(kObjChunk, obj_hi - c0);
+        __syncthreads();
+        for (int j = threadIdx.x; j < nc * 2; j += kThreads)
+            reinterpret_cast<float4*>(s_obj)[j] = reinterpret_cast<const float4*>(bounds + c0)[j];
+        __syncthreads();
+        for (int j = 0; j < nc; ++j) {
+            const ObjBound& b = s_obj[j];
+            unsigned cand = 0;
+#pragma unroll
+            for (int e = 0; e < kPtsPerThread; ++e) {
+                const bool in = (px[e] >= b.lo[0]) & (px[e] <= b.hi[0]) & (py[e] >= b.lo[1]) & (py[e] <= b.hi[1]) &
+                                (pz[e] >= b.lo[2]) & (pz[e] <= b.hi[2]) & !((removed >> e) & 1u);
+                cand |= (unsigned)in << e;
+            }
+            if (!__any_sync(0xffffffffu, cand != 0)) continue;
+            const float* rows = obj_pts + (size_t)(c0 + j) * pts_per_obj * 3;
+#pragma unroll
+            for (int e = 0; e < kPtsPerThread; ++e) {
+                unsigned m = __ballot_sync(0xffffffffu, (cand >> e) & 1u);
+                while (m) {
+                    const int src_lane = __ffs(m) - 1;
+                    m &= m - 1;
+                    const float x = __shfl_sync(0xffffffffu, px[e], src_lane);
+                    const float y = __shfl_sync(0xffffffffu, py[e], src_lane);
+                    const float z = __shfl_sync(0xffffffffu, pz[e], src_lane);
+                    const bool near = warp_near_object(x, y, z, rows, b.count, t2_in, t2_out, thresh);
+                    if (near && lane_id() == src_lane) removed |= 1u << e;
+                }
+            }
+        }
+    }
+
+    int kept = 0;
+#pragma unroll
+    for (int e = 0; e < kPtsPerThread; ++e) {
+        const int i = e * kThreads + threadIdx.x;
+        if (i < npts) {
+            const unsigned k = ((removed >> e) & 1u) ^ 1u;
+            keep[(size_t)f * pts_per_frame + p0 + i] = (unsigned char)k;
+            kept += (int)k;
+        }
+    }
+    if (tile_kept) {
+        for (int s = 16; s > 0; s >>= 1) kept += __shfl_xor_sync(0xffffffffu, kept, s);
+        if (lane_id() == 0) s_cnt[warp_id()] = kept;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            int tot = 0;
+            for (int w = 0; w < kThreads / 32; ++w) tot += s_cnt[w];
+            tile_kept[(size_t)f * gridDim.x + tile] = tot;
+        }
+    }
+}
+
+// Block-wide exclusive scan of one int per thread (256 threads); returns the exclusive prefix, total in *total.
+__device__ __forceinline__ int block_exscan(int v, int* s_warp, int* total) {
+    int inc = v;
+    for (int s = 1; s < 32; s <<= 1) { const int n = __shfl_up_sync(0xffffffffu, inc, s); if (lane_id() >= s) inc += n; }
+    __syncthreads();
+    if (lane_id() == 31) s_warp[warp_id()] = inc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int t = 0;
+        for (int w = 0; w < kThreads / 32; ++w) { const int c = s_warp[w]; s_warp[w] = t; t += c; }
+        s_warp[kThreads / 32] = t;
+    }
+    __syncthreads();
+    *total = s_warp[kThreads / 32];
+    return s_warp[warp_id()] + inc - v;
+}
+
+// grid F: row offsets of the frame's merged cloud = [object rows ..., surviving frame points by tile ...].
+__global__ void __launch_bounds__(kThreads)
+splice_offsets_kernel(int num_obj, int ntiles, const ObjBound* __restrict__ bounds, const int* __restrict__ tile_kept,
+                      int* __restrict__ obj_off, int* __restrict__ tile_off, int* __restrict__ merged_count,
+                      int* __restrict__ completed_count) {
+    __shared__ int s_warp[kThreads / 32 + 1];
+    __shared__ int s_range[2];
+    const int f = blockIdx.x;
+    if (threadIdx.x == 0) s_range[0] = lower_bound_frame(bounds, num_obj, f);
+    if (threadIdx.x == 32) s_range[1] = lower_bound_frame(bounds, num_obj, f + 1);
+    __syncthreads();
+    int base = 0;
+    for (int o0 = s_range[0]; o0 < s_range[1]; o0 += kThreads) {
+        const int o = o0 + threadIdx.x;
+        const int c = o < s_range[1] ? bounds[o].count : 0;
+        int tot;
+        const int ex = block_exscan(c, s_warp, &tot);
+        if (o < s_range[1]) obj_off[o] = base + ex;
+        base += tot;
+    }
+    if (threadIdx.x == 0 && completed_count) completed_count[f] = base;
+    for (int t0 = 0; t0 < ntiles; t0 += kThreads) {
+        const int t = t0 + threadIdx.x;
+        const int c = t < ntiles ? tile_kept[(size_t)f * ntiles + t] : 0;
+        int tot;
+        const int ex = block_exscan(c, s_warp, &tot);
+        if (t < ntiles) tile_off[(size_t)f * ntiles + t] = base + ex;
+        base += tot;
+    }
+    if (threadIdx.x == 0) merged_count[f] = base;
+}
+
+// grid (ntiles + ceil(objects' rows ...), F) is awkward for ragged object lists, so two launches share this file:
+// surviving frame points, stable (ascending point index) within the frame.
+__global__ void __launch_bounds__(kThreads)
+splice_scatter_points_kernel(int pts_per_frame, const float* __restrict__ frame_pts, const unsigned char* __restrict__ keep,
+                             const int* __restrict__ tile_off, int out_stride, float* __restrict__ merged) {
+    __shared__ int s_w[kPtsPerThread][kThreads / 32];
+    const int f = blockIdx.y, tile = blockIdx.x;
+    const int p0 = tile * kTilePts;
+    const int npts = min(kTilePts, pts_per_frame - p0);
+    unsigned mine = 0, ball[kPtsPerThread];
+#pragma unroll
+    for (int e = 0; e < kPtsPerThread; ++e) {
+        const int i = e * kThreads + threadIdx.x;
+        const bool k = i < npts && keep[(size_t)f * pts_per_frame + p0 + i] != 0;
+        ball[e] = __ballot_sync(0xffffffffu, k);
+        mine |= (unsigned)k << e;
+        if (lane_id() == 0) s_w[e][warp_id()] = __popc(ball[e]);
+    }
+    __syncthreads();
+    const int base = tile_off[(size_t)f * gridDim.x + tile];
+#pragma unroll
+    for (int e = 0; e < kPtsPerThread; ++e) {
+        if (!((mine >> e) & 1u)) continue;
+        int rank = __popc(ball[e] & ((1u << lane_id()) - 1));
+        for (int ee = 0; ee < kPtsPerThread; ++ee)
+            for (int w = 0; w < kThreads / 32; ++w)
+                if (ee < e || (ee == e && w < warp_id())) rank += s_w[ee][w];
+        const int i = e * kThreads + threadIdx.x;
+        const float* p = frame_pts + ((size_t)f * pts_per_frame + p0 + i) * 3;
+        float* o = merged + ((size_t)f * out_stride + base + rank) * 3;
+        o[0] = p[0]; o[1] = p[1]; o[2] = p[2];
+    }
+}
+
+// grid (ceil(S*3 / 256), O): the first count rows of every object go to the head of its frame's merged cloud.
+__global__ void __launch_bounds__(kThreads)
+splice_scatter_objects_kernel(int pts_per_obj, const float* __restrict__ obj_pts, const ObjBound* __restrict__ bounds,
+                              const int* __restrict__ obj_off, int out_stride, float* __restrict__ merged) {
+    const int o = blockIdx.y;
+    const ObjBound b = bounds[o];
+    const int j = blockIdx.x * kThreads + threadIdx.x;
+    if (j >= b.count * 3) return;
+    merged[((size_t)b.frame * out_stride + obj_off[o]) * 3 + j] = obj_pts[(size_t)o * pts_per_obj * 3 + j];
+}
+
+struct SpliceWs {
+    size_t off_bounds, off_tile_kept, off_tile_off, off_obj_off, total;
+};
+SpliceWs splice_layout(int num_frames, int pts_per_frame, int num_obj) {
+    SpliceWs w;
+    const size_t ntiles = (size_t)div_up(pts_per_frame > 0 ? pts_per_frame : 1, kTilePts);
+    size_t off = 0;
+    w.off_bounds = off;    off = align_up(off + sizeof(ObjBound) * (size_t)(num_obj > 0 ? num_obj : 1), 256);
+    w.off_tile_kept = off; off = align_up(off + 4 * ntiles * (size_t)(num_frames > 0 ? num_frames : 1), 256);
+    w.off_tile_off = off;  off = align_up(off + 4 * ntiles * (size_t)(num_frames > 0 ? num_frames : 1), 256);
+    w.off_obj_off = off;   off = align_up(off + 4 * (size_t)(num_obj > 0 ? num_obj : 1), 256);
+    w.total = off;
+    return w;
+}
+
+}  // namespace
+
+extern "C" size_t seevcn_splice_workspace_bytes(int num_frames, int pts_per_frame, int num_obj) {
+    return splice_layout(num_frames, pts_per_frame, num_obj).total;
+}
+
+extern "C" int seevcn_splice(int num_frames, int pts_per_frame, const float* frame_pts, int num_obj, int pts_per_obj,
+                             const float* obj_pts, const int* obj_count, const int* obj_frame, double thresh,
+                             unsigned char* keep, int out_stride, float* merged, int* merged_count, int* completed_count,
+                             void* workspace, size_t workspace_bytes, seevcn_stream_t stream) {
+    SEEVCN_REQUIRE(num_frames >= 0 && pts_per_frame >= 0 && num_obj >= 0 && pts_per_obj >= 0, "splice: negative size");
+    SEEVCN_REQUIRE(thresh >= 0.0 && thresh < 1e18, "splice: thresh=%g", thresh);
+    SEEVCN_REQUIRE((long long)num_frames * pts_per_frame < (1ll << 31) && (long long)num_obj * pts_per_obj * 3 < (1ll << 31),
+                   "splice: more than 2^31 elements");
+    SEEVCN_REQUIRE(num_frames <= 65535 && num_obj <= 65535, "splice: more than 65535 frames or objects per call");
+    cudaStream_t st = as_stream(stream);
+    if (num_frames == 0) return SEEVCN_OK;
+    SEEVCN_REQUIRE(keep || pts_per_frame == 0, "splice: null keep mask");
+    SEEVCN_REQUIRE(pts_per_frame == 0 || frame_pts, "splice: null frame points");
+    SEEVCN_REQUIRE(num_obj == 0 || pts_per_obj == 0 || (obj_pts && obj_frame), "splice: null object arrays");
+    SEEVCN_REQUIRE(!merged || (merged_count && out_stride >= 0), "splice: merged output needs merged_count and out_stride");
+    const SpliceWs w = splice_layout(num_frames, pts_per_frame, num_obj);
+    if (workspace_bytes < w.total || !workspace) {
+        seevcn_set_error("splice: workspace %zu < %zu", workspace_bytes, w.total);
+        return SEEVCN_E_WORKSPACE;
+    }
+    SEEVCN_PROF("splice", st);
+    char* ws = static_cast<char*>(workspace);
+    auto* bounds = reinterpret_cast<ObjBound*>(ws + w.off_bounds);
+    int* tile_kept = reinterpret_cast<int*>(ws + w.off_tile_kept);
+    int* tile_off = reinterpret_cast<int*>(ws + w.off_tile_off);
+    int* obj_off = reinterpret_cast<int*>(ws + w.off_obj_off);
+    const int n_obj = pts_per_obj > 0 ? num_obj : 0;
+    const int ntiles = div_up(pts_per_frame > 0 ? pts_per_frame : 1, kTilePts);
+    if (n_obj > 0) {
+        splice_bounds_kernel<<<div_up(n_obj, kThreads / 32), kThreads, 0, st>>>(n_obj, pts_per_obj, obj_pts, obj_count, obj_frame,
+                                                                                (float)thresh, bounds);
+        SEEVCN_LAUNCH_CHECK();
+    }
+    if (pts_per_frame > 0) {
+        // float(thresh) rounded up so the fp32 guard band always contains the float64 threshold
+        const float tf = nextafterf((float)thresh, INFINITY);
+        splice_mask_kernel<<<dim3(ntiles, num_frames), kThreads, 0, st>>>(pts_per_frame, frame_pts, n_obj, pts_per_obj, obj_pts,
+                                                                          bounds, tf, thresh, keep, merged ? tile_kept : nullptr);
+        SEEVCN_LAUNCH_CHECK();
+    }
+    if (merged) {
+        if (pts_per_frame == 0) SEEVCN_CUDA_CHECK(cudaMemsetAsync(tile_kept, 0, 4 * (size_t)ntiles * num_frames, st));
+        splice_offsets_kernel<<<num_frames, kThreads, 0, st>>>(n_obj, ntiles, bounds, tile_kept, obj_off, tile_off, merged_count,
+                                                               completed_count);
+        SEEVCN_LAUNCH_CHECK();
+        if (pts_per_frame > 0) {
+            splice_scatter_points_kernel<<<dim3(ntiles, num_frames), kThreads, 0, st>>>(pts_per_frame, frame_pts, keep, tile_off,
+                                                                                        out_stride, merged);
+            SEEVCN_LAUNCH_CHECK();
+        }
+        if (n_obj > 0) {
+            splice_scatter_objects_kernel<<<dim3(div_up(pts_per_obj * 3, kThreads), n_obj), kThreads, 0, st>>>(
+                pts_per_obj, obj_pts, bounds, obj_off, out_stride, merged);
+            SEEVCN_LAUNCH_CHECK();
+        }
+    }
+    return SEEVCN_OK;
+}

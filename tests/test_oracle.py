@@ -145,3 +145,45 @@ def test_chamfer_zero_on_identical_clouds():
     a = np.random.default_rng(0).standard_normal((2, 100, 3)).astype(np.float32)
     assert np.allclose(oracle.chamfer_l2(a, a), 0)
     assert (oracle.chamfer_l2(a, a + 0.1) > 0).all()
+
+
+def test_knn_exact_ties_go_to_the_lower_index():
+    """Lattice + flat cloud full of equidistant neighbours: the restatement equals a stable sort by distance."""
+    rng = np.random.default_rng(5)
+    g = np.stack(np.meshgrid(np.arange(8), np.arange(8), np.arange(4), indexing="ij"), -1).reshape(1, -1, 3).astype(np.float32)
+    g = g[:, rng.permutation(g.shape[1])]
+    flat = np.zeros((1, 256, 3), np.float32); flat[0, :, 1] = rng.permutation(256) * 0.25
+    dense = np.concatenate([g, flat])
+    part = np.concatenate([g[:, :128] + np.float32(0.5), flat[:, ::2] + np.float32(0.125)])
+    _, idx = oracle.knn(7, dense, part)
+    for b in range(2):
+        d = ((part[b].astype(np.float64)[:, None, :] - dense[b].astype(np.float64)[None]) ** 2).sum(-1)
+        np.testing.assert_array_equal(idx[b], np.argsort(d, axis=1, kind="stable")[:, :7])
+
+
+def test_splice_restatement_kdtree_equals_brute_force():
+    """replace_with_completed_pts (SEE_VCN.py:247-265): KD-tree and brute-force nearest distances agree; the merged
+    cloud is [completed ++ surviving originals in order]; points exactly at the threshold survive (dist < thresh)."""
+    rng = np.random.default_rng(11)
+    pts = rng.uniform(-5, 5, (4000, 3)).astype(np.float32)
+    comp = (pts[rng.choice(4000, 300, replace=False)] + rng.normal(0, 0.05, (300, 3))).astype(np.float32)
+    d_tree, d_brute = oracle.nearest_dist(pts, comp), oracle.nearest_dist(pts, comp, brute=True)
+    np.testing.assert_allclose(d_tree, d_brute, rtol=1e-14, atol=0)
+    merged, keep = oracle.replace_with_completed_pts(pts, comp, 0.1)
+    assert 0 < keep.sum() < len(pts) - 100
+    np.testing.assert_array_equal(merged[:300], comp)
+    np.testing.assert_array_equal(merged[300:], pts[keep])
+    np.testing.assert_array_equal(keep, ~(d_brute < 0.1))
+    # boundary: one completed point at the origin, originals at distance exactly 0.5 (kept) and just inside (dropped)
+    o = np.zeros((1, 3), np.float32)
+    p = np.array([[0.5, 0, 0], [np.nextafter(np.float32(0.5), np.float32(0)), 0, 0], [0, 0.3, 0.4]], np.float32)
+    _, keep = oracle.replace_with_completed_pts(p, o, 0.5, brute=True)
+    assert keep.tolist() == [True, False, False] or keep.tolist() == [True, False, True]   # 0.3^2+0.4^2 rounds in fp32 inputs
+    merged, keep = oracle.replace_with_completed_pts(p, None)
+    assert keep.all() and merged.shape == (3, 3)
+
+
+def test_all_instances_is_sorted_unique_rows():
+    c = np.array([[[1, 2, 3], [0, 0, 1], [1, 2, 3]], [[0, 0, 1], [5, 5, 5], [9, 9, 9]]], np.float32)
+    out = oracle.all_instances(c, counts=[3, 2])
+    assert out.tolist() == [[0, 0, 1], [1, 2, 3], [5, 5, 5]]
