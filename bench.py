@@ -4,7 +4,7 @@
   python bench.py [--gpus N] [--steps K] [--warmup W] [--frames F] [--impl ours|reference]
 
 A step = one pass of the hot path (crop -> resample -> VCN forward -> kNN surface select ->
-largest-cluster filter -> dynamic voxelization) over a batch of F synthetic Waymo-like frames (BASELINE.json configs[1]:
+largest-cluster filter -> splice (raw points replaced by the completed ones) -> dynamic voxelization) over a batch of F synthetic Waymo-like frames (BASELINE.json configs[1]:
 64 beams x 2812 azimuth steps = 180k pts, 50 car boxes, 1024 pts/object) per GPU.  Frames shard
 across ranks with no collective on the data path; one all-gather-v of the completed clouds per
 step stands for "collect for the detector" when N > 1 (weak scaling: F frames per GPU).
@@ -31,6 +31,7 @@ sys.path.insert(0, ROOT)
 METRIC = "completed objects/sec"
 SEL_K = 20               # SURFACE_COMPLETION.VCN.SEL_K_NEAREST (see/surface_completion/cfgs/WAY-GT_VCN-VC.yaml:13)
 CLUSTER_EPS = 0.3        # SURFACE_COMPLETION.VCN.CLUSTER_EPS   (WAY-GT_VCN-VC.yaml:14)
+SPLICE_THRESH = 0.1      # replace_with_completed_pts(point_dist_thresh=0.1)          (see/surface_completion/SEE_VCN.py:247)
 RESAMPLE = 1024
 FLOP_PER_OBJ = 2.0 * (959040 * 1024 + 5771776)   # VCN_VC, N = 1024 -> 1.976 GFLOP
 FLOP_ENC2_REF = 2.0 * (512 * 512 + 512 * 1024) * 1024    # enc2 as the reference graph states it
@@ -115,14 +116,23 @@ def cpu_path_once(pts, boxes, sd, threads):
         for k in np.nonzero(cnt >= 30)[0]:
             clouds.append(oracle.resample_points(pts[f][idx[f] == k], RESAMPLE, rng)[0]); fid.append(f)
     n_obj = len(clouds)
-    rows = [np.concatenate([np.full((pts.shape[1], 1), f, np.float32), pts[f]], axis=1) for f in range(pts.shape[0])]
+    frame_sc = [None] * pts.shape[0]
     if n_obj:
         inp = np.stack(clouds).astype(np.float32)
         with torch.no_grad():
             coarse = oracle.vcn_forward_ref(sd, inp, None, "VCN_VC")["coarse"].numpy()
         surf, _ = oracle.get_partial_mesh_batch(inp, coarse, k=SEL_K)
-        surf, _ = oracle.get_largest_cluster_batch(surf, eps=CLUSTER_EPS, min_points=2, total_pts=RESAMPLE)
-        rows += [np.concatenate([np.full((RESAMPLE, 1), fid[o], np.float32), surf[o]], axis=1) for o in range(n_obj)]
+        surf, cnt = oracle.get_largest_cluster_batch(surf, eps=CLUSTER_EPS, min_points=2, total_pts=RESAMPLE)
+        fid = np.asarray(fid)
+        for f in range(pts.shape[0]):   # SEE_VCN.py:244: all_instances = np.unique(np.vstack(clustered), axis=0)
+            sel = np.nonzero(fid == f)[0]
+            if len(sel):
+                frame_sc[f] = oracle.all_instances(surf[sel], cnt[sel])
+    rows = []
+    for f in range(pts.shape[0]):       # SEE_VCN.py:247-265 splice, then the [batch_idx, x, y, z] rows of dataset.py:187-192
+        merged, _ = oracle.replace_with_completed_pts(pts[f], frame_sc[f] if frame_sc[f] is not None and len(frame_sc[f]) else None,
+                                                      SPLICE_THRESH)
+        rows.append(np.concatenate([np.full((len(merged), 1), f, np.float32), merged], axis=1))
     vox = np.concatenate(rows).astype(np.float32)
     from seevcn_b200.pipeline import WAYMO_VOXEL_CFG
     oracle.dynamic_voxelize(vox, *WAYMO_VOXEL_CFG)
@@ -168,7 +178,7 @@ def run_reference(args):
         "warmup": args.warmup, "ms_per_step": 1e3 * tot_sec / max(args.steps, 1), "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": "C2: synthetic Waymo-like 64-beam frame (180k pts, 50 car boxes, 1024 pts/object)",
-                   "frames_per_step": sample_frames, "sel_k": SEL_K},
+                   "frames_per_step": sample_frames, "sel_k": SEL_K, "cluster_eps": CLUSTER_EPS, "splice_thresh": SPLICE_THRESH},
         "voxelized_mpts_per_sec": tot_vox / tot_sec / 1e6,
         "cpu_baseline": {"value": val, "unit": "objects/s", "cores": threads, "kind": "port", "sample": sample},
         "e2e": {"value": val, "unit": "objects/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -200,7 +210,8 @@ def run_ours(args):
         if isinstance(m, torch.nn.BatchNorm1d):
             m.running_mean.normal_(0, 0.1); m.running_var.uniform_(0.5, 1.5)
     sd = ref_model.state_dict()
-    pipe = CompletionPipeline("VCN_VC", sd, dev, sel_k=SEL_K, precision=args.precision, cluster_eps=CLUSTER_EPS)
+    pipe = CompletionPipeline("VCN_VC", sd, dev, sel_k=SEL_K, precision=args.precision, cluster_eps=CLUSTER_EPS,
+                              splice_thresh=SPLICE_THRESH)
 
     F = args.frames
     pts_h, boxes_h = make_inputs(F, 1000 + rank * F)         # rank r owns frames [r*F, (r+1)*F)
@@ -307,6 +318,7 @@ def run_ours(args):
             "dynamic_voxelize": ("hbm", 16.0 * out["num_voxel_points"] + 32.0 * n_voxels),
             "knn_surface_select": ("alu", None), "knn_prepare_kernel": ("alu", None), "knn_sweep_select_kernel": ("alu", None),
             "largest_cluster": ("alu", None), "crop": ("hbm", None),
+            "splice": ("hbm", 13.0 * F * P_pts + 12.0 * RESAMPLE * obj_rank0),
         }
         stages = []
         for name, (cnt, tot_ms) in prof.items():
@@ -335,7 +347,7 @@ def run_ours(args):
             "dtype": "bf16" if args.precision == "bf16" else "f32", "data": "synthetic",
             "config": {"workload": "C2: synthetic Waymo-like 64-beam frame (180k pts, 50 car boxes, 1024 pts/object), random-init VCN_VC",
                        "frames_per_step_per_gpu": F, "objects_per_step": int(round(n_obj_res / steps)), "sel_k": SEL_K,
-                       "cluster_eps": CLUSTER_EPS, "l2": "flushed (256 MB write) before every step, inside the timed region",
+                       "cluster_eps": CLUSTER_EPS, "splice_thresh": SPLICE_THRESH, "l2": "flushed (256 MB write) before every step, inside the timed region",
                        "parallelism": f"frame-sharded x{world}"},
             "voxelized_mpts_per_sec": n_vox_pts / (ms_res / 1e3) / 1e6, "voxels_per_step_rank0": int(n_voxels),
             "e2e": {"value": e2e, "unit": "objects/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),

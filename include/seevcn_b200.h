@@ -234,6 +234,28 @@ int seevcn_linear_bf16(int rows, int cin, int cout, const float* X, const float*
                        const float* obj_bias, int rows_per_obj, int act, float* Y, float* colmax,
                        void* workspace, size_t workspace_bytes, seevcn_stream_t stream);
 
+/* ---------------------------------------------- splice: completed clouds replace raw points */
+
+/* ref: SEE_VCN.replace_with_completed_pts  see/surface_completion/SEE_VCN.py:247-265 (demo twin
+ * demo/see_vcn_dataset.py:127-135): a raw frame point is dropped when its nearest completed point is closer than
+ * thresh (`compute_point_cloud_distance(...) < point_dist_thresh`, float64), the rest is stacked under the completed
+ * points.  PARITY UNPINNED (open3d is not vendored).
+ *   frame_pts (F,P,3) f32; obj_pts (O,S,3) f32 completed clouds, object o belongs to frame obj_frame[o] (O int32,
+ *   NON-DECREASING) and only its first obj_count[o] rows count (O int32, NULL = S; 0 = object contributes nothing).
+ *   keep (F,P) uint8: 1 = the point survives.
+ *   merged (F,out_stride,3) f32 or NULL: per frame [rows of its objects in object order ++ surviving points in point
+ *   order]; merged_count (F) int32 rows written per frame (out_stride >= P + the frame's object rows);
+ *   completed_count (F) int32 or NULL = how many of them are object rows.  The reference stacks
+ *   np.unique(all object rows) (SEE_VCN.py:244, lexicographic order, cross-object duplicates removed) — same rows up to
+ *   order whenever two objects share no point.
+ * workspace: seevcn_splice_workspace_bytes(F, P, O) bytes, 16-byte aligned. */
+size_t seevcn_splice_workspace_bytes(int num_frames, int pts_per_frame, int num_obj);
+int seevcn_splice(int num_frames, int pts_per_frame, const float* frame_pts,
+                  int num_obj, int pts_per_obj, const float* obj_pts, const int* obj_count, const int* obj_frame,
+                  double thresh, unsigned char* keep,
+                  int out_stride, float* merged, int* merged_count, int* completed_count,
+                  void* workspace, size_t workspace_bytes, seevcn_stream_t stream);
+
 /* ------------------------------------------------------------ stage 6: voxelization -- */
 
 /* ref: MeanVFE.forward  detector3d/pcdet/models/backbones_3d/vfe/mean_vfe.py:14-31
@@ -276,6 +298,20 @@ int seevcn_dynamic_voxelize_frames(int num_frames, int pts_per_frame, const floa
                                    int max_voxels, int sorted,
                                    int* voxel_coords, float* voxel_features, int* voxel_counts, int* num_voxels,
                                    void* workspace, size_t workspace_bytes, seevcn_stream_t stream);
+
+/* Same, after the splice step: frame point (f,p) is skipped when frame_keep[f*P+p] == 0 (frame_keep (F,P) uint8 from
+ * seevcn_splice, NULL = keep all) and object o contributes only its first obj_count[o] rows (obj_count (O) int32 DEVICE,
+ * NULL = all pts_per_obj rows; the distinct rows of a cyclically tiled cloud, i.e. sel_count / out_count of the stages
+ * above) — the rows of the reference's merged frame cloud `vstack(all_instances, pcd_without_object)`
+ * (SEE_VCN.py:244,247-265). */
+int seevcn_dynamic_voxelize_spliced(int num_frames, int pts_per_frame, const float* frame_pts,
+                                    const unsigned char* frame_keep,
+                                    int num_obj, int pts_per_obj, const float* obj_pts, const int* obj_frame,
+                                    const int* obj_count,
+                                    const float* pc_range, const float* voxel_size, const int* grid_size,
+                                    int max_voxels, int sorted,
+                                    int* voxel_coords, float* voxel_features, int* voxel_counts, int* num_voxels,
+                                    void* workspace, size_t workspace_bytes, seevcn_stream_t stream);
 
 /* ref: VoxelGeneratorWrapper.generate  detector3d/pcdet/datasets/processor/data_processor.py:44-60
  * (spconv hard voxelization: first-seen voxel order, first max_points points per voxel in

@@ -64,6 +64,10 @@ SIGNATURES = {
                                     I, I, I, P, P, P, P, P, c_size_t, P]),
     "seevcn_dynamic_voxelize_frames": (I, [I, I, P, I, I, P, P, POINTER(ctypes.c_float), POINTER(ctypes.c_float), POINTER(c_int),
                                            I, I, P, P, P, P, P, c_size_t, P]),
+    "seevcn_dynamic_voxelize_spliced": (I, [I, I, P, P, I, I, P, P, P, POINTER(ctypes.c_float), POINTER(ctypes.c_float),
+                                            POINTER(c_int), I, I, P, P, P, P, P, c_size_t, P]),
+    "seevcn_splice_workspace_bytes": (c_size_t, [I, I, I]),
+    "seevcn_splice": (I, [I, I, P, I, I, P, P, P, ctypes.c_double, P, I, P, P, P, P, c_size_t, P]),
     "seevcn_hard_voxelize_workspace_bytes": (c_size_t, [I, I, I]),
     "seevcn_hard_voxelize": (I, [I, I, P, POINTER(ctypes.c_float), POINTER(ctypes.c_float), POINTER(c_int),
                                  I, I, P, P, P, P, P, c_size_t, P]),

@@ -59,5 +59,28 @@ __device__ __forceinline__ float4 ld_stream_f4(const float4* p) {
     return r;
 }
 
+// Stage `nfl` floats starting at src into smem so that s[mis + j] = src[j], using aligned
+// 128-bit loads for the body.  Returns mis (0..3).
+__device__ __forceinline__ int stage_floats(float* s, const float* __restrict__ src, int nfl) {
+    const int mis = (int)((reinterpret_cast<uintptr_t>(src) >> 2) & 3);
+    const float* base = src - mis;                  // 16 B aligned
+    const int total = mis + nfl;
+    const int nvec = (total + 3) >> 2;
+    for (int v = threadIdx.x; v < nvec; v += blockDim.x) {
+        const int j0 = v * 4;
+        if (j0 >= mis && j0 + 4 <= total) {
+            float4 q = ld_stream_f4(reinterpret_cast<const float4*>(base + j0));
+            *reinterpret_cast<float4*>(s + j0) = q;
+        } else {
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const int j = j0 + e;
+                if (j >= mis && j < total) s[j] = base[j];
+            }
+        }
+    }
+    return mis;
+}
+
 __device__ __forceinline__ int lane_id() { return threadIdx.x & 31; }
 __device__ __forceinline__ int warp_id() { return threadIdx.x >> 5; }

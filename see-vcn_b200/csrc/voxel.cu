@@ -87,16 +87,24 @@ dynvox_insert_kernel(int n, int c, const float* __restrict__ points, VoxGeom g, 
 // The frame pipeline's rows without the concatenated (N,4) matrix: frame f's raw points carry batch index f,
 // object o's completed points carry obj_frame[o].
 __global__ void __launch_bounds__(256)
-dynvox_insert_frames_kernel(int n_frame_pts, int pts_per_frame, const float* __restrict__ frame_pts, int n_obj_pts,
+dynvox_insert_frames_kernel(int n_frame_pts, int pts_per_frame, const float* __restrict__ frame_pts,
+                            const unsigned char* __restrict__ frame_keep, int n_obj_pts,
                             int pts_per_obj, const float* __restrict__ obj_pts, const int* __restrict__ obj_frame,
+                            const int* __restrict__ obj_count,
                             VoxGeom g, unsigned long long hmask, unsigned long long* __restrict__ keys,
                             float* __restrict__ acc) {
     const int n = n_frame_pts + n_obj_pts;
     for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < n; p += gridDim.x * blockDim.x) {
         const float* row;
         long long b;
-        if (p < n_frame_pts) { row = frame_pts + (size_t)p * 3; b = p / pts_per_frame; }
-        else { const int q = p - n_frame_pts; row = obj_pts + (size_t)q * 3; b = obj_frame[q / pts_per_obj]; }
+        if (p < n_frame_pts) {
+            if (frame_keep && !frame_keep[p]) continue;          // replaced by a completed cloud (splice step)
+            row = frame_pts + (size_t)p * 3; b = p / pts_per_frame;
+        } else {
+            const int q = p - n_frame_pts, o = q / pts_per_obj;
+            if (obj_count && q - o * pts_per_obj >= obj_count[o]) continue;   // cyclic repeats of the object's distinct rows
+            row = obj_pts + (size_t)q * 3; b = obj_frame[o];
+        }
         float f[kMaxFeat];
 #pragma unroll
         for (int j = 0; j < kMaxFeat; ++j) f[j] = j < 3 ? row[j] : 0.f;
@@ -357,8 +365,8 @@ extern "C" size_t seevcn_dynamic_voxelize_workspace_bytes(int num_points, int nu
 namespace {
 struct DynSrc {   // either one (N,1+C) matrix, or frames + object clouds
     const float* points;
-    int n_frame_pts, pts_per_frame; const float* frame_pts;
-    int n_obj_pts, pts_per_obj; const float* obj_pts; const int* obj_frame;
+    int n_frame_pts, pts_per_frame; const float* frame_pts; const unsigned char* frame_keep;
+    int n_obj_pts, pts_per_obj; const float* obj_pts; const int* obj_frame; const int* obj_count;
 };
 
 int dynvox_run(const char* what, int num_points, int num_features, const DynSrc& src, const float* pc_range,
@@ -393,8 +401,9 @@ int dynvox_run(const char* what, int num_points, int num_features, const DynSrc&
         SEEVCN_CUDA_CHECK(cudaMemsetAsync(o_keys, 0xff, (size_t)max_voxels * 8, st));
     }
     if (!src.points) {
-        dynvox_insert_frames_kernel<<<grid_ins, 256, 0, st>>>(src.n_frame_pts, src.pts_per_frame, src.frame_pts, src.n_obj_pts,
-                                                             src.pts_per_obj, src.obj_pts, src.obj_frame, g, w.nslots - 1, keys, acc);
+        dynvox_insert_frames_kernel<<<grid_ins, 256, 0, st>>>(src.n_frame_pts, src.pts_per_frame, src.frame_pts, src.frame_keep,
+                                                             src.n_obj_pts, src.pts_per_obj, src.obj_pts, src.obj_frame, src.obj_count,
+                                                             g, w.nslots - 1, keys, acc);
         SEEVCN_LAUNCH_CHECK();
         dynvox_finalize_kernel<4><<<grid_fin, 256, 0, st>>>(w.nslots, num_features, g, keys, acc, max_voxels, o_coords,
                                                            o_feat, o_cnt, o_keys, num_voxels);
@@ -452,8 +461,9 @@ extern "C" int seevcn_dynamic_voxelize(int num_points, int num_features, const f
                       batch_hint, voxel_coords, voxel_features, voxel_counts, num_voxels, workspace, workspace_bytes, st);
 }
 
-extern "C" int seevcn_dynamic_voxelize_frames(int num_frames, int pts_per_frame, const float* frame_pts, int num_obj,
-                                              int pts_per_obj, const float* obj_pts, const int* obj_frame,
+extern "C" int seevcn_dynamic_voxelize_spliced(int num_frames, int pts_per_frame, const float* frame_pts,
+                                               const unsigned char* frame_keep, int num_obj,
+                                               int pts_per_obj, const float* obj_pts, const int* obj_frame, const int* obj_count,
                                               const float* pc_range, const float* voxel_size, const int* grid_size,
                                               int max_voxels, int sorted, int* voxel_coords, float* voxel_features,
                                               int* voxel_counts, int* num_voxels, void* workspace, size_t workspace_bytes,
@@ -469,11 +479,22 @@ extern "C" int seevcn_dynamic_voxelize_frames(int num_frames, int pts_per_frame,
     SEEVCN_REQUIRE((n_frame == 0 || frame_pts) && (n_obj == 0 || (obj_pts && obj_frame)) && voxel_coords && voxel_features &&
                    voxel_counts && workspace, "dynamic_voxelize_frames: null pointer");
     DynSrc src{};
-    src.n_frame_pts = (int)n_frame; src.pts_per_frame = pts_per_frame > 0 ? pts_per_frame : 1; src.frame_pts = frame_pts;
-    src.n_obj_pts = (int)n_obj; src.pts_per_obj = pts_per_obj > 0 ? pts_per_obj : 1; src.obj_pts = obj_pts; src.obj_frame = obj_frame;
+    src.n_frame_pts = (int)n_frame; src.pts_per_frame = pts_per_frame > 0 ? pts_per_frame : 1; src.frame_pts = frame_pts; src.frame_keep = frame_keep;
+    src.n_obj_pts = (int)n_obj; src.pts_per_obj = pts_per_obj > 0 ? pts_per_obj : 1; src.obj_pts = obj_pts; src.obj_frame = obj_frame; src.obj_count = obj_count;
     return dynvox_run("dynamic_voxelize_frames", (int)(n_frame + n_obj), 3, src, pc_range, voxel_size, grid_size, max_voxels,
                       sorted, num_frames > 0 ? num_frames : 1, voxel_coords, voxel_features, voxel_counts, num_voxels, workspace,
                       workspace_bytes, st);
+}
+
+extern "C" int seevcn_dynamic_voxelize_frames(int num_frames, int pts_per_frame, const float* frame_pts, int num_obj,
+                                              int pts_per_obj, const float* obj_pts, const int* obj_frame,
+                                              const float* pc_range, const float* voxel_size, const int* grid_size,
+                                              int max_voxels, int sorted, int* voxel_coords, float* voxel_features,
+                                              int* voxel_counts, int* num_voxels, void* workspace, size_t workspace_bytes,
+                                              seevcn_stream_t stream) {
+    return seevcn_dynamic_voxelize_spliced(num_frames, pts_per_frame, frame_pts, nullptr, num_obj, pts_per_obj, obj_pts, obj_frame,
+                                           nullptr, pc_range, voxel_size, grid_size, max_voxels, sorted, voxel_coords,
+                                           voxel_features, voxel_counts, num_voxels, workspace, workspace_bytes, stream);
 }
 
 extern "C" size_t seevcn_hard_voxelize_workspace_bytes(int num_points, int max_points, int max_voxels) {

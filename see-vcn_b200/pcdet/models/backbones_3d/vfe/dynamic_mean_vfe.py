@@ -38,11 +38,14 @@ def dynamic_voxelize(points, point_cloud_range, voxel_size, grid_size, max_voxel
     return coords[:m], feats[:m], counts[:m]
 
 
-def dynamic_voxelize_frames(frame_pts, obj_pts, obj_frame, point_cloud_range, voxel_size, grid_size, sort=True):
+def dynamic_voxelize_frames(frame_pts, obj_pts, obj_frame, point_cloud_range, voxel_size, grid_size, sort=True,
+                            frame_keep=None, obj_count=None):
     """The frame pipeline's form: frame_pts (F,P,3) rows carry batch index = frame, obj_pts (O,S,3) rows carry
     obj_frame[o]; same result as ``dynamic_voxelize`` on the concatenated [batch_idx,x,y,z] matrix, which is never
-    built.  No host sync: returns FULL-capacity tensors plus the device scalar M —
-    (coords (N,4), feats (N,3), counts (N,), num_voxels (1,) int32 CUDA); rows >= M are undefined."""
+    built.  After the splice step (SEE_VCN.py:247-265): ``frame_keep`` (F,P) uint8 drops the replaced frame points and
+    ``obj_count`` (O,) int32 limits every object to its distinct rows.  No host sync: returns FULL-capacity tensors
+    plus the device scalar M — (coords (N,4), feats (N,3), counts (N,), num_voxels (1,) int32 CUDA); rows >= M are
+    undefined."""
     frame_pts = frame_pts.contiguous()
     _abi.require_cuda(frame_pts)
     F, P, _ = frame_pts.shape
@@ -52,9 +55,17 @@ def dynamic_voxelize_frames(frame_pts, obj_pts, obj_frame, point_cloud_range, vo
         _abi.require_cuda(obj_pts, obj_frame)
         assert obj_frame.dtype == torch.int32 and obj_frame.shape[0] == obj_pts.shape[0]
         O, S, _ = obj_pts.shape
+        if obj_count is not None:
+            obj_count = obj_count.contiguous()
+            _abi.require_cuda(obj_count)
+            assert obj_count.dtype == torch.int32 and obj_count.shape[0] == O
     else:
-        obj_pts = obj_frame = None
+        obj_pts = obj_frame = obj_count = None
         O = S = 0
+    if frame_keep is not None:
+        frame_keep = frame_keep.contiguous()
+        _abi.require_cuda(frame_keep)
+        assert frame_keep.dtype == torch.uint8 and frame_keep.numel() == F * P
     N = F * P + O * S
     L = _abi.lib()
     cap = max(N, 1)
@@ -64,11 +75,12 @@ def dynamic_voxelize_frames(frame_pts, obj_pts, obj_frame, point_cloud_range, vo
     counts = torch.empty((cap,), dtype=torch.int32, device=dev)
     num = torch.empty((1,), dtype=torch.int32, device=dev)
     with torch.cuda.device(dev):
-        _abi.check(L.seevcn_dynamic_voxelize_frames(F, P, _abi.ptr(frame_pts), O, S, _abi.ptr(obj_pts), _abi.ptr(obj_frame),
-                                                    _abi.farray(point_cloud_range), _abi.farray(voxel_size),
-                                                    _abi.iarray(grid_size), cap, 1 if sort else 0, _abi.ptr(coords),
-                                                    _abi.ptr(feats), _abi.ptr(counts), _abi.ptr(num), _abi.ptr(ws),
-                                                    ws.numel(), _abi.stream()))
+        _abi.check(L.seevcn_dynamic_voxelize_spliced(F, P, _abi.ptr(frame_pts), _abi.ptr(frame_keep), O, S, _abi.ptr(obj_pts),
+                                                     _abi.ptr(obj_frame), _abi.ptr(obj_count),
+                                                     _abi.farray(point_cloud_range), _abi.farray(voxel_size),
+                                                     _abi.iarray(grid_size), cap, 1 if sort else 0, _abi.ptr(coords),
+                                                     _abi.ptr(feats), _abi.ptr(counts), _abi.ptr(num), _abi.ptr(ws),
+                                                     ws.numel(), _abi.stream()))
     return coords, feats, counts, num
 
 

@@ -13,6 +13,7 @@ from .pcdet.ops.roiaware_pool3d import roiaware_pool3d_utils as roi
 from .pcdet.models.backbones_3d.vfe.dynamic_mean_vfe import dynamic_voxelize, dynamic_voxelize_frames  # noqa: F401
 from .see.surface_completion.models.vcn.models.build import MODELS
 from .see.surface_completion.models.vcn.utils.sampling import get_partial_mesh_batch, get_largest_cluster_batch
+from .see.surface_completion.SEE_VCN import splice_frames
 
 WAYMO_VOXEL_CFG = ([-75.2, -75.2, -2.0, 75.2, 75.2, 4.0], [0.1, 0.1, 0.15], [1504, 1504, 40])   # sc_waymo_dataset.yaml:4,39-45
 
@@ -30,7 +31,7 @@ class _Crop:
 
 class CompletionPipeline:
     def __init__(self, model_name="VCN_VC", state_dict=None, device=None, sel_k=10, min_lidar_pts=30, resample_num=1024,
-                 voxel_cfg=WAYMO_VOXEL_CFG, precision="bf16", host_rng=False, cluster_eps=None):
+                 voxel_cfg=WAYMO_VOXEL_CFG, precision="bf16", host_rng=False, cluster_eps=None, splice_thresh=None):
         self.device = device if device is not None else torch.device("cuda", torch.cuda.current_device())
         self.model = MODELS.build({"NAME": model_name}, precision=precision)
         self.state_dict = state_dict
@@ -44,6 +45,7 @@ class CompletionPipeline:
         self.voxel_cfg = voxel_cfg
         self.host_rng = host_rng              # True: numpy permutation per object on the host (reference's draw)
         self.cluster_eps = cluster_eps        # SURFACE_COMPLETION.VCN.CLUSTER_EPS; None skips the largest-cluster filter
+        self.splice_thresh = splice_thresh    # replace_with_completed_pts point_dist_thresh (SEE_VCN.py:247); None = no splice
         self._side = None                     # stream of the small D2H copies (box counts, number of voxels)
 
     def _side_stream(self):
@@ -115,8 +117,8 @@ class CompletionPipeline:
                                                     return_count=True)
         out.update(input=inp, coarse=coarse, surface=surface, surface_count=sel_count, obj_frame_dev=obj_frame)
         if self.cluster_eps is not None:   # models/VCN.py:95-98
-            out["clustered"] = get_largest_cluster_batch(surface, eps=self.cluster_eps, min_points=2,
-                                                         total_pts=coarse.shape[1], period=sel_count)
+            out["clustered"], out["clustered_count"] = get_largest_cluster_batch(
+                surface, eps=self.cluster_eps, min_points=2, total_pts=coarse.shape[1], period=sel_count, return_count=True)
         return out
 
     # ---- stage B: complete + voxelize.  The number of voxels M is data dependent; it travels to the host on the side
@@ -127,8 +129,15 @@ class CompletionPipeline:
         points = h.points
         F, P, _ = points.shape
         completed = out.get("clustered", out["surface"])
+        keep = count = None
+        if self.splice_thresh is not None and completed.shape[0] > 0:
+            # SEE_VCN.py:244,247-265: the frame the detector sees = distinct completed points ++ raw points farther
+            # than thresh from all of them.  The mask feeds the voxelizer directly; the merged cloud is not built.
+            count = out.get("clustered_count", out.get("surface_count"))
+            keep = splice_frames(points, completed, out["obj_frame_dev"], count, self.splice_thresh)
+            out["frame_keep"], out["completed_count"] = keep, count
         coords, feats, nums, num_dev = dynamic_voxelize_frames(points, completed, out.get("obj_frame_dev"), *self.voxel_cfg,
-                                                              sort=True)
+                                                              sort=True, frame_keep=keep, obj_count=count)
         out["num_voxel_points"] = F * P + completed.shape[0] * completed.shape[1]
         out["_frame_points"] = points
         out["_vox_full"] = (coords, feats, nums, num_dev)
@@ -177,11 +186,18 @@ class CompletionPipeline:
         F, P, _ = points.shape
         fid = torch.arange(F, device=points.device, dtype=torch.float32).view(F, 1, 1).expand(F, P, 1)
         rows = [torch.cat((fid, points), dim=2).view(F * P, 4)]
+        if "frame_keep" in out:
+            rows[0] = rows[0][out["frame_keep"].view(-1) != 0]
         completed = out.get("clustered", out["surface"])
         if completed.shape[0] > 0:
             O, S, _ = completed.shape
             ofid = out["obj_frame_dev"].to(torch.float32).view(O, 1, 1).expand(O, S, 1)
-            rows.append(torch.cat((ofid, completed), dim=2).view(O * S, 4))
+            orows = torch.cat((ofid, completed), dim=2)
+            if "completed_count" in out:
+                sel = torch.arange(S, device=points.device).view(1, S) < out["completed_count"].view(O, 1)
+                rows.append(orows[sel])
+            else:
+                rows.append(orows.view(O * S, 4))
         return torch.cat(rows, dim=0).contiguous()
 
 

@@ -1,0 +1,71 @@
+"""The splice step of the SEE-VCN frame driver on the B200 path.
+
+ref: see/surface_completion/SEE_VCN.py:247-265 (``SEE_VCN.replace_with_completed_pts``; demo twin
+demo/see_vcn_dataset.py:127-135).  The reference measures, on the host, every raw frame point against an open3d
+KD-tree of the completed points and drops those closer than ``point_dist_thresh``; here the completed clouds stay on
+the device as per-object blocks and one kernel pair (csrc/splice.cu) produces the keep mask, optionally the merged
+cloud.
+"""
+import numpy as np
+import torch
+
+from ... import _abi
+
+
+def splice_frames(frame_pts, obj_pts, obj_frame, obj_count=None, point_dist_thresh=0.1, merged=False):
+    """frame_pts (F,P,3) f32 CUDA; obj_pts (O,S,3) f32 CUDA completed clouds, obj_frame (O,) int32 non-decreasing,
+    obj_count (O,) int32 or None = the distinct rows of every (cyclically tiled) object cloud.
+
+    -> keep (F,P) uint8 CUDA (1 = the raw point survives); with ``merged=True`` also
+       (merged (F,P+max rows,3) f32, merged_count (F,) int32, completed_count (F,) int32): per frame
+       [completed rows ++ surviving raw points], the reference's return value, rows >= merged_count[f] undefined."""
+    frame_pts = frame_pts.contiguous()
+    _abi.require_cuda(frame_pts)
+    assert frame_pts.dtype == torch.float32 and frame_pts.dim() == 3 and frame_pts.shape[2] == 3
+    F, P, _ = frame_pts.shape
+    dev = frame_pts.device
+    if obj_pts is not None and obj_pts.shape[0] > 0:
+        obj_pts = obj_pts.contiguous(); obj_frame = obj_frame.contiguous()
+        _abi.require_cuda(obj_pts, obj_frame)
+        assert obj_pts.dtype == torch.float32 and obj_frame.dtype == torch.int32 and obj_frame.shape[0] == obj_pts.shape[0]
+        O, S, _ = obj_pts.shape
+        if obj_count is not None:
+            obj_count = obj_count.contiguous()
+            _abi.require_cuda(obj_count)
+            assert obj_count.dtype == torch.int32 and obj_count.shape[0] == O
+    else:
+        obj_pts = obj_frame = obj_count = None
+        O = S = 0
+    L = _abi.lib()
+    keep = torch.empty((F, P), dtype=torch.uint8, device=dev)
+    ws = torch.empty(max(L.seevcn_splice_workspace_bytes(F, P, O), 16), dtype=torch.uint8, device=dev)
+    out = m_cnt = c_cnt = None
+    stride = 0
+    if merged:
+        # capacity: every raw point + the rows of the frame with the most objects (host-known upper bound O*S)
+        stride = P + O * S
+        out = torch.empty((F, stride, 3), dtype=torch.float32, device=dev)
+        m_cnt = torch.empty((F,), dtype=torch.int32, device=dev)
+        c_cnt = torch.empty((F,), dtype=torch.int32, device=dev)
+    with torch.cuda.device(dev):
+        _abi.check(L.seevcn_splice(F, P, _abi.ptr(frame_pts), O, S, _abi.ptr(obj_pts), _abi.ptr(obj_count), _abi.ptr(obj_frame),
+                                   float(point_dist_thresh), _abi.ptr(keep), stride, _abi.ptr(out), _abi.ptr(m_cnt),
+                                   _abi.ptr(c_cnt), _abi.ptr(ws), ws.numel(), _abi.stream()))
+    return (keep, out, m_cnt, c_cnt) if merged else keep
+
+
+def replace_with_completed_pts(original_points, sc_instances, point_dist_thresh=0.1, device=None):
+    """Reference-shaped entry (SEE_VCN.py:247-265): host arrays in, host array out.
+
+    original_points (P,3) numpy (the reference takes an open3d PointCloud), sc_instances (N,3) numpy or None
+    -> np.vstack((sc_instances, original points farther than point_dist_thresh from every completed point))."""
+    pts = np.ascontiguousarray(np.asarray(original_points)[:, :3], dtype=np.float32)
+    if sc_instances is None:
+        return pts
+    sc = np.ascontiguousarray(sc_instances, dtype=np.float32)
+    dev = device if device is not None else torch.device("cuda", torch.cuda.current_device())
+    d_pts = torch.from_numpy(pts).to(dev).view(1, -1, 3)
+    d_sc = torch.from_numpy(sc).to(dev).view(1, -1, 3)
+    frame = torch.zeros((1,), dtype=torch.int32, device=dev)
+    _, merged, m_cnt, _ = splice_frames(d_pts, d_sc, frame, None, point_dist_thresh, merged=True)
+    return merged[0, : int(m_cnt[0])].cpu().numpy()

@@ -1,0 +1,175 @@
+"""GPU parity of the splice step (csrc/splice.cu) against the oracle restatement of
+SEE_VCN.replace_with_completed_pts (see/surface_completion/SEE_VCN.py:247-265).  PARITY UNPINNED upstream (open3d is
+not vendored); bit-exact against the float64 restatement."""
+import numpy as np
+import pytest
+import torch
+
+import oracle
+from seevcn_b200 import synth
+from seevcn_b200.see.surface_completion.SEE_VCN import splice_frames, replace_with_completed_pts
+
+pytestmark = pytest.mark.gpu
+
+
+def dev(a, cuda):
+    return torch.from_numpy(np.ascontiguousarray(a)).to(cuda)
+
+
+def _scene(seed, F, n_az, n_boxes, S, jitter=0.05):
+    """Frames with cars; per car a 'completed' cloud = S points scattered around the car's own LiDAR returns."""
+    rng = np.random.default_rng(seed)
+    pts, boxes = synth.make_stream(F, n_beams=32, n_az=n_az, n_boxes=n_boxes, first_seed=seed)
+    idx = oracle.points_in_boxes_gpu(pts, boxes)
+    objs, frame, count = [], [], []
+    for f in range(F):
+        for k in range(boxes.shape[1]):
+            own = pts[f][idx[f] == k]
+            if len(own) < 5:
+                continue
+            base = own[rng.integers(0, len(own), S)]
+            objs.append((base + rng.normal(0, jitter, (S, 3))).astype(np.float32))
+            frame.append(f)
+            count.append(int(rng.integers(1, S + 1)))
+    return pts, np.stack(objs), np.asarray(frame, np.int32), np.asarray(count, np.int32)
+
+
+def _want(pts, objs, frame, count, thresh):
+    keep = np.ones(pts.shape[:2], bool)
+    merged = []
+    for f in range(pts.shape[0]):
+        rows = [objs[o][: (objs.shape[1] if count is None else count[o])] for o in np.nonzero(frame == f)[0]]
+        sc = np.concatenate(rows) if rows else np.zeros((0, 3), np.float32)
+        m, keep[f] = oracle.replace_with_completed_pts(pts[f], sc, thresh)
+        merged.append(m)
+    return keep, merged
+
+
+@pytest.mark.parametrize("thresh", [0.1, 0.2])
+@pytest.mark.parametrize("use_count", [True, False])
+def test_splice_mask_and_merged_cloud_vs_oracle(cuda, thresh, use_count):
+    pts, objs, frame, count = _scene(71, 3, 700, 14, 256)
+    if not use_count:
+        count = None
+    want_keep, want_merged = _want(pts, objs, frame, count, thresh)
+    assert 0.01 < 1.0 - want_keep.mean() < 0.5          # the cars' returns go, the ground stays
+    keep, merged, m_cnt, c_cnt = splice_frames(dev(pts, cuda), dev(objs, cuda), dev(frame, cuda),
+                                               None if count is None else dev(count, cuda), thresh, merged=True)
+    np.testing.assert_array_equal(keep.cpu().numpy().astype(bool), want_keep)
+    for f in range(pts.shape[0]):
+        n = int(m_cnt[f])
+        assert n == len(want_merged[f])
+        np.testing.assert_array_equal(merged[f, :n].cpu().numpy(), want_merged[f])
+        assert int(c_cnt[f]) == n - int(want_keep[f].sum())
+    only_mask = splice_frames(dev(pts, cuda), dev(objs, cuda), dev(frame, cuda), None if count is None else dev(count, cuda), thresh)
+    np.testing.assert_array_equal(only_mask.cpu().numpy(), keep.cpu().numpy())
+
+
+def test_splice_threshold_is_strict_and_evaluated_in_float64(cuda):
+    """dist < thresh (SEE_VCN.py:259): a point at exactly thresh survives; pairs inside the fp32 guard band follow the
+    float64 evaluation of the reference."""
+    t = 0.1
+    rng = np.random.default_rng(3)
+    comp = rng.uniform(-1, 1, (1, 64, 3)).astype(np.float32) * 50
+    dirs = rng.standard_normal((4096, 3)); dirs /= np.linalg.norm(dirs, axis=1, keepdims=True)
+    scale = t * (1.0 + rng.uniform(-3e-7, 3e-7, (4096, 1)))      # distances within a few fp32 ulps of thresh
+    pts = (comp[0][rng.integers(0, 64, 4096)].astype(np.float64) + dirs * scale).astype(np.float32)[None]
+    d = oracle.nearest_dist(pts[0], comp[0], brute=True)
+    assert 0.2 < (d < t).mean() < 0.8                                   # the band straddles the threshold
+    got = splice_frames(dev(pts, cuda), dev(comp, cuda), torch.zeros(1, dtype=torch.int32, device=cuda), None, t)
+    np.testing.assert_array_equal(got[0].cpu().numpy().astype(bool), ~(d < t))
+    # exactly representable distances 0.5 and 0.25 from a completed point, thresh 0.5: strict <
+    one = np.array([[[1000.0, 0.0, 0.0]]], np.float32)
+    exact = np.array([[[1000.5, 0.0, 0.0], [1000.25, 0.0, 0.0], [1000.0, 0.5, 0.0], [1000.0, 0.3, 0.4]]], np.float32)
+    got = splice_frames(dev(exact, cuda), dev(one, cuda), torch.zeros(1, dtype=torch.int32, device=cuda), None, 0.5)
+    want = ~(oracle.nearest_dist(exact[0], one[0], brute=True) < 0.5)
+    assert want[:3].tolist() == [True, False, True]
+    np.testing.assert_array_equal(got[0].cpu().numpy().astype(bool), want)
+
+
+def test_splice_edge_cases(cuda):
+    rng = np.random.default_rng(5)
+    pts = rng.uniform(-20, 20, (2, 1500, 3)).astype(np.float32)
+    # no objects at all: everything survives, merged = the frame
+    keep, merged, m_cnt, c_cnt = splice_frames(dev(pts, cuda), None, None, None, 0.1, merged=True)
+    assert keep.all() and m_cnt.tolist() == [1500, 1500] and c_cnt.tolist() == [0, 0]
+    np.testing.assert_array_equal(merged[:, :1500].cpu().numpy(), pts)
+    # objects only in frame 1, one of them with count 0 (all noise): contributes nothing and removes nothing
+    objs = np.stack([pts[1, :64] + np.float32(0.01), pts[1, 64:128] + np.float32(0.01), pts[0, :64]]).astype(np.float32)
+    frame = np.array([1, 1, 1], np.int32); count = np.array([64, 0, 64], np.int32)
+    want_keep, want_merged = _want(pts, objs, frame, count, 0.1)
+    assert want_keep[0].all() and want_keep[1, 64:128].all() and not want_keep[1, :64].any()
+    keep, merged, m_cnt, _ = splice_frames(dev(pts, cuda), dev(objs, cuda), dev(frame, cuda), dev(count, cuda), 0.1, merged=True)
+    np.testing.assert_array_equal(keep.cpu().numpy().astype(bool), want_keep)
+    for f in range(2):
+        np.testing.assert_array_equal(merged[f, : int(m_cnt[f])].cpu().numpy(), want_merged[f])
+    # more objects in one frame than one shared-memory chunk of bounds (256), ragged tile (P % 1024 != 0), one frame
+    P = 3333
+    pts = rng.uniform(-30, 30, (1, P, 3)).astype(np.float32)
+    objs = (pts[0, rng.integers(0, P, (300, 8))] + rng.normal(0, 0.04, (300, 8, 3))).astype(np.float32)
+    frame = np.zeros(300, np.int32)
+    want_keep, want_merged = _want(pts, objs, frame, None, 0.1)
+    keep, merged, m_cnt, _ = splice_frames(dev(pts, cuda), dev(objs, cuda), dev(frame, cuda), None, 0.1, merged=True)
+    np.testing.assert_array_equal(keep.cpu().numpy().astype(bool), want_keep)
+    np.testing.assert_array_equal(merged[0, : int(m_cnt[0])].cpu().numpy(), want_merged[0])
+    assert 100 < (~want_keep).sum() < P
+
+
+def test_replace_with_completed_pts_reference_entry(cuda):
+    rng = np.random.default_rng(8)
+    pts = rng.uniform(-10, 10, (5000, 3)).astype(np.float32)
+    sc = (pts[:400] + rng.normal(0, 0.03, (400, 3))).astype(np.float32)
+    got = replace_with_completed_pts(pts, sc, 0.1, device=cuda)
+    want, keep = oracle.replace_with_completed_pts(pts, sc, 0.1)
+    np.testing.assert_array_equal(got, want)
+    np.testing.assert_array_equal(replace_with_completed_pts(pts, None), pts)
+
+
+def test_splice_full_size_properties(cuda):
+    """C2 size (8 frames x 180k points, ~50 objects x 1024 rows per frame): idempotence-style properties that need no
+    CPU pass — a larger threshold never keeps more; thresh 0 keeps everything; every completed row's own location is
+    removed; merged_count = completed rows + kept points."""
+    pts, boxes = synth.make_stream(2, first_seed=1000)
+    idx = oracle.points_in_boxes_gpu(pts, boxes)
+    rng = np.random.default_rng(0)
+    objs, frame = [], []
+    for f in range(2):
+        for k in range(boxes.shape[1]):
+            own = pts[f][idx[f] == k]
+            if len(own) >= 30:
+                objs.append(own[rng.integers(0, len(own), 1024)] + rng.normal(0, 0.03, (1024, 3)).astype(np.float32))
+                frame.append(f)
+    objs = np.stack(objs).astype(np.float32); frame = np.asarray(frame, np.int32)
+    d_pts, d_objs, d_frame = dev(pts, cuda), dev(objs, cuda), dev(frame, cuda)
+    k0 = splice_frames(d_pts, d_objs, d_frame, None, 0.0)
+    k1, merged, m_cnt, c_cnt = splice_frames(d_pts, d_objs, d_frame, None, 0.1, merged=True)
+    k2 = splice_frames(d_pts, d_objs, d_frame, None, 0.2)
+    assert bool(k0.all()) and bool((k2 <= k1).all()) and int(k2.sum()) < int(k1.sum()) < k0.numel()
+    assert (m_cnt - c_cnt).tolist() == k1.sum(dim=1).tolist()
+    assert c_cnt.tolist() == [int((frame == f).sum()) * 1024 for f in range(2)]
+    # the surviving rows of the merged cloud are exactly the kept points, in order; one frame checked against the oracle
+    f = 1
+    want, keep = oracle.replace_with_completed_pts(pts[f], objs[frame == f].reshape(-1, 3), 0.1)
+    np.testing.assert_array_equal(k1[f].cpu().numpy().astype(bool), keep)
+    np.testing.assert_array_equal(merged[f, : int(m_cnt[f])].cpu().numpy(), want)
+
+
+def test_pipeline_with_splice_voxelizes_the_merged_frame(cuda):
+    """CompletionPipeline(splice_thresh=0.1): voxels = DynamicMeanVFE of [distinct completed rows ++ surviving raw
+    points] (SEE_VCN.py:244-265 then dynamic_mean_vfe.py:37-76), checked against the oracle on the materialised rows."""
+    from seevcn_b200.pipeline import CompletionPipeline
+    pipe = CompletionPipeline("VCN_VC", oracle.make_state_dict("VCN_VC", seed=0), cuda, sel_k=10, cluster_eps=0.3,
+                              splice_thresh=0.1)
+    pts, boxes = synth.make_stream(2, n_beams=32, n_az=1090, n_boxes=10, first_seed=300)
+    out = pipe.run(dev(pts, cuda), dev(boxes, cuda), seed=0)
+    keep = out["frame_keep"].cpu().numpy().astype(bool)
+    comp, cnt, ofr = out["clustered"].cpu().numpy(), out["completed_count"].cpu().numpy(), out["obj_frame"]
+    want_keep, _ = _want(pts, comp, ofr, cnt, 0.1)
+    np.testing.assert_array_equal(keep, want_keep)
+    assert 0 < (~keep).sum() < keep.size
+    rows = pipe.voxel_points(out).cpu().numpy()
+    assert len(rows) == keep.sum() + cnt.sum()
+    vc, vf, vn = oracle.dynamic_voxelize(rows, *pipe.voxel_cfg)
+    np.testing.assert_array_equal(out["voxel_coords"].cpu().numpy(), vc)
+    np.testing.assert_array_equal(out["voxel_num_points"].cpu().numpy(), vn)
+    np.testing.assert_allclose(out["voxel_features"].cpu().numpy(), vf, rtol=1e-5, atol=1e-5)

@@ -27,7 +27,7 @@ def main():
         if isinstance(m, torch.nn.BatchNorm1d):
             m.running_mean.normal_(0, 0.1); m.running_var.uniform_(0.5, 1.5)
     pipe = CompletionPipeline("VCN_VC", ref_model.state_dict(), dev, sel_k=bench.SEL_K, precision=args.precision,
-                              cluster_eps=bench.CLUSTER_EPS)
+                              cluster_eps=bench.CLUSTER_EPS, splice_thresh=bench.SPLICE_THRESH)
     pts, boxes = bench.make_inputs(args.frames, 1000)
     pts_d, boxes_d = torch.from_numpy(pts).to(dev), torch.from_numpy(boxes).to(dev)
     for _ in range(args.steps):
