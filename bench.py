@@ -316,7 +316,7 @@ def run_ours(args):
             "vcn_chain_enc2": ("tensor", FLOP_ENC2_EXEC * obj_rank0),
             "vcn_forward": ("tensor", FLOP_PER_OBJ * obj_rank0),
             "dynamic_voxelize": ("hbm", 16.0 * out["num_voxel_points"] + 32.0 * n_voxels),
-            "knn_surface_select": ("alu", None), "knn_prepare_kernel": ("alu", None), "knn_sweep_select_kernel": ("alu", None),
+            "knn_surface_select": ("alu", None), "knn_prepare_kernel": ("alu", None), "knn_scan_kernel": ("alu", None), "knn_emit_kernel": ("hbm", None),
             "largest_cluster": ("alu", None), "crop": ("hbm", None),
             "splice": ("hbm", 13.0 * F * P_pts + 12.0 * RESAMPLE * obj_rank0),
         }

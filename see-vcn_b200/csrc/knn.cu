@@ -29,29 +29,40 @@ __device__ __forceinline__ float sqdist(float qx, float qy, float qz, float4 r) 
     return __fmaf_rn(dz, dz, __fmaf_rn(dy, dy, __fmul_rn(dx, dx)));
 }
 
-// Per-thread top-k state.  list / buf are this thread's columns of [slot][T] arrays in shared memory.
+// Per-thread top-k state.  list / buf are this thread's columns of [slot][T] arrays in shared memory.  list is a binary
+// MAX-heap of k keys (root = the k-th best so far, kInfKey while fewer than k were seen): an accepted candidate replaces
+// the root and sifts down, <= log2(k) levels of two loads and one store.
 template <int T>
 struct TopK {
     u64* list; u64* buf;
-    u64 thr; float thr_f; int maxpos, nbuf, k;
+    u64 thr; float thr_f; int nbuf, k;
     __device__ __forceinline__ void init(u64* list_, u64* buf_, int k_) {
         list = list_; buf = buf_; k = k_;
         for (int j = 0; j < k; ++j) list[j * T] = kInfKey;
-        thr = kInfKey; thr_f = __int_as_float(0x7f800000); maxpos = 0; nbuf = 0;
+        thr = kInfKey; thr_f = __int_as_float(0x7f800000); nbuf = 0;
     }
     __device__ __forceinline__ void offer(float d, int idx) {
         if (d <= thr_f) { buf[nbuf * T] = ((u64)__float_as_uint(d) << 32) | (unsigned)idx; ++nbuf; }
     }
+    __device__ __forceinline__ void insert(u64 key) {   // key < thr
+        int i = 0;
+        while (true) {
+            int c = 2 * i + 1;
+            if (c >= k) break;
+            u64 a = list[c * T];
+            if (c + 1 < k) { const u64 b = list[(c + 1) * T]; if (b > a) { a = b; ++c; } }
+            if (a <= key) break;
+            list[i * T] = a;
+            i = c;
+        }
+        list[i * T] = key;
+        thr = list[0];
+        thr_f = thr == kInfKey ? __int_as_float(0x7f800000) : __uint_as_float((unsigned)(thr >> 32));
+    }
     __device__ __forceinline__ void flush() {
         for (int e = 0; e < nbuf; ++e) {
             const u64 key = buf[e * T];
-            if (key < thr) {
-                list[maxpos * T] = key;
-                u64 m = 0; int mp = 0;
-                for (int j = 0; j < k; ++j) { const u64 v = list[j * T]; if (v > m) { m = v; mp = j; } }
-                thr = m; maxpos = mp;
-                thr_f = thr == kInfKey ? __int_as_float(0x7f800000) : __uint_as_float((unsigned)(thr >> 32));
-            }
+            if (key < thr) insert(key);
         }
         nbuf = 0;
     }
@@ -132,14 +143,6 @@ __device__ __forceinline__ unsigned hash3(float x, float y, float z) {
     return h ^ (h >> 15);
 }
 
-// float -> unsigned with the same order (-0 < +0)
-__device__ __forceinline__ unsigned f2ord(float f) {
-    const unsigned u = __float_as_uint(f);
-    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
-}
-
-__device__ __forceinline__ float axis_of(float4 v, int a) { return a == 0 ? v.x : a == 1 ? v.y : v.z; }
-
 // ascending bitonic sort of s[0..len), len a power of two, by the whole CTA (ends with a barrier)
 template <int T>
 __device__ void bitonic_sort(u64* s, int len) {
@@ -155,48 +158,79 @@ __device__ void bitonic_sort(u64* s, int len) {
         }
 }
 
-// Surface selection = union over the object's queries of their k nearest completed points.  Two kernels.
+// Surface selection = union over the object's queries of their k nearest completed points.  Three kernels.
 //
-// (1) knn_prepare_kernel, one CTA per object: picks the axis along which the completed cloud is longest,
-// sorts the completed points along it (bitonic sort of (coordinate, index) keys in shared memory) and writes
-// them as float4 (x, y, z, original index) to the workspace; de-duplicates the object's queries with a
-// shared-memory hash set keyed by the exact coordinates (duplicate queries cannot change a union — the
-// reference's np.unique(partial) at sampling.py:31 is the same optimisation; resampled clouds are mostly
-// duplicates), sorts the unique ones along the same axis and writes them out, with their number.
+// (1) knn_prepare_kernel, one CTA per object: sorts the completed points by the Morton code of their position in
+// the cloud's bounding box (bitonic sort of (code, index) keys in shared memory), writes them as float4
+// (x, y, z, original index) and, for every block of 32 consecutive sorted points — a compact patch of the cloud —
+// its bounding box; de-duplicates the object's queries with a shared-memory hash set keyed by the exact
+// coordinates (duplicate queries cannot change a union — the reference's np.unique(partial) at sampling.py:31
+// is the same optimisation; resampled clouds are mostly duplicates) and writes the unique ones in Morton order
+// too, so that the 32 queries of a warp are neighbours in space.
 //
-// (2) knn_sweep_select_kernel, grid (query chunks, objects): one thread per unique query.  The thread finds
-// its position in the sorted cloud by binary search and sweeps outwards on both sides; a side stops when
-// the squared coordinate difference alone exceeds the k-th best distance so far (every further point on
-// that side is farther still: fl(da*da) <= fl(dx*dx + dy*dy + dz*dz) under round-to-nearest).  A car-sized
-// cloud of 1024 points with k = 20 visits ~1/5 of the pairs of the brute-force scan, and because queries
-// are sorted along the sweep axis the lanes of a warp walk neighbouring addresses for similar trip counts.
-// Neighbour sets are OR-ed into a global bit mask; the last CTA of an object to arrive (global counter)
-// emits complete[sorted(S)] cyclically.  The result is exactly the brute-force one (ties: lower index).
+// (2) knn_scan_kernel, grid (query chunks, objects): one thread per unique query, warps independent (no CTA
+// barrier).  A warp walks the blocks in lockstep — every lane reads the same point, one broadcast load per
+// point — and skips a block when, for every lane, the squared distance from the query to the block's box
+// exceeds the lane's k-th best distance so far.  The box distance is evaluated with the operation order of
+// the point distance, so in fp32 it never exceeds the distance of a point inside the box and the result is
+// exactly the brute-force one (ties: lower index).  Each lane first gets its own nearest block scanned (the
+// warp's lanes share a handful of nearest blocks), which fills its heap with a tight k-th distance; after
+// that a far-away query only touches the blocks of the cap of the cloud that faces it, a query inside the
+// cloud only the patches around it.  Each warp ORs its neighbour sets into a private shared-memory mask and
+// then, one word per lane, into the object's global bit mask.
 //
+// (3) knn_emit_kernel, one CTA per object: complete[sorted(S)] repeated cyclically, and |S|.
+//
+__device__ __forceinline__ unsigned spread10(unsigned v) {   // bit i -> bit 3i
+    v &= 0x3ffu;
+    v = (v | (v << 16)) & 0x030000FFu;
+    v = (v | (v << 8)) & 0x0300F00Fu;
+    v = (v | (v << 4)) & 0x030C30C3u;
+    v = (v | (v << 2)) & 0x09249249u;
+    return v;
+}
+// lo/inv: box origin and 1023 / extent (0 for a flat axis).  Any monotone-per-axis code would do: the order only
+// decides which points share a block, never the result.
+__device__ __forceinline__ unsigned morton30(float x, float y, float z, const float* lo, const float* inv) {
+    const int ix = min(1023, max(0, (int)((x - lo[0]) * inv[0])));
+    const int iy = min(1023, max(0, (int)((y - lo[1]) * inv[1])));
+    const int iz = min(1023, max(0, (int)((z - lo[2]) * inv[2])));
+    return spread10((unsigned)ix) | (spread10((unsigned)iy) << 1) | (spread10((unsigned)iz) << 2);
+}
+
 // prepare smem: keys max(rp2, qp2) u64 | partial SoA 3*np f32 | hash table H i32
 template <int T>
 __global__ void __launch_bounds__(T)
 knn_prepare_kernel(int np, int r, int rp2, int qp2, int hash_size, const float* __restrict__ partial,
-                   const float* __restrict__ complete, float4* __restrict__ ws_refs, float4* __restrict__ ws_q,
-                   int* __restrict__ ws_meta) {
+                   const float* __restrict__ complete, float4* __restrict__ ws_refs, float4* __restrict__ ws_box,
+                   float4* __restrict__ ws_q, int* __restrict__ ws_meta) {
     extern __shared__ __align__(16) unsigned char s_raw[];
     u64* keys = reinterpret_cast<u64*>(s_raw);
     float* qx = reinterpret_cast<float*>(keys + max(rp2, qp2));
     float* qy = qx + np; float* qz = qy + np;
     int* tab = reinterpret_cast<int*>(qz + np);
-    __shared__ float s_lo[3][T / 32], s_hi[3][T / 32];
-    __shared__ int s_axis, s_run;
+    __shared__ float s_lo[6][T / 32], s_hi[6][T / 32];   // 0..2 completed cloud, 3..5 queries
+    __shared__ float s_org[6], s_inv[6];
+    __shared__ int s_run;
 
     const int b = blockIdx.x;
     const float* cp = complete + (size_t)b * r * 3;
     const float* pp = partial + (size_t)b * np * 3;
     const float inf = __int_as_float(0x7f800000);
-    float lo[3] = {inf, inf, inf}, hi[3] = {-inf, -inf, -inf};
+    float lo[6] = {inf, inf, inf, inf, inf, inf}, hi[6] = {-inf, -inf, -inf, -inf, -inf, -inf};
     for (int p = threadIdx.x; p < r; p += T)
 #pragma unroll
         for (int c = 0; c < 3; ++c) { const float v = cp[p * 3 + c]; lo[c] = fminf(lo[c], v); hi[c] = fmaxf(hi[c], v); }
+    for (int p = threadIdx.x; p < np; p += T) {
 #pragma unroll
-    for (int c = 0; c < 3; ++c) {
+        for (int c = 0; c < 3; ++c) {
+            const float v = pp[p * 3 + c];
+            (c == 0 ? qx : c == 1 ? qy : qz)[p] = v;
+            lo[3 + c] = fminf(lo[3 + c], v); hi[3 + c] = fmaxf(hi[3 + c], v);
+        }
+    }
+#pragma unroll
+    for (int c = 0; c < 6; ++c) {
 #pragma unroll
         for (int off = 16; off > 0; off >>= 1) {
             lo[c] = fminf(lo[c], __shfl_xor_sync(0xffffffffu, lo[c], off));
@@ -204,37 +238,47 @@ knn_prepare_kernel(int np, int r, int rp2, int qp2, int hash_size, const float* 
         }
         if (lane_id() == 0) { s_lo[c][warp_id()] = lo[c]; s_hi[c][warp_id()] = hi[c]; }
     }
-    for (int f = threadIdx.x; f < np * 3; f += T) {
-        const float v = pp[f]; const int p = f / 3, c = f - 3 * p;
-        (c == 0 ? qx : c == 1 ? qy : qz)[p] = v;
-    }
     for (int i = threadIdx.x; i < hash_size; i += T) tab[i] = -1;
     if (threadIdx.x == 0) s_run = 0;
     __syncthreads();
-    if (threadIdx.x == 0) {
-        float ext[3];
-        for (int c = 0; c < 3; ++c) {
-            float l = inf, h = -inf;
-            for (int w = 0; w < T / 32; ++w) { l = fminf(l, s_lo[c][w]); h = fmaxf(h, s_hi[c][w]); }
-            ext[c] = h - l;
-        }
-        int a = 0;
-        if (ext[1] > ext[a]) a = 1;
-        if (ext[2] > ext[a]) a = 2;
-        s_axis = a;
+    if (threadIdx.x < 6) {
+        const int c = threadIdx.x;
+        float l = inf, h = -inf;
+        for (int w = 0; w < T / 32; ++w) { l = fminf(l, s_lo[c][w]); h = fmaxf(h, s_hi[c][w]); }
+        const float ext = h - l;
+        s_org[c] = l;
+        s_inv[c] = (ext > 0.f && ext < inf) ? 1023.f / ext : 0.f;
     }
     __syncthreads();
-    const int axis = s_axis;
 
-    // completed cloud, sorted along the axis
+    // completed cloud in Morton order + the box of every 32 consecutive points
     for (int p = threadIdx.x; p < rp2; p += T)
-        keys[p] = p < r ? ((u64)f2ord(cp[p * 3 + axis]) << 32) | (unsigned)p : kInfKey;
+        keys[p] = p < r ? ((u64)morton30(cp[p * 3], cp[p * 3 + 1], cp[p * 3 + 2], s_org, s_inv) << 32) | (unsigned)p : kInfKey;
     __syncthreads();
     bitonic_sort<T>(keys, rp2);
     float4* wr = ws_refs + (size_t)b * r;
-    for (int p = threadIdx.x; p < r; p += T) {
-        const int i = (int)(unsigned)keys[p];
-        wr[p] = make_float4(cp[i * 3 + 0], cp[i * 3 + 1], cp[i * 3 + 2], __int_as_float(i));
+    const int nblk = (r + 31) >> 5;
+    float4* wb = ws_box + (size_t)b * nblk * 2;
+    for (int p0 = warp_id() * 32; p0 < r; p0 += T) {                    // one block per warp pass
+        const int p = p0 + lane_id();
+        float bl[3] = {inf, inf, inf}, bh[3] = {-inf, -inf, -inf};
+        if (p < r) {
+            const int i = (int)(unsigned)keys[p];
+            const float x = cp[i * 3 + 0], y = cp[i * 3 + 1], z = cp[i * 3 + 2];
+            wr[p] = make_float4(x, y, z, __int_as_float(i));
+            bl[0] = bh[0] = x; bl[1] = bh[1] = y; bl[2] = bh[2] = z;
+        }
+#pragma unroll
+        for (int c = 0; c < 3; ++c)
+#pragma unroll
+            for (int off = 16; off > 0; off >>= 1) {
+                bl[c] = fminf(bl[c], __shfl_xor_sync(0xffffffffu, bl[c], off));
+                bh[c] = fmaxf(bh[c], __shfl_xor_sync(0xffffffffu, bh[c], off));
+            }
+        if (lane_id() == 0) {
+            wb[(p0 >> 5) * 2] = make_float4(bl[0], bl[1], bl[2], 0.f);
+            wb[(p0 >> 5) * 2 + 1] = make_float4(bh[0], bh[1], bh[2], 0.f);
+        }
     }
     __syncthreads();
 
@@ -257,7 +301,7 @@ knn_prepare_kernel(int np, int r, int rp2, int qp2, int hash_size, const float* 
         while (true) {
             const int cur = tab[h];
             if (qx[cur] == x && qy[cur] == y && qz[cur] == z) {
-                if (cur == qi) keys[atomicAdd(&s_run, 1)] = ((u64)f2ord(axis == 0 ? x : axis == 1 ? y : z) << 32) | (unsigned)qi;
+                if (cur == qi) keys[atomicAdd(&s_run, 1)] = ((u64)morton30(x, y, z, s_org + 3, s_inv + 3) << 32) | (unsigned)qi;
                 break;
             }
             h = (h + 1) & (hash_size - 1);
@@ -273,86 +317,116 @@ knn_prepare_kernel(int np, int r, int rp2, int qp2, int hash_size, const float* 
         const int qi = (int)(unsigned)keys[p];
         wq[p] = make_float4(qx[qi], qy[qi], qz[qi], 0.f);
     }
-    if (threadIdx.x == 0) { ws_meta[2 * b] = nuniq; ws_meta[2 * b + 1] = axis; }
+    if (threadIdx.x == 0) { ws_meta[2 * b] = nuniq; ws_meta[2 * b + 1] = nblk; }
 }
 
-// select smem: [sorted cloud float4[R] if kSmemRefs] | list k*T u64 | buf kBuf*T u64 | bitmask nw u32 | prefix (nw+1) i32
-template <int T, bool kSmemRefs>
+constexpr int kScanThreads = 128;
+
+// squared distance from q to the box [lo, hi], in the operation order of sqdist(): for a point r inside the box
+// |fl(r.x - q.x)| >= ex etc. (rounding is monotone), hence box_sqdist <= sqdist(q, r) in fp32 as well.
+__device__ __forceinline__ float box_sqdist(float qx, float qy, float qz, float4 lo, float4 hi) {
+    const float ex = fmaxf(fmaxf(__fsub_rn(lo.x, qx), __fsub_rn(qx, hi.x)), 0.f);
+    const float ey = fmaxf(fmaxf(__fsub_rn(lo.y, qy), __fsub_rn(qy, hi.y)), 0.f);
+    const float ez = fmaxf(fmaxf(__fsub_rn(lo.z, qz), __fsub_rn(qz, hi.z)), 0.f);
+    return __fmaf_rn(ez, ez, __fmaf_rn(ey, ey, __fmul_rn(ex, ex)));
+}
+
+// every lane offers the cnt points of one block (warp-uniform addresses: broadcast loads)
+__device__ __forceinline__ void scan_block(TopK<32>& tk, bool active, float qx, float qy, float qz,
+                                           const float4* __restrict__ pts, int cnt) {
+    for (int r0 = 0; r0 < cnt; r0 += 8) {
+        if (active) {
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                if (r0 + u < cnt) { const float4 c = __ldg(&pts[r0 + u]); tk.offer(sqdist(qx, qy, qz, c), __float_as_int(c.w)); }
+            }
+        }
+        if (__any_sync(0xffffffffu, tk.nbuf > kBuf - 8)) tk.flush();
+    }
+    tk.flush();
+}
+
+// per warp in shared memory: heap k x 32 u64 | buffer kBuf x 32 u64 | union mask nwords u32 | scanned blocks nbw u32
+__host__ __device__ inline size_t scan_warp_smem(int k, int r) {
+    const size_t nwords = (size_t)(r + 31) >> 5, nbw = (nwords + 31) >> 5;
+    return ((size_t)(k + kBuf) * 32 * 8 + (nwords + nbw) * 4 + 15) & ~(size_t)15;
+}
+
+__global__ void __launch_bounds__(kScanThreads)
+knn_scan_kernel(int np, int r, int k, const float4* __restrict__ ws_refs, const float4* __restrict__ ws_box,
+                const float4* __restrict__ ws_q, const int* __restrict__ ws_meta, unsigned* __restrict__ g_mask) {
+    extern __shared__ __align__(16) unsigned char s_raw[];
+    const int nwords = (r + 31) >> 5;            // = number of blocks
+    const int nbw = (nwords + 31) >> 5;
+    const int b = blockIdx.y;
+    const int nuniq = ws_meta[2 * b];
+    const int u0 = (blockIdx.x * (kScanThreads / 32) + warp_id()) * 32;
+    if (u0 >= nuniq) return;                                            // warp-uniform
+    unsigned char* mine = s_raw + scan_warp_smem(k, r) * warp_id();
+    u64* s_list = reinterpret_cast<u64*>(mine);
+    u64* s_buf = s_list + (size_t)k * 32;
+    unsigned* mask = reinterpret_cast<unsigned*>(s_buf + (size_t)kBuf * 32);
+    unsigned* done = mask + nwords;
+    for (int i = lane_id(); i < nwords + nbw; i += 32) mask[i] = 0u;
+    __syncwarp();
+
+    const float4* refs = ws_refs + (size_t)b * r;
+    const float4* box = ws_box + (size_t)b * nwords * 2;
+    const int u = u0 + lane_id();
+    const bool active = u < nuniq;
+    float4 q = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (active) q = ws_q[(size_t)b * np + u];
+    TopK<32> tk;
+    tk.init(s_list + lane_id(), s_buf + lane_id(), k);
+
+    // this lane's nearest block (first minimum of the box distance)
+    float best = __int_as_float(0x7f800000);
+    int nearest = 0;
+    for (int blk = 0; blk < nwords; ++blk) {
+        const float bd = box_sqdist(q.x, q.y, q.z, __ldg(&box[2 * blk]), __ldg(&box[2 * blk + 1]));
+        if (bd < best) { best = bd; nearest = blk; }
+    }
+    bool seeded = !active;
+    while (true) {
+        const unsigned m = __ballot_sync(0xffffffffu, !seeded);
+        if (!m) break;
+        const int blk = __shfl_sync(0xffffffffu, nearest, __ffs(m) - 1);
+        scan_block(tk, active, q.x, q.y, q.z, refs + blk * 32, min(32, r - blk * 32));
+        if (lane_id() == 0) done[blk >> 5] |= 1u << (blk & 31);
+        __syncwarp();
+        if (nearest == blk) seeded = true;
+    }
+    for (int blk = 0; blk < nwords; ++blk) {
+        if ((done[blk >> 5] >> (blk & 31)) & 1u) continue;              // warp-uniform
+        const float bd = box_sqdist(q.x, q.y, q.z, __ldg(&box[2 * blk]), __ldg(&box[2 * blk + 1]));
+        if (!__any_sync(0xffffffffu, active && bd <= tk.thr_f)) continue;
+        scan_block(tk, active, q.x, q.y, q.z, refs + blk * 32, min(32, r - blk * 32));
+    }
+    if (active)
+        for (int j = 0; j < k; ++j) {
+            const u64 key = tk.list[j * 32];
+            if (key != kInfKey) { const unsigned i = (unsigned)key; atomicOr(&mask[i >> 5], 1u << (i & 31)); }
+        }
+    __syncwarp();
+    unsigned* gm = g_mask + (size_t)b * nwords;
+    for (int w = lane_id(); w < nwords; w += 32)
+        if (mask[w]) atomicOr(&gm[w], mask[w]);
+}
+
+// One CTA per object: complete[sorted(S)] repeated cyclically, S = the bits of the object's union mask.
+// smem: mask nwords u32 | prefix (nwords + 1) i32
+template <int T>
 __global__ void __launch_bounds__(T)
-knn_sweep_select_kernel(int np, int r, int k, int surface_pts, const float* __restrict__ complete,
-                        const float4* __restrict__ ws_refs, const float4* __restrict__ ws_q,
-                        const int* __restrict__ ws_meta, float* __restrict__ out, int* __restrict__ sel_count,
-                        unsigned* __restrict__ g_mask, unsigned* __restrict__ g_arrive) {
+knn_emit_kernel(int r, int surface_pts, const float* __restrict__ complete, const unsigned* __restrict__ g_mask,
+                float* __restrict__ out, int* __restrict__ sel_count) {
     extern __shared__ __align__(16) unsigned char s_raw[];
     const int nwords = (r + 31) >> 5;
-    float4* cref = reinterpret_cast<float4*>(s_raw);
-    u64* s_list = reinterpret_cast<u64*>(cref + (kSmemRefs ? r : 0));
-    u64* s_buf = s_list + (size_t)k * T;
-    unsigned* mask = reinterpret_cast<unsigned*>(s_buf + (size_t)kBuf * T);
+    unsigned* mask = reinterpret_cast<unsigned*>(s_raw);
     int* prefix = reinterpret_cast<int*>(mask + nwords);
-    __shared__ int s_total, s_last;
-
-    const int b = blockIdx.y, chunk = blockIdx.x;
-    const int nuniq = ws_meta[2 * b], axis = ws_meta[2 * b + 1];
-    const float4* gref = ws_refs + (size_t)b * r;
-    for (int i = threadIdx.x; i < nwords; i += T) mask[i] = 0u;
-    if (chunk * T < nuniq) {                                          // CTA-uniform
-        const float4* refs = gref;
-        if (kSmemRefs) {
-            for (int p = threadIdx.x; p < r; p += T) cref[p] = gref[p];
-            refs = cref;
-        }
-        __syncthreads();
-        const int u = chunk * T + threadIdx.x;
-        if (chunk * T + (int)(threadIdx.x & ~31u) < nuniq) {            // warp-uniform
-            const bool active = u < nuniq;
-            float4 q = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (active) q = ws_q[(size_t)b * np + u];
-            const float qa = axis_of(q, axis);
-            int lo = 0, hi = r;                                         // first sorted position with coordinate >= qa
-            while (lo < hi) {
-                const int mid = (lo + hi) >> 1;
-                if (axis_of(refs[mid], axis) < qa) lo = mid + 1; else hi = mid;
-            }
-            int pr = lo, pl = lo - 1;
-            bool go_r = active && pr < r, go_l = active && pl >= 0;
-            TopK<T> tk;
-            tk.init(s_list + threadIdx.x, s_buf + threadIdx.x, k);
-            int it = 0;
-            while (__any_sync(0xffffffffu, go_r || go_l)) {
-                if (go_r) {
-                    const float4 c = refs[pr];
-                    const float da = __fsub_rn(axis_of(c, axis), qa);
-                    if (__fmul_rn(da, da) > tk.thr_f) go_r = false;
-                    else { tk.offer(sqdist(q.x, q.y, q.z, c), __float_as_int(c.w)); go_r = ++pr < r; }
-                }
-                if (go_l) {
-                    const float4 c = refs[pl];
-                    const float da = __fsub_rn(axis_of(c, axis), qa);
-                    if (__fmul_rn(da, da) > tk.thr_f) go_l = false;
-                    else { tk.offer(sqdist(q.x, q.y, q.z, c), __float_as_int(c.w)); go_l = --pl >= 0; }
-                }
-                if ((++it & 3) == 0 && __any_sync(0xffffffffu, tk.nbuf > kBuf - 8)) tk.flush();
-            }
-            tk.flush();
-            if (active)
-                for (int j = 0; j < k; ++j) {
-                    const u64 key = tk.list[j * T];
-                    if (key != kInfKey) { const unsigned i = (unsigned)key; atomicOr(&mask[i >> 5], 1u << (i & 31)); }
-                }
-        }
-    }
-    __syncthreads();
-    unsigned* gm = g_mask + (size_t)b * nwords;
-    for (int w = threadIdx.x; w < nwords; w += T)
-        if (mask[w]) atomicOr(&gm[w], mask[w]);
-    __threadfence();
-    __syncthreads();
-    if (threadIdx.x == 0) s_last = atomicAdd(&g_arrive[b], 1u) == gridDim.x - 1;
-    __syncthreads();
-    if (!s_last) return;
-    __threadfence();
-    for (int w = threadIdx.x; w < nwords; w += T) mask[w] = __ldcg(&gm[w]);
+    __shared__ int s_total;
+    const int b = blockIdx.x;
+    const unsigned* gm = g_mask + (size_t)b * nwords;
+    for (int w = threadIdx.x; w < nwords; w += T) mask[w] = gm[w];
     __syncthreads();
     // exclusive prefix of popcounts over mask words (nwords <= 512): one warp, serial chunks
     if (threadIdx.x < 32) {
@@ -391,26 +465,7 @@ knn_sweep_select_kernel(int np, int r, int k, int surface_pts, const float* __re
 
 int next_pow2(int v) { int p = 1; while (p < v) p <<= 1; return p; }
 
-size_t select_smem(int T, bool smem_refs, int r, int k) {
-    const int nwords = (r + 31) / 32;
-    return (smem_refs ? (size_t)r * 16 : 0) + (size_t)(k + kBuf) * T * 8 + (size_t)nwords * 4 + (size_t)(nwords + 1) * 4 + 16;
-}
-
-template <int T, bool kSmemRefs>
-int launch_select(int b, int np, int r, int k, int surface_pts, size_t smem, const float* complete, const float4* ws_refs,
-                  const float4* ws_q, const int* ws_meta, float* out, int* sel_count, unsigned* g_mask, unsigned* g_arrive,
-                  cudaStream_t st) {
-    auto kern = knn_sweep_select_kernel<T, kSmemRefs>;
-    if (smem > 40 * 1024)
-        SEEVCN_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    const int chunks = np > 0 ? div_up(np, T) : 1;
-    SEEVCN_PROF("knn_sweep_select_kernel", st);
-    kern<<<dim3(chunks, b), T, smem, st>>>(np, r, k, surface_pts, complete, ws_refs, ws_q, ws_meta, out, sel_count, g_mask, g_arrive);
-    SEEVCN_LAUNCH_CHECK();
-    return SEEVCN_OK;
-}
-
-struct SelectWs { size_t mask, arrive, meta, refs, q, total; };
+struct SelectWs { size_t mask, arrive, meta, refs, box, q, total; };
 SelectWs select_ws(int b, int np, int r) {
     const size_t B = b > 0 ? b : 0, R = r > 0 ? r : 0, N = np > 0 ? np : 0;
     SelectWs w;
@@ -418,7 +473,8 @@ SelectWs select_ws(int b, int np, int r) {
     w.arrive = w.mask + B * ((R + 31) / 32) * 4;
     w.meta = w.arrive + B * 4;
     w.refs = align_up(w.meta + B * 8, 256);
-    w.q = w.refs + B * R * 16;
+    w.box = w.refs + B * R * 16;
+    w.q = w.box + B * ((R + 31) / 32) * 32;
     w.total = w.q + B * N * 16 + 256;
     return w;
 }
@@ -465,9 +521,9 @@ extern "C" int seevcn_knn_surface_select(int b, int n_partial, int r, int k, int
     unsigned char* base = static_cast<unsigned char*>(workspace);
     SEEVCN_REQUIRE((reinterpret_cast<uintptr_t>(base) & 15) == 0, "knn_surface_select: workspace must be 16-byte aligned");
     unsigned* g_mask = reinterpret_cast<unsigned*>(base + w.mask);
-    unsigned* g_arrive = reinterpret_cast<unsigned*>(base + w.arrive);
     int* ws_meta = reinterpret_cast<int*>(base + w.meta);
     float4* ws_refs = reinterpret_cast<float4*>(base + w.refs);
+    float4* ws_box = reinterpret_cast<float4*>(base + w.box);
     float4* ws_q = reinterpret_cast<float4*>(base + w.q);
     SEEVCN_PROF("knn_surface_select", st);
     SEEVCN_CUDA_CHECK(cudaMemsetAsync(base, 0, w.meta, st));
@@ -480,17 +536,23 @@ extern "C" int seevcn_knn_surface_select(int b, int n_partial, int r, int k, int
         if (smem > 40 * 1024)
             SEEVCN_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         SEEVCN_PROF("knn_prepare_kernel", st);
-        kern<<<b, TP, smem, st>>>(n_partial, r, rp2, qp2, hash_size, partial, complete, ws_refs, ws_q, ws_meta);
+        kern<<<b, TP, smem, st>>>(n_partial, r, rp2, qp2, hash_size, partial, complete, ws_refs, ws_box, ws_q, ws_meta);
         SEEVCN_LAUNCH_CHECK();
     }
-    const size_t lim = 227 * 1024;
-    const bool fits = r <= 4096;
-    if (fits && select_smem(256, true, r, k) <= lim / 2)   // two CTAs per SM
-        return launch_select<256, true>(b, n_partial, r, k, surface_pts, select_smem(256, true, r, k), complete, ws_refs, ws_q,
-                                        ws_meta, out, sel_count, g_mask, g_arrive, st);
-    if (fits && select_smem(128, true, r, k) <= lim)
-        return launch_select<128, true>(b, n_partial, r, k, surface_pts, select_smem(128, true, r, k), complete, ws_refs, ws_q,
-                                        ws_meta, out, sel_count, g_mask, g_arrive, st);
-    return launch_select<128, false>(b, n_partial, r, k, surface_pts, select_smem(128, false, r, k), complete, ws_refs, ws_q,
-                                     ws_meta, out, sel_count, g_mask, g_arrive, st);
+    {
+        const int nwords = (r + 31) / 32;
+        const size_t smem = (size_t)(kScanThreads / 32) * scan_warp_smem(k, r);
+        if (smem > 40 * 1024)
+            SEEVCN_CUDA_CHECK(cudaFuncSetAttribute(knn_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        const int chunks = n_partial > 0 ? div_up(n_partial, kScanThreads) : 1;
+        {
+            SEEVCN_PROF("knn_scan_kernel", st);
+            knn_scan_kernel<<<dim3(chunks, b), kScanThreads, smem, st>>>(n_partial, r, k, ws_refs, ws_box, ws_q, ws_meta, g_mask);
+            SEEVCN_LAUNCH_CHECK();
+        }
+        SEEVCN_PROF("knn_emit_kernel", st);
+        knn_emit_kernel<256><<<b, 256, (size_t)(2 * nwords + 1) * 4, st>>>(r, surface_pts, complete, g_mask, out, sel_count);
+        SEEVCN_LAUNCH_CHECK();
+    }
+    return SEEVCN_OK;
 }
