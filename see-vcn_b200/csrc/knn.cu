@@ -29,9 +29,9 @@ __device__ __forceinline__ float sqdist(float qx, float qy, float qz, float4 r) 
     return __fmaf_rn(dz, dz, __fmaf_rn(dy, dy, __fmul_rn(dx, dx)));
 }
 
-// Per-thread top-k state.  list / buf are this thread's columns of [slot][T] arrays in shared memory.  list is a binary
+// Per-thread top-k state.  list / buf are this thread's columns of [slot][T] arrays in shared memory.  list is a 4-ary
 // MAX-heap of k keys (root = the k-th best so far, kInfKey while fewer than k were seen): an accepted candidate replaces
-// the root and sifts down, <= log2(k) levels of two loads and one store.
+// the root and sifts down, <= log4(k) levels (two for k = 20) of four loads and one store.
 template <int T>
 struct TopK {
     u64* list; u64* buf;
@@ -47,13 +47,16 @@ struct TopK {
     __device__ __forceinline__ void insert(u64 key) {   // key < thr
         int i = 0;
         while (true) {
-            int c = 2 * i + 1;
+            const int c = 4 * i + 1;
             if (c >= k) break;
-            u64 a = list[c * T];
-            if (c + 1 < k) { const u64 b = list[(c + 1) * T]; if (b > a) { a = b; ++c; } }
-            if (a <= key) break;
-            list[i * T] = a;
-            i = c;
+            u64 m = list[c * T];
+            int mc = c;
+#pragma unroll
+            for (int t = 1; t < 4; ++t)
+                if (c + t < k) { const u64 v = list[(c + t) * T]; if (v > m) { m = v; mc = c + t; } }
+            if (m <= key) break;
+            list[i * T] = m;
+            i = mc;
         }
         list[i * T] = key;
         thr = list[0];
@@ -173,10 +176,11 @@ __device__ void bitonic_sort(u64* s, int len) {
 // point — and skips a block when, for every lane, the squared distance from the query to the block's box
 // exceeds the lane's k-th best distance so far.  The box distance is evaluated with the operation order of
 // the point distance, so in fp32 it never exceeds the distance of a point inside the box and the result is
-// exactly the brute-force one (ties: lower index).  Each lane first gets its own nearest block scanned (the
-// warp's lanes share a handful of nearest blocks), which fills its heap with a tight k-th distance; after
-// that a far-away query only touches the blocks of the cap of the cloud that faces it, a query inside the
-// cloud only the patches around it.  Each warp ORs its neighbour sets into a private shared-memory mask and
+// exactly the brute-force one (ties: lower index).  Blocks are visited nearest first (key = the smallest box
+// distance over the warp's queries), so the heaps fill with a tight k-th distance at once, and the walk ends
+// when the next key exceeds every lane's k-th distance: a far-away query only touches the blocks of the cap
+// of the cloud that faces it, a query inside the cloud only the patches around it.  The next block's points
+// are loaded (one coalesced 512 B read) while the current one is scanned from the warp's shared-memory tile.  Each warp ORs its neighbour sets into a private shared-memory mask and
 // then, one word per lane, into the object's global bit mask.
 //
 // (3) knn_emit_kernel, one CTA per object: complete[sorted(S)] repeated cyclically, and |S|.
@@ -331,25 +335,36 @@ __device__ __forceinline__ float box_sqdist(float qx, float qy, float qz, float4
     return __fmaf_rn(ez, ez, __fmaf_rn(ey, ey, __fmul_rn(ex, ex)));
 }
 
-// every lane offers the cnt points of one block (warp-uniform addresses: broadcast loads)
+// every lane offers the cnt points of one block staged in the warp's shared-memory tile (broadcast loads)
 __device__ __forceinline__ void scan_block(TopK<32>& tk, bool active, float qx, float qy, float qz,
-                                           const float4* __restrict__ pts, int cnt) {
-    for (int r0 = 0; r0 < cnt; r0 += 8) {
-        if (active) {
+                                           const float4* pts, int cnt) {
+    if (cnt == 32) {
+#pragma unroll 1
+        for (int r0 = 0; r0 < 32; r0 += 8) {
+            if (active) {
 #pragma unroll
-            for (int u = 0; u < 8; ++u) {
-                if (r0 + u < cnt) { const float4 c = __ldg(&pts[r0 + u]); tk.offer(sqdist(qx, qy, qz, c), __float_as_int(c.w)); }
+                for (int u = 0; u < 8; ++u) { const float4 c = pts[r0 + u]; tk.offer(sqdist(qx, qy, qz, c), __float_as_int(c.w)); }
             }
+            if (__any_sync(0xffffffffu, tk.nbuf > kBuf - 8)) tk.flush();
         }
-        if (__any_sync(0xffffffffu, tk.nbuf > kBuf - 8)) tk.flush();
+    } else {
+        for (int r0 = 0; r0 < cnt; r0 += 8) {
+            if (active) {
+#pragma unroll
+                for (int u = 0; u < 8; ++u)
+                    if (r0 + u < cnt) { const float4 c = pts[r0 + u]; tk.offer(sqdist(qx, qy, qz, c), __float_as_int(c.w)); }
+            }
+            if (__any_sync(0xffffffffu, tk.nbuf > kBuf - 8)) tk.flush();
+        }
     }
     tk.flush();
 }
 
-// per warp in shared memory: heap k x 32 u64 | buffer kBuf x 32 u64 | union mask nwords u32 | scanned blocks nbw u32
+// per warp in shared memory: heap k x 32 u64 | buffer kBuf x 32 u64 | block tile 32 float4 | union mask nwords u32 |
+// block keys nwords u32
 __host__ __device__ inline size_t scan_warp_smem(int k, int r) {
-    const size_t nwords = (size_t)(r + 31) >> 5, nbw = (nwords + 31) >> 5;
-    return ((size_t)(k + kBuf) * 32 * 8 + (nwords + nbw) * 4 + 15) & ~(size_t)15;
+    const size_t nwords = (size_t)(r + 31) >> 5;
+    return ((size_t)(k + kBuf) * 32 * 8 + 512 + 2 * nwords * 4 + 15) & ~(size_t)15;
 }
 
 __global__ void __launch_bounds__(kScanThreads)
@@ -357,7 +372,6 @@ knn_scan_kernel(int np, int r, int k, const float4* __restrict__ ws_refs, const 
                 const float4* __restrict__ ws_q, const int* __restrict__ ws_meta, unsigned* __restrict__ g_mask) {
     extern __shared__ __align__(16) unsigned char s_raw[];
     const int nwords = (r + 31) >> 5;            // = number of blocks
-    const int nbw = (nwords + 31) >> 5;
     const int b = blockIdx.y;
     const int nuniq = ws_meta[2 * b];
     const int u0 = (blockIdx.x * (kScanThreads / 32) + warp_id()) * 32;
@@ -365,10 +379,11 @@ knn_scan_kernel(int np, int r, int k, const float4* __restrict__ ws_refs, const 
     unsigned char* mine = s_raw + scan_warp_smem(k, r) * warp_id();
     u64* s_list = reinterpret_cast<u64*>(mine);
     u64* s_buf = s_list + (size_t)k * 32;
-    unsigned* mask = reinterpret_cast<unsigned*>(s_buf + (size_t)kBuf * 32);
-    unsigned* done = mask + nwords;
-    for (int i = lane_id(); i < nwords + nbw; i += 32) mask[i] = 0u;
-    __syncwarp();
+    float4* tile = reinterpret_cast<float4*>(s_buf + (size_t)kBuf * 32);
+    unsigned* mask = reinterpret_cast<unsigned*>(tile + 32);
+    unsigned* wkey = mask + nwords;
+    const unsigned full = 0xffffffffu;
+    for (int i = lane_id(); i < nwords; i += 32) mask[i] = 0u;
 
     const float4* refs = ws_refs + (size_t)b * r;
     const float4* box = ws_box + (size_t)b * nwords * 2;
@@ -379,28 +394,46 @@ knn_scan_kernel(int np, int r, int k, const float4* __restrict__ ws_refs, const 
     TopK<32> tk;
     tk.init(s_list + lane_id(), s_buf + lane_id(), k);
 
-    // this lane's nearest block (first minimum of the box distance)
-    float best = __int_as_float(0x7f800000);
-    int nearest = 0;
+    // block key = the smallest box distance over the warp's queries (non-negative float bits order like unsigned)
+#pragma unroll 4
     for (int blk = 0; blk < nwords; ++blk) {
         const float bd = box_sqdist(q.x, q.y, q.z, __ldg(&box[2 * blk]), __ldg(&box[2 * blk + 1]));
-        if (bd < best) { best = bd; nearest = blk; }
+        const unsigned m = __reduce_min_sync(full, active ? __float_as_uint(bd) : 0xffffffffu);
+        if (lane_id() == 0) wkey[blk] = m;
     }
-    bool seeded = !active;
-    while (true) {
-        const unsigned m = __ballot_sync(0xffffffffu, !seeded);
-        if (!m) break;
-        const int blk = __shfl_sync(0xffffffffu, nearest, __ffs(m) - 1);
-        scan_block(tk, active, q.x, q.y, q.z, refs + blk * 32, min(32, r - blk * 32));
-        if (lane_id() == 0) done[blk >> 5] |= 1u << (blk & 31);
+    __syncwarp();
+
+    // nearest unscanned block whose key does not exceed the largest k-th distance of the warp, or -1; marks it scanned
+    auto pick = [&]() -> int {
+        unsigned best = 0xffffffffu; int bi = -1;
+        for (int j = lane_id(); j < nwords; j += 32) { const unsigned v = wkey[j]; if (v < best) { best = v; bi = j; } }
+        const unsigned m = __reduce_min_sync(full, best);
+        const unsigned tmax = __reduce_max_sync(full, active ? __float_as_uint(tk.thr_f) : 0u);
+        if (m == 0xffffffffu || m > tmax) return -1;
+        const int src = __ffs(__ballot_sync(full, best == m)) - 1;
+        const int blk = __shfl_sync(full, bi, src);
+        if (lane_id() == src) wkey[blk] = 0xffffffffu;
         __syncwarp();
-        if (nearest == blk) seeded = true;
-    }
-    for (int blk = 0; blk < nwords; ++blk) {
-        if ((done[blk >> 5] >> (blk & 31)) & 1u) continue;              // warp-uniform
-        const float bd = box_sqdist(q.x, q.y, q.z, __ldg(&box[2 * blk]), __ldg(&box[2 * blk + 1]));
-        if (!__any_sync(0xffffffffu, active && bd <= tk.thr_f)) continue;
-        scan_block(tk, active, q.x, q.y, q.z, refs + blk * 32, min(32, r - blk * 32));
+        return blk;
+    };
+    auto load = [&](int blk) -> float4 {
+        const int p = blk * 32 + lane_id();
+        return (blk >= 0 && p < r) ? __ldg(&refs[p]) : make_float4(0.f, 0.f, 0.f, 0.f);
+    };
+
+    int cur = pick();
+    float4 regs = load(cur);
+    while (cur >= 0) {
+        const int nxt = pick();                   // chosen with the k-th distances as they stand: never skips a needed block
+        const float4 nregs = load(nxt);           // in flight while the current block is scanned
+        const float bd = box_sqdist(q.x, q.y, q.z, __ldg(&box[2 * cur]), __ldg(&box[2 * cur + 1]));
+        if (__any_sync(full, active && bd <= tk.thr_f)) {
+            tile[lane_id()] = regs;
+            __syncwarp();
+            scan_block(tk, active, q.x, q.y, q.z, tile, min(32, r - cur * 32));
+            __syncwarp();
+        }
+        cur = nxt; regs = nregs;
     }
     if (active)
         for (int j = 0; j < k; ++j) {
