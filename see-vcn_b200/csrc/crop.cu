@@ -75,6 +75,7 @@ points_in_boxes_kernel(int boxes_num, int pts_num, const float* __restrict__ box
                        int* __restrict__ tile_counts /* (B, ntiles, T) */) {
     __shared__ __align__(16) float s_pts[kTilePts * 3 + 8];
     __shared__ BoxConst s_box[kBoxChunk];
+    __shared__ float s_rxy[kBoxChunk];
     extern __shared__ int s_hist[];   // HIST: boxes_num ints
 
     const int b = blockIdx.y;
@@ -89,25 +90,55 @@ points_in_boxes_kernel(int boxes_num, int pts_num, const float* __restrict__ box
     float px[kPtsPerThread], py[kPtsPerThread], pz[kPtsPerThread];
 #pragma unroll
     for (int j = 0; j < kPtsPerThread; ++j) res[j] = -1;
+    // a warp owns 128 CONSECUTIVE points (point j of lane l = warp*128 + j*32 + l): in sensor order that is a short
+    // arc of one beam, so its bounding box misses almost every object box and the exact test is skipped for those
+    float wlo[3], whi[3];
+    const int wbase = warp_id() * (32 * kPtsPerThread) + lane_id();
 
     const float* fboxes = boxes + (size_t)b * boxes_num * 7;
     for (int k0 = 0; k0 < boxes_num; k0 += kBoxChunk) {
         const int nb = min(kBoxChunk, boxes_num - k0);
         __syncthreads();   // staging done (first pass) / previous chunk consumed
-        if (threadIdx.x < nb) load_box_const(s_box[threadIdx.x], fboxes + (size_t)(k0 + threadIdx.x) * 7, nullptr, 1e-5f);
+        if (threadIdx.x < nb) {
+            BoxConst bc;
+            load_box_const(bc, fboxes + (size_t)(k0 + threadIdx.x) * 7, nullptr, 1e-5f);
+            s_box[threadIdx.x] = bc;
+            // a point that passes the test lies within rxy of the centre in xy and hz in z (the rotation preserves
+            // length up to fp32 rounding: 1e-4 relative + 1e-4 absolute slack is orders of magnitude above it)
+            s_rxy[threadIdx.x] = sqrtf(bc.tx * bc.tx + bc.ty * bc.ty) * 1.0001f + 1e-4f;
+        }
         __syncthreads();
         if (k0 == 0) {
+            const float inf = __int_as_float(0x7f800000);
+            wlo[0] = wlo[1] = wlo[2] = inf; whi[0] = whi[1] = whi[2] = -inf;
 #pragma unroll
             for (int j = 0; j < kPtsPerThread; ++j) {
-                const int i = threadIdx.x + j * kThreads;
+                const int i = wbase + j * 32;
                 const bool ok = i < npts;
                 px[j] = ok ? s_pts[mis + 3 * i + 0] : 0.f;
                 py[j] = ok ? s_pts[mis + 3 * i + 1] : 0.f;
                 pz[j] = ok ? s_pts[mis + 3 * i + 2] : 0.f;
+                if (ok) {
+                    wlo[0] = fminf(wlo[0], px[j]); whi[0] = fmaxf(whi[0], px[j]);
+                    wlo[1] = fminf(wlo[1], py[j]); whi[1] = fmaxf(whi[1], py[j]);
+                    wlo[2] = fminf(wlo[2], pz[j]); whi[2] = fmaxf(whi[2], pz[j]);
+                }
             }
+#pragma unroll
+            for (int c = 0; c < 3; ++c)
+#pragma unroll
+                for (int off = 16; off > 0; off >>= 1) {
+                    wlo[c] = fminf(wlo[c], __shfl_xor_sync(0xffffffffu, wlo[c], off));
+                    whi[c] = fmaxf(whi[c], __shfl_xor_sync(0xffffffffu, whi[c], off));
+                }
         }
         for (int k = 0; k < nb; ++k) {
             const BoxConst bc = s_box[k];
+            const float rxy = s_rxy[k], rz = bc.hz * 1.0001f + 1e-4f;
+            // warp-uniform; written so that NaN boxes are never skipped (they fall through to the exact test)
+            if (wlo[0] > bc.cx + rxy || whi[0] < bc.cx - rxy || wlo[1] > bc.cy + rxy || whi[1] < bc.cy - rxy ||
+                wlo[2] > bc.cz + rz || whi[2] < bc.cz - rz)
+                continue;
 #pragma unroll
             for (int j = 0; j < kPtsPerThread; ++j)
                 if (res[j] < 0 && pt_in_box<true>(bc, px[j], py[j], pz[j])) res[j] = k0 + k;
@@ -116,7 +147,7 @@ points_in_boxes_kernel(int boxes_num, int pts_num, const float* __restrict__ box
     int* out = box_idx_of_points + (size_t)b * pts_num + p0;
 #pragma unroll
     for (int j = 0; j < kPtsPerThread; ++j) {
-        const int i = threadIdx.x + j * kThreads;
+        const int i = wbase + j * 32;
         if (i < npts) {
             out[i] = res[j];
             if (HIST && res[j] >= 0) atomicAdd(&s_hist[res[j]], 1);

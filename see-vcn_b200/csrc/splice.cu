@@ -113,16 +113,32 @@ splice_mask_kernel(int pts_per_frame, const float* __restrict__ frame_pts, int n
     __syncthreads();
     const int obj_lo = s_range[0], obj_hi = s_range[1];
 
+    // a warp owns 128 CONSECUTIVE points (point e of lane l = warp*128 + e*32 + l): in sensor order a short arc of one
+    // beam, whose bounding box misses almost every object bound — those objects cost one warp-uniform test
     float px[kPtsPerThread], py[kPtsPerThread], pz[kPtsPerThread];
-    unsigned removed = 0;   // bit e: point e*256 + tid is replaced
+    unsigned removed = 0;   // bit e: point wbase + e*32 is replaced
+    const int wbase = warp_id() * (32 * kPtsPerThread) + lane_id();
+    float wlo[3] = {INFINITY, INFINITY, INFINITY}, whi[3] = {-INFINITY, -INFINITY, -INFINITY};
 #pragma unroll
     for (int e = 0; e < kPtsPerThread; ++e) {
-        const int i = e * kThreads + threadIdx.x;
+        const int i = wbase + e * 32;
         const bool ok = i < npts;
         px[e] = ok ? s_pts[mis + i * 3] : INFINITY;   // +inf fails every bound test
         py[e] = ok ? s_pts[mis + i * 3 + 1] : INFINITY;
         pz[e] = ok ? s_pts[mis + i * 3 + 2] : INFINITY;
+        if (ok) {
+            wlo[0] = fminf(wlo[0], px[e]); whi[0] = fmaxf(whi[0], px[e]);
+            wlo[1] = fminf(wlo[1], py[e]); whi[1] = fmaxf(whi[1], py[e]);
+            wlo[2] = fminf(wlo[2], pz[e]); whi[2] = fmaxf(whi[2], pz[e]);
+        }
     }
+#pragma unroll
+    for (int c = 0; c < 3; ++c)
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) {
+            wlo[c] = fminf(wlo[c], __shfl_xor_sync(0xffffffffu, wlo[c], off));
+            whi[c] = fmaxf(whi[c], __shfl_xor_sync(0xffffffffu, whi[c], off));
+        }
     const float t2 = thresh_f * thresh_f;
     const float t2_in = t2 * (1.f - 1e-5f), t2_out = t2 * (1.f + 1e-5f);
 
@@ -134,6 +150,9 @@ splice_mask_kernel(int pts_per_frame, const float* __restrict__ frame_pts, int n
         __syncthreads();
         for (int j = 0; j < nc; ++j) {
             const ObjBound& b = s_obj[j];
+            if (wlo[0] > b.hi[0] || whi[0] < b.lo[0] || wlo[1] > b.hi[1] || whi[1] < b.lo[1] || wlo[2] > b.hi[2] ||
+                whi[2] < b.lo[2])
+                continue;                                                 // warp-uniform
             unsigned cand = 0;
 #pragma unroll
             for (int e = 0; e < kPtsPerThread; ++e) {
@@ -162,7 +181,7 @@ splice_mask_kernel(int pts_per_frame, const float* __restrict__ frame_pts, int n
     int kept = 0;
 #pragma unroll
     for (int e = 0; e < kPtsPerThread; ++e) {
-        const int i = e * kThreads + threadIdx.x;
+        const int i = wbase + e * 32;
         if (i < npts) {
             const unsigned k = ((removed >> e) & 1u) ^ 1u;
             keep[(size_t)f * pts_per_frame + p0 + i] = (unsigned char)k;

@@ -5,7 +5,7 @@ import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
 
-from seevcn_b200.dist import shard_range, all_gather_v, rebase_batch_index
+from seevcn_b200.dist import shard_range, all_gather_v, all_gather_padded, rebase_batch_index
 
 
 def test_shard_range_covers_everything():
@@ -27,8 +27,11 @@ def _worker(rank, world, port, ret):
     full, counts = all_gather_v(local)
     coords = torch.tensor([[0, 1, 2, 3], [hi - lo - 1, 4, 5, 6]], dtype=torch.int32)
     allc, _ = all_gather_v(rebase_batch_index(coords, lo))
+    pg = all_gather_padded(local, 4, async_op=True)            # streaming form: fixed capacity, counts as a tensor
+    parts = pg.parts()
     if rank == 0:
         ret["full"] = full.clone(); ret["counts"] = counts; ret["coords"] = allc.clone()
+        ret["padded_counts"] = pg.counts.tolist(); ret["padded"] = torch.cat(parts).clone(); ret["padded_shape"] = tuple(pg.out.shape)
     dist.destroy_process_group()
 
 
@@ -40,3 +43,5 @@ def test_all_gather_v_gloo_world2():
     assert ret["counts"] == [3, 2]
     assert ret["full"][:, 0, 0].tolist() == [0.0, 1.0, 2.0, 3.0, 4.0]
     assert ret["coords"][:, 0].tolist() == [0, 2, 3, 4]
+    assert ret["padded_counts"] == [3, 2] and ret["padded_shape"] == (2, 4, 4, 3)
+    assert torch.equal(ret["padded"], ret["full"])
