@@ -31,21 +31,22 @@ __device__ __forceinline__ float sqdist(float qx, float qy, float qz, float4 r) 
 
 // Per-thread top-k state.  list / buf are this thread's columns of [slot][T] arrays in shared memory.  list is a 4-ary
 // MAX-heap of k keys (root = the k-th best so far, kInfKey while fewer than k were seen): an accepted candidate replaces
-// the root and sifts down, <= log4(k) levels (two for k = 20) of four loads and one store.
+// the root and sifts down, <= log4(k) levels (two for k = 20) of four loads and one store.  The first k candidates
+// are appended and the heap is built once (Floyd), so filling costs no sifts.
 template <int T>
 struct TopK {
     u64* list; u64* buf;
-    u64 thr; float thr_f; int nbuf, k;
+    u64 thr; float thr_f; int nbuf, k, count;
     __device__ __forceinline__ void init(u64* list_, u64* buf_, int k_) {
         list = list_; buf = buf_; k = k_;
         for (int j = 0; j < k; ++j) list[j * T] = kInfKey;
-        thr = kInfKey; thr_f = __int_as_float(0x7f800000); nbuf = 0;
+        thr = kInfKey; thr_f = __int_as_float(0x7f800000); nbuf = 0; count = 0;
     }
     __device__ __forceinline__ void offer(float d, int idx) {
         if (d <= thr_f) { buf[nbuf * T] = ((u64)__float_as_uint(d) << 32) | (unsigned)idx; ++nbuf; }
     }
-    __device__ __forceinline__ void insert(u64 key) {   // key < thr
-        int i = 0;
+    // put key into the hole at node i and let it sink
+    __device__ __forceinline__ void sift_down(int i, u64 key) {
         while (true) {
             const int c = 4 * i + 1;
             if (c >= k) break;
@@ -59,8 +60,22 @@ struct TopK {
             i = mc;
         }
         list[i * T] = key;
+    }
+    __device__ __forceinline__ void set_thr() {
         thr = list[0];
         thr_f = thr == kInfKey ? __int_as_float(0x7f800000) : __uint_as_float((unsigned)(thr >> 32));
+    }
+    __device__ __forceinline__ void insert(u64 key) {   // key < thr
+        if (count < k) {                                // filling: append, heapify once when the k-th arrives
+            list[count * T] = key;
+            if (++count == k) {
+                for (int i = (k - 2) / 4; i >= 0; --i) sift_down(i, list[i * T]);
+                set_thr();
+            }
+            return;
+        }
+        sift_down(0, key);
+        set_thr();
     }
     __device__ __forceinline__ void flush() {
         for (int e = 0; e < nbuf; ++e) {
@@ -325,6 +340,7 @@ knn_prepare_kernel(int np, int r, int rp2, int qp2, int hash_size, const float* 
 }
 
 constexpr int kScanThreads = 128;
+constexpr int kScanBuf = 8;   // candidate buffer of the block scan (flushed when more than 4 are pending)
 
 // squared distance from q to the box [lo, hi], in the operation order of sqdist(): for a point r inside the box
 // |fl(r.x - q.x)| >= ex etc. (rounding is monotone), hence box_sqdist <= sqdist(q, r) in fp32 as well.
@@ -340,31 +356,31 @@ __device__ __forceinline__ void scan_block(TopK<32>& tk, bool active, float qx, 
                                            const float4* pts, int cnt) {
     if (cnt == 32) {
 #pragma unroll 1
-        for (int r0 = 0; r0 < 32; r0 += 8) {
+        for (int r0 = 0; r0 < 32; r0 += 4) {
             if (active) {
 #pragma unroll
-                for (int u = 0; u < 8; ++u) { const float4 c = pts[r0 + u]; tk.offer(sqdist(qx, qy, qz, c), __float_as_int(c.w)); }
+                for (int u = 0; u < 4; ++u) { const float4 c = pts[r0 + u]; tk.offer(sqdist(qx, qy, qz, c), __float_as_int(c.w)); }
             }
-            if (__any_sync(0xffffffffu, tk.nbuf > kBuf - 8)) tk.flush();
+            if (__any_sync(0xffffffffu, tk.nbuf > kScanBuf - 4)) tk.flush();
         }
     } else {
-        for (int r0 = 0; r0 < cnt; r0 += 8) {
+        for (int r0 = 0; r0 < cnt; r0 += 4) {
             if (active) {
 #pragma unroll
-                for (int u = 0; u < 8; ++u)
+                for (int u = 0; u < 4; ++u)
                     if (r0 + u < cnt) { const float4 c = pts[r0 + u]; tk.offer(sqdist(qx, qy, qz, c), __float_as_int(c.w)); }
             }
-            if (__any_sync(0xffffffffu, tk.nbuf > kBuf - 8)) tk.flush();
+            if (__any_sync(0xffffffffu, tk.nbuf > kScanBuf - 4)) tk.flush();
         }
     }
     tk.flush();
 }
 
-// per warp in shared memory: heap k x 32 u64 | buffer kBuf x 32 u64 | block tile 32 float4 | union mask nwords u32 |
+// per warp in shared memory: heap k x 32 u64 | buffer kScanBuf x 32 u64 | block tile 32 float4 | union mask nwords u32 |
 // block keys nwords u32
 __host__ __device__ inline size_t scan_warp_smem(int k, int r) {
     const size_t nwords = (size_t)(r + 31) >> 5;
-    return ((size_t)(k + kBuf) * 32 * 8 + 512 + 2 * nwords * 4 + 15) & ~(size_t)15;
+    return ((size_t)(k + kScanBuf) * 32 * 8 + 512 + 2 * nwords * 4 + 15) & ~(size_t)15;
 }
 
 __global__ void __launch_bounds__(kScanThreads)
@@ -379,7 +395,7 @@ knn_scan_kernel(int np, int r, int k, const float4* __restrict__ ws_refs, const 
     unsigned char* mine = s_raw + scan_warp_smem(k, r) * warp_id();
     u64* s_list = reinterpret_cast<u64*>(mine);
     u64* s_buf = s_list + (size_t)k * 32;
-    float4* tile = reinterpret_cast<float4*>(s_buf + (size_t)kBuf * 32);
+    float4* tile = reinterpret_cast<float4*>(s_buf + (size_t)kScanBuf * 32);
     unsigned* mask = reinterpret_cast<unsigned*>(tile + 32);
     unsigned* wkey = mask + nwords;
     const unsigned full = 0xffffffffu;

@@ -280,6 +280,7 @@ linear_skinny_kernel(int rows, int cin, int cout, const float* __restrict__ X, i
 #pragma unroll
     for (int c = 0; c < 16; ++c) acc[c] = 0.f;
     const float* x = X + (size_t)row * ldx;
+#pragma unroll 4
     for (int k = lane_id(); k < cin; k += 32) {
         const float xv = x[k];
 #pragma unroll

@@ -118,7 +118,7 @@ __global__ void __launch_bounds__(256)
 dynvox_finalize_kernel(unsigned long long nslots, int c, VoxGeom g, const unsigned long long* __restrict__ keys,
                        const float* __restrict__ acc, int max_voxels, int* __restrict__ voxel_coords,
                        float* __restrict__ voxel_features, int* __restrict__ voxel_counts,
-                       unsigned long long* __restrict__ out_keys, int* __restrict__ num_voxels) {
+                       unsigned long long* __restrict__ out_keys, int key32, int* __restrict__ num_voxels) {
     __shared__ int s_wcnt[8];
     __shared__ int s_base;
     const unsigned long long nthreads = (unsigned long long)gridDim.x * blockDim.x;
@@ -151,7 +151,10 @@ dynvox_finalize_kernel(unsigned long long nslots, int c, VoxGeom g, const unsign
         reinterpret_cast<int4*>(voxel_coords)[row] = make_int4((int)b, (int)z, (int)y, (int)x);   // [b,z,y,x]
         for (int j = 0; j < c; ++j) voxel_features[(size_t)row * c + j] = __fdiv_rn(a[j], cnt);
         voxel_counts[row] = (int)cnt;
-        if (out_keys) out_keys[row] = key;
+        if (out_keys) {   // sort keys: 32-bit when the whole grid x batch fits (halves the radix sort's key traffic)
+            if (key32) reinterpret_cast<unsigned*>(out_keys)[row] = (unsigned)key;
+            else out_keys[row] = key;
+        }
     }
 }
 
@@ -304,6 +307,10 @@ HardWs hard_layout(int n, int t, int max_voxels) {
     w.off_cnt = take(mv * 4);
     size_t cub_bytes = 0;
     cub::DeviceScan::ExclusiveSum(nullptr, cub_bytes, (const int*)nullptr, (int*)nullptr, (int)np);
+    size_t cub_bytes32 = 0;
+    cub::DeviceRadixSort::SortPairs(nullptr, cub_bytes32, (const unsigned*)nullptr, (unsigned*)nullptr, (const int*)nullptr,
+                                    (int*)nullptr, (int)mv);
+    if (cub_bytes32 > cub_bytes) cub_bytes = cub_bytes32;
     w.cub_bytes = cub_bytes;
     w.off_cub = take(cub_bytes);
     w.total = o;
@@ -338,6 +345,10 @@ DynWs dyn_layout(int n, int c, int max_voxels) {
     size_t cub_bytes = 0;
     cub::DeviceRadixSort::SortPairs(nullptr, cub_bytes, (const unsigned long long*)nullptr, (unsigned long long*)nullptr,
                                     (const int*)nullptr, (int*)nullptr, (int)mv);
+    size_t cub_bytes32 = 0;
+    cub::DeviceRadixSort::SortPairs(nullptr, cub_bytes32, (const unsigned*)nullptr, (unsigned*)nullptr, (const int*)nullptr,
+                                    (int*)nullptr, (int)mv);
+    if (cub_bytes32 > cub_bytes) cub_bytes = cub_bytes32;
     w.cub_bytes = cub_bytes;
     w.off_cub = take(cub_bytes);
     w.total = o;
@@ -400,23 +411,25 @@ int dynvox_run(const char* what, int num_points, int num_features, const DynSrc&
         o_keys = reinterpret_cast<unsigned long long*>(ws + w.off_sort_keys_in);
         SEEVCN_CUDA_CHECK(cudaMemsetAsync(o_keys, 0xff, (size_t)max_voxels * 8, st));
     }
+    const double span = (double)batch_hint * g.g[0] * g.g[1] * g.g[2];   // keys are < span
+    const int key32 = sorted && span <= 4294967295.0 ? 1 : 0;
     if (!src.points) {
         dynvox_insert_frames_kernel<<<grid_ins, 256, 0, st>>>(src.n_frame_pts, src.pts_per_frame, src.frame_pts, src.frame_keep,
                                                              src.n_obj_pts, src.pts_per_obj, src.obj_pts, src.obj_frame, src.obj_count,
                                                              g, w.nslots - 1, keys, acc);
         SEEVCN_LAUNCH_CHECK();
         dynvox_finalize_kernel<4><<<grid_fin, 256, 0, st>>>(w.nslots, num_features, g, keys, acc, max_voxels, o_coords,
-                                                           o_feat, o_cnt, o_keys, num_voxels);
+                                                           o_feat, o_cnt, o_keys, key32, num_voxels);
     } else if (w.accw == 4) {
         dynvox_insert_kernel<4><<<grid_ins, 256, 0, st>>>(num_points, num_features, src.points, g, w.nslots - 1, keys, acc);
         SEEVCN_LAUNCH_CHECK();
         dynvox_finalize_kernel<4><<<grid_fin, 256, 0, st>>>(w.nslots, num_features, g, keys, acc, max_voxels, o_coords,
-                                                           o_feat, o_cnt, o_keys, num_voxels);
+                                                           o_feat, o_cnt, o_keys, key32, num_voxels);
     } else {
         dynvox_insert_kernel<8><<<grid_ins, 256, 0, st>>>(num_points, num_features, src.points, g, w.nslots - 1, keys, acc);
         SEEVCN_LAUNCH_CHECK();
         dynvox_finalize_kernel<8><<<grid_fin, 256, 0, st>>>(w.nslots, num_features, g, keys, acc, max_voxels, o_coords,
-                                                           o_feat, o_cnt, o_keys, num_voxels);
+                                                           o_feat, o_cnt, o_keys, key32, num_voxels);
     }
     SEEVCN_LAUNCH_CHECK();
     if (sorted) {
@@ -428,10 +441,15 @@ int dynvox_run(const char* what, int num_points, int num_features, const DynSrc&
         size_t cub_bytes = w.cub_bytes;
         // keys are < 2^kb except the all-ones padding of unused rows, which any bit range keeps last
         int kb = 1;
-        const double span = (double)batch_hint * g.g[0] * g.g[1] * g.g[2];
         while (kb < 64 && (double)(1ull << kb) < span) ++kb;
-        SEEVCN_CUDA_CHECK(cub::DeviceRadixSort::SortPairs(ws + w.off_cub, cub_bytes, o_keys, keys_out, order_in,
-                                                          order_out, max_voxels, 0, kb < 64 ? kb + 1 : 64, st));
+        if (key32) {
+            SEEVCN_CUDA_CHECK(cub::DeviceRadixSort::SortPairs(ws + w.off_cub, cub_bytes, reinterpret_cast<const unsigned*>(o_keys),
+                                                              reinterpret_cast<unsigned*>(keys_out), order_in, order_out,
+                                                              max_voxels, 0, kb < 32 ? kb + 1 : 32, st));
+        } else {
+            SEEVCN_CUDA_CHECK(cub::DeviceRadixSort::SortPairs(ws + w.off_cub, cub_bytes, o_keys, keys_out, order_in,
+                                                              order_out, max_voxels, 0, kb < 64 ? kb + 1 : 64, st));
+        }
         dynvox_permute_kernel<<<div_up(max_voxels, 256), 256, 0, st>>>(
             max_voxels, num_features, num_voxels, order_out, reinterpret_cast<const int4*>(o_coords), o_feat, o_cnt,
             reinterpret_cast<int4*>(voxel_coords), voxel_features, voxel_counts);
