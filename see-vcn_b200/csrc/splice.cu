@@ -24,6 +24,7 @@ constexpr int kThreads = 256;
 constexpr int kPtsPerThread = 4;
 constexpr int kTilePts = kThreads * kPtsPerThread;   // 1024 points = 12 KB
 constexpr int kObjChunk = 256;                       // object bounds staged per pass
+constexpr int kWorkCap = 2048;                       // candidate pairs queued per tile and pass
 
 struct __align__(16) ObjBound {   // 32 B
     float lo[3]; int count;
@@ -100,7 +101,10 @@ splice_mask_kernel(int pts_per_frame, const float* __restrict__ frame_pts, int n
                    unsigned char* __restrict__ keep, int* __restrict__ tile_kept) {
     __shared__ __align__(16) float s_pts[kTilePts * 3 + 8];
     __shared__ ObjBound s_obj[kObjChunk];
+    __shared__ unsigned s_work[kWorkCap];          // candidate (point, object) pairs of the tile: (point << 8) | object
+    __shared__ unsigned char s_removed[kTilePts];
     __shared__ int s_range[2];
+    __shared__ int s_nwork;
     __shared__ int s_cnt[kThreads / 32];
 
     const int f = blockIdx.y, tile = blockIdx.x;
@@ -108,6 +112,7 @@ splice_mask_kernel(int pts_per_frame, const float* __restrict__ frame_pts, int n
     const int npts = min(kTilePts, pts_per_frame - p0);
     const float* src = frame_pts + ((size_t)f * pts_per_frame + p0) * 3;
     const int mis = stage_floats(s_pts, src, npts * 3);
+    for (int i = threadIdx.x; i < kTilePts; i += kThreads) s_removed[i] = 0;
     if (threadIdx.x == 0) s_range[0] = lower_bound_frame(bounds, num_obj, f);
     if (threadIdx.x == 32) s_range[1] = lower_bound_frame(bounds, num_obj, f + 1);
     __syncthreads();
@@ -116,7 +121,6 @@ splice_mask_kernel(int pts_per_frame, const float* __restrict__ frame_pts, int n
     // a warp owns 128 CONSECUTIVE points (point e of lane l = warp*128 + e*32 + l): in sensor order a short arc of one
     // beam, whose bounding box misses almost every object bound — those objects cost one warp-uniform test
     float px[kPtsPerThread], py[kPtsPerThread], pz[kPtsPerThread];
-    unsigned removed = 0;   // bit e: point wbase + e*32 is replaced
     const int wbase = warp_id() * (32 * kPtsPerThread) + lane_id();
     float wlo[3] = {INFINITY, INFINITY, INFINITY}, whi[3] = {-INFINITY, -INFINITY, -INFINITY};
 #pragma unroll
@@ -142,48 +146,66 @@ splice_mask_kernel(int pts_per_frame, const float* __restrict__ frame_pts, int n
     const float t2 = thresh_f * thresh_f;
     const float t2_in = t2 * (1.f - 1e-5f), t2_out = t2 * (1.f + 1e-5f);
 
+    // Candidates (points inside an object's bound) cluster in the few warps whose arc crosses a car, and each costs a
+    // scan of that object's rows: they are queued per tile and the scans are spread over all warps of the CTA.
     for (int c0 = obj_lo; c0 < obj_hi; c0 += kObjChunk) {
         const int nc = min(kObjChunk, obj_hi - c0);
         __syncthreads();
         for (int j = threadIdx.x; j < nc * 2; j += kThreads)
             reinterpret_cast<float4*>(s_obj)[j] = reinterpret_cast<const float4*>(bounds + c0)[j];
+        if (threadIdx.x == 0) s_nwork = 0;
         __syncthreads();
         for (int j = 0; j < nc; ++j) {
             const ObjBound& b = s_obj[j];
             if (wlo[0] > b.hi[0] || whi[0] < b.lo[0] || wlo[1] > b.hi[1] || whi[1] < b.lo[1] || wlo[2] > b.hi[2] ||
                 whi[2] < b.lo[2])
                 continue;                                                 // warp-uniform
-            unsigned cand = 0;
 #pragma unroll
             for (int e = 0; e < kPtsPerThread; ++e) {
+                const int i = wbase + e * 32;
                 const bool in = (px[e] >= b.lo[0]) & (px[e] <= b.hi[0]) & (py[e] >= b.lo[1]) & (py[e] <= b.hi[1]) &
-                                (pz[e] >= b.lo[2]) & (pz[e] <= b.hi[2]) & !((removed >> e) & 1u);
-                cand |= (unsigned)in << e;
-            }
-            if (!__any_sync(0xffffffffu, cand != 0)) continue;
-            const float* rows = obj_pts + (size_t)(c0 + j) * pts_per_obj * 3;
-#pragma unroll
-            for (int e = 0; e < kPtsPerThread; ++e) {
-                unsigned m = __ballot_sync(0xffffffffu, (cand >> e) & 1u);
-                while (m) {
-                    const int src_lane = __ffs(m) - 1;
-                    m &= m - 1;
-                    const float x = __shfl_sync(0xffffffffu, px[e], src_lane);
-                    const float y = __shfl_sync(0xffffffffu, py[e], src_lane);
-                    const float z = __shfl_sync(0xffffffffu, pz[e], src_lane);
-                    const bool near = warp_near_object(x, y, z, rows, b.count, t2_in, t2_out, thresh);
-                    if (near && lane_id() == src_lane) removed |= 1u << e;
+                                (pz[e] >= b.lo[2]) & (pz[e] <= b.hi[2]);
+                unsigned m = __ballot_sync(0xffffffffu, in);
+                if (!m) continue;
+                int base = 0;
+                if (lane_id() == 0) base = atomicAdd(&s_nwork, __popc(m));
+                base = __shfl_sync(0xffffffffu, base, 0);
+                if (base + __popc(m) <= kWorkCap) {
+                    if (in) s_work[base + __popc(m & ((1u << lane_id()) - 1))] = ((unsigned)i << 8) | (unsigned)j;
+                } else {                                                  // queue full: scan here, one point at a time
+                    const float* rows = obj_pts + (size_t)(c0 + j) * pts_per_obj * 3;
+                    while (m) {
+                        const int src_lane = __ffs(m) - 1;
+                        m &= m - 1;
+                        const float x = __shfl_sync(0xffffffffu, px[e], src_lane);
+                        const float y = __shfl_sync(0xffffffffu, py[e], src_lane);
+                        const float z = __shfl_sync(0xffffffffu, pz[e], src_lane);
+                        const bool near = warp_near_object(x, y, z, rows, b.count, t2_in, t2_out, thresh);
+                        if (near && lane_id() == src_lane) s_removed[i] = 1;
+                    }
                 }
             }
         }
+        __syncthreads();
+        const int nwork = min(s_nwork, kWorkCap);
+        for (int w = warp_id(); w < nwork; w += kThreads / 32) {
+            const unsigned ent = s_work[w];
+            const int i = (int)(ent >> 8), j = (int)(ent & 255u);
+            if (*reinterpret_cast<volatile unsigned char*>(&s_removed[i])) continue;   // another object already replaced it
+            const float x = s_pts[mis + i * 3], y = s_pts[mis + i * 3 + 1], z = s_pts[mis + i * 3 + 2];
+            const bool near = warp_near_object(x, y, z, obj_pts + (size_t)(c0 + j) * pts_per_obj * 3, s_obj[j].count, t2_in,
+                                               t2_out, thresh);
+            if (near && lane_id() == 0) s_removed[i] = 1;
+        }
     }
+    __syncthreads();
 
     int kept = 0;
 #pragma unroll
     for (int e = 0; e < kPtsPerThread; ++e) {
         const int i = wbase + e * 32;
         if (i < npts) {
-            const unsigned k = ((removed >> e) & 1u) ^ 1u;
+            const unsigned k = s_removed[i] ? 0u : 1u;
             keep[(size_t)f * pts_per_frame + p0 + i] = (unsigned char)k;
             kept += (int)k;
         }

@@ -115,6 +115,26 @@ def test_splice_edge_cases(cuda):
     assert 100 < (~want_keep).sum() < P
 
 
+def test_splice_candidate_queue_overflow(cuda):
+    """Every point of a tile lies inside the bounds of four objects (4 x 1024 pairs > the per-tile queue): the
+    overflow path gives the same mask."""
+    rng = np.random.default_rng(21)
+    pts = rng.uniform(0, 1, (2, 1500, 3)).astype(np.float32)
+    corners = np.array([[x, y, z] for x in (-0.2, 1.2) for y in (-0.2, 1.2) for z in (-0.2, 1.2)], np.float32)
+    objs = []
+    for o in range(8):
+        near = pts[o // 4, rng.integers(0, 1500, 56)] + rng.normal(0, 0.03, (56, 3)).astype(np.float32)
+        objs.append(np.concatenate([corners + rng.normal(0, 0.01, (8, 3)).astype(np.float32), near]))
+    objs = np.stack(objs).astype(np.float32)
+    frame = np.repeat(np.arange(2), 4).astype(np.int32)
+    want_keep, want_merged = _want(pts, objs, frame, None, 0.1)
+    assert 0.1 < want_keep.mean() < 0.9
+    keep, merged, m_cnt, _ = splice_frames(dev(pts, cuda), dev(objs, cuda), dev(frame, cuda), None, 0.1, merged=True)
+    np.testing.assert_array_equal(keep.cpu().numpy().astype(bool), want_keep)
+    for f in range(2):
+        np.testing.assert_array_equal(merged[f, : int(m_cnt[f])].cpu().numpy(), want_merged[f])
+
+
 def test_replace_with_completed_pts_reference_entry(cuda):
     rng = np.random.default_rng(8)
     pts = rng.uniform(-10, 10, (5000, 3)).astype(np.float32)
