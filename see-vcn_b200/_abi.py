@@ -120,8 +120,47 @@ def ptr(t):
     return None if t is None else c_void_p(t.data_ptr())
 
 
+_raw_stream = getattr(torch._C, "_cuda_getCurrentRawStream", None)
+
+
 def stream():
+    """The current torch stream of the current device as a raw ``cudaStream_t``."""
+    if _raw_stream is not None:      # no Stream object per call: this sits on every launch path
+        return c_void_p(_raw_stream(torch.cuda.current_device()))
     return c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+class _NoGuard:
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        return False
+
+
+_NO_GUARD = _NoGuard()
+
+
+def device_guard(dev):
+    """``torch.cuda.device(dev)`` only when ``dev`` is not already current (the guard costs ~10 us per wrapper call)."""
+    idx = dev.index if dev.index is not None else torch.cuda.current_device()
+    return _NO_GUARD if idx == torch.cuda.current_device() else torch.cuda.device(idx)
+
+
+_workspaces = {}
+
+
+def workspace(dev, nbytes, tag):
+    """Grow-only scratch buffer per (device, current stream, tag).  Kernels of successive calls on one stream are
+    ordered, so a stage's scratch can be reused by its next call instead of going through the allocator."""
+    idx = dev.index if dev.index is not None else torch.cuda.current_device()
+    sid = _raw_stream(idx) if _raw_stream is not None else torch.cuda.current_stream(idx).cuda_stream
+    key = (idx, sid, tag)
+    buf = _workspaces.get(key)
+    if buf is None or buf.numel() < nbytes:
+        buf = torch.empty(max(int(nbytes), 16), dtype=torch.uint8, device=torch.device("cuda", idx))
+        _workspaces[key] = buf
+    return buf
 
 
 def farray(vals):

@@ -44,7 +44,7 @@ class VoxelGeneratorWrapper():
         coords = torch.empty((MV, 3), dtype=torch.int32, device=dev)
         num_pts = torch.empty((MV,), dtype=torch.int32, device=dev)
         num = torch.zeros((1,), dtype=torch.int32, device=dev)
-        with torch.cuda.device(dev):
+        with _abi.device_guard(dev):
             _abi.check(L.seevcn_hard_voxelize(N, C, _abi.ptr(points), _abi.farray(self.coors_range_xyz),
                                               _abi.farray(self.vsize_xyz), _abi.iarray(self.grid_size), T, MV,
                                               _abi.ptr(voxels), _abi.ptr(coords), _abi.ptr(num_pts), _abi.ptr(num),

@@ -29,7 +29,7 @@ def dynamic_voxelize(points, point_cloud_range, voxel_size, grid_size, max_voxel
     feats = torch.empty((max_voxels, C), dtype=torch.float32, device=dev)
     counts = torch.empty((max_voxels,), dtype=torch.int32, device=dev)
     num = torch.zeros((1,), dtype=torch.int32, device=dev)
-    with torch.cuda.device(dev):
+    with _abi.device_guard(dev):
         _abi.check(L.seevcn_dynamic_voxelize(N, C, _abi.ptr(points), _abi.farray(point_cloud_range),
                                              _abi.farray(voxel_size), _abi.iarray(grid_size), max_voxels,
                                              1 if sort else 0, int(batch_size), _abi.ptr(coords), _abi.ptr(feats), _abi.ptr(counts),
@@ -69,12 +69,12 @@ def dynamic_voxelize_frames(frame_pts, obj_pts, obj_frame, point_cloud_range, vo
     N = F * P + O * S
     L = _abi.lib()
     cap = max(N, 1)
-    ws = torch.empty(L.seevcn_dynamic_voxelize_workspace_bytes(N, 3, cap), dtype=torch.uint8, device=dev)
+    ws = _abi.workspace(dev, L.seevcn_dynamic_voxelize_workspace_bytes(N, 3, cap), "dynvox")
     coords = torch.empty((cap, 4), dtype=torch.int32, device=dev)
     feats = torch.empty((cap, 3), dtype=torch.float32, device=dev)
     counts = torch.empty((cap,), dtype=torch.int32, device=dev)
     num = torch.empty((1,), dtype=torch.int32, device=dev)
-    with torch.cuda.device(dev):
+    with _abi.device_guard(dev):
         _abi.check(L.seevcn_dynamic_voxelize_spliced(F, P, _abi.ptr(frame_pts), _abi.ptr(frame_keep), O, S, _abi.ptr(obj_pts),
                                                      _abi.ptr(obj_frame), _abi.ptr(obj_count),
                                                      _abi.farray(point_cloud_range), _abi.farray(voxel_size),

@@ -23,7 +23,7 @@ class MeanVFE(VFETemplate):
         assert voxels.dtype == torch.float32
         M, T, C = voxels.shape
         out = torch.empty((M, C), dtype=torch.float32, device=voxels.device)
-        with torch.cuda.device(voxels.device):
+        with _abi.device_guard(voxels.device):
             _abi.check(_abi.lib().seevcn_mean_vfe(M, T, C, _abi.ptr(voxels), _abi.ptr(num), _abi.ptr(out), _abi.stream()))
         batch_dict['voxel_features'] = out
         return batch_dict

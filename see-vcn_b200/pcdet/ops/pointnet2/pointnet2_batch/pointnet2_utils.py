@@ -16,7 +16,7 @@ def furthest_point_sample(xyz: torch.Tensor, npoint: int) -> torch.Tensor:
     B, N, _ = xyz.size()
     output = torch.empty((B, npoint), dtype=torch.int32, device=xyz.device)
     temp = torch.empty((B, N), dtype=torch.float32, device=xyz.device)
-    with torch.cuda.device(xyz.device):
+    with _abi.device_guard(xyz.device):
         _abi.check(_abi.lib().seevcn_furthest_point_sampling(B, N, npoint, _abi.ptr(xyz), _abi.ptr(temp),
                                                              _abi.ptr(output), _abi.stream()))
     return output
@@ -34,7 +34,7 @@ def gather_operation(features: torch.Tensor, idx: torch.Tensor) -> torch.Tensor:
     B, npoint = idx.size()
     _, C, N = features.size()
     output = torch.empty((B, C, npoint), dtype=torch.float32, device=features.device)
-    with torch.cuda.device(features.device):
+    with _abi.device_guard(features.device):
         _abi.check(_abi.lib().seevcn_gather_points(B, C, N, npoint, _abi.ptr(features), _abi.ptr(idx),
                                                    _abi.ptr(output), _abi.stream()))
     return output
@@ -50,7 +50,7 @@ def grouping_operation(features: torch.Tensor, idx: torch.Tensor) -> torch.Tenso
     B, nfeatures, nsample = idx.size()
     _, C, N = features.size()
     output = torch.empty((B, C, nfeatures, nsample), dtype=torch.float32, device=features.device)
-    with torch.cuda.device(features.device):
+    with _abi.device_guard(features.device):
         _abi.check(_abi.lib().seevcn_group_points(B, C, N, nfeatures, nsample, _abi.ptr(features), _abi.ptr(idx),
                                                   _abi.ptr(output), _abi.stream()))
     return output
@@ -68,7 +68,7 @@ def knn(k: int, ref: torch.Tensor, query: torch.Tensor):
     Q = query.shape[1]
     dist = torch.empty((B, Q, k), dtype=torch.float32, device=ref.device)
     idx = torch.empty((B, Q, k), dtype=torch.int32, device=ref.device)
-    with torch.cuda.device(ref.device):
+    with _abi.device_guard(ref.device):
         _abi.check(_abi.lib().seevcn_knn(B, R, Q, k, _abi.ptr(ref), _abi.ptr(query), _abi.ptr(dist), _abi.ptr(idx),
                                          _abi.stream()))
     return dist, idx

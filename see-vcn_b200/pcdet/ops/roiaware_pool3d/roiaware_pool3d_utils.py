@@ -23,7 +23,7 @@ def points_in_boxes_gpu(points, boxes):
     _abi.require_cuda(points, boxes)
     assert points.dtype == torch.float32 and boxes.dtype == torch.float32
     box_idxs_of_pts = torch.empty((batch_size, num_points), dtype=torch.int32, device=points.device)
-    with torch.cuda.device(points.device):
+    with _abi.device_guard(points.device):
         _abi.check(_abi.lib().seevcn_points_in_boxes(batch_size, boxes.shape[1], num_points, _abi.ptr(boxes),
                                                      _abi.ptr(points), _abi.ptr(box_idxs_of_pts), _abi.stream()))
     return box_idxs_of_pts
@@ -80,8 +80,8 @@ def crop_points_in_boxes(points, boxes):
     offsets = torch.empty((B, T), dtype=torch.int32, device=dev)
     box_points = torch.empty((B, M), dtype=torch.int32, device=dev)
     ws_bytes = L.seevcn_crop_workspace_bytes(B, T, M)
-    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
-    with torch.cuda.device(dev):
+    ws = _abi.workspace(dev, ws_bytes, "crop")
+    with _abi.device_guard(dev):
         _abi.check(L.seevcn_crop_points_in_boxes(B, T, M, _abi.ptr(boxes), _abi.ptr(points), _abi.ptr(idx),
                                                  _abi.ptr(counts), _abi.ptr(offsets), _abi.ptr(box_points),
                                                  _abi.ptr(ws), ws_bytes, _abi.stream()))
@@ -98,7 +98,7 @@ def resample_gather(points, box_counts, box_offsets, box_points, obj_frame, obj_
     B, M, _ = points.shape
     T = box_counts.shape[1]
     out = torch.empty((O, n, 3), dtype=torch.float32, device=points.device)
-    with torch.cuda.device(points.device):
+    with _abi.device_guard(points.device):
         _abi.check(_abi.lib().seevcn_resample_gather(O, n, T, M, _abi.ptr(points), _abi.ptr(box_counts),
                                                      _abi.ptr(box_offsets), _abi.ptr(box_points), _abi.ptr(obj_frame),
                                                      _abi.ptr(obj_box), _abi.ptr(choice), _abi.ptr(out), _abi.stream()))
@@ -114,7 +114,7 @@ def resample_gather_rng(points, box_counts, box_offsets, box_points, obj_frame, 
     B, M, _ = points.shape
     T = box_counts.shape[1]
     out = torch.empty((O, n_points, 3), dtype=torch.float32, device=points.device)
-    with torch.cuda.device(points.device):
+    with _abi.device_guard(points.device):
         _abi.check(_abi.lib().seevcn_resample_gather_rng(O, n_points, T, M, int(seed) & 0xffffffff, _abi.ptr(points),
                                                          _abi.ptr(box_counts), _abi.ptr(box_offsets), _abi.ptr(box_points),
                                                          _abi.ptr(obj_frame), _abi.ptr(obj_box), _abi.ptr(out), _abi.stream()))

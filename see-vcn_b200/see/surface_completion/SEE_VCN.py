@@ -38,7 +38,7 @@ def splice_frames(frame_pts, obj_pts, obj_frame, obj_count=None, point_dist_thre
         O = S = 0
     L = _abi.lib()
     keep = torch.empty((F, P), dtype=torch.uint8, device=dev)
-    ws = torch.empty(max(L.seevcn_splice_workspace_bytes(F, P, O), 16), dtype=torch.uint8, device=dev)
+    ws = _abi.workspace(dev, L.seevcn_splice_workspace_bytes(F, P, O), "splice")
     out = m_cnt = c_cnt = None
     stride = 0
     if merged:
@@ -47,7 +47,7 @@ def splice_frames(frame_pts, obj_pts, obj_frame, obj_count=None, point_dist_thre
         out = torch.empty((F, stride, 3), dtype=torch.float32, device=dev)
         m_cnt = torch.empty((F,), dtype=torch.int32, device=dev)
         c_cnt = torch.empty((F,), dtype=torch.int32, device=dev)
-    with torch.cuda.device(dev):
+    with _abi.device_guard(dev):
         _abi.check(L.seevcn_splice(F, P, _abi.ptr(frame_pts), O, S, _abi.ptr(obj_pts), _abi.ptr(obj_count), _abi.ptr(obj_frame),
                                    float(point_dist_thresh), _abi.ptr(keep), stride, _abi.ptr(out), _abi.ptr(m_cnt),
                                    _abi.ptr(c_cnt), _abi.ptr(ws), ws.numel(), _abi.stream()))

@@ -66,10 +66,19 @@ class VCNBase(nn.Module):
         self._handle = None
         self._handle_key = None
         self._ws = None
+        self._plist = None
 
     # -- packing ---------------------------------------------------------------------
     def _param_key(self):
-        return tuple((p.data_ptr(), p._version) for p in list(self.parameters()) + list(self.buffers()))
+        # (storage address, in-place version) of every parameter/buffer: changes on load_state_dict, .to(), training
+        # steps.  The tensor list itself is cached (walking the module tree costs ~0.3 ms per forward); _apply resets it.
+        if self._plist is None:
+            self._plist = list(self.parameters()) + list(self.buffers())
+        return tuple((p.data_ptr(), p._version) for p in self._plist)
+
+    def _apply(self, fn, *args, **kwargs):
+        self._plist = None
+        return super()._apply(fn, *args, **kwargs)
 
     def _folded(self):
         raise NotImplementedError
@@ -115,7 +124,7 @@ class VCNBase(nn.Module):
         _abi.require_cuda(pts)
         B, N, _ = pts.shape
         dev = pts.device
-        with torch.cuda.device(dev):
+        with _abi.device_guard(dev):
             handle = self._pack()
             L = _abi.lib()
             ws_bytes = L.seevcn_vcn_workspace_bytes(handle, B, N)

@@ -21,8 +21,8 @@ def get_partial_mesh_batch(batch_partial, batch_complete, k=20, surface_pts=1024
     out = torch.empty((B, surface_pts, 3), dtype=torch.float32, device=batch_partial.device)
     cnt = torch.empty((B,), dtype=torch.int32, device=batch_partial.device)
     L = _abi.lib()
-    ws = torch.empty(L.seevcn_knn_surface_select_workspace_bytes(B, Np, R), dtype=torch.uint8, device=batch_partial.device)
-    with torch.cuda.device(batch_partial.device):
+    ws = _abi.workspace(batch_partial.device, L.seevcn_knn_surface_select_workspace_bytes(B, Np, R), "knn_select")
+    with _abi.device_guard(batch_partial.device):
         _abi.check(L.seevcn_knn_surface_select(B, Np, R, k, surface_pts, _abi.ptr(batch_partial),
                                                _abi.ptr(batch_complete), _abi.ptr(out), _abi.ptr(cnt),
                                                _abi.ptr(ws), ws.numel(), _abi.stream()))
@@ -42,7 +42,7 @@ def get_largest_cluster_batch(pc, eps=0.4, min_points=1, total_pts=1024, return_
     B, N, _ = pc.shape
     out = torch.empty((B, total_pts, 3), dtype=torch.float32, device=pc.device)
     cnt = torch.empty((B,), dtype=torch.int32, device=pc.device)
-    with torch.cuda.device(pc.device):
+    with _abi.device_guard(pc.device):
         if period is None:
             _abi.check(_abi.lib().seevcn_largest_cluster(B, N, total_pts, float(eps), int(min_points), _abi.ptr(pc),
                                                          _abi.ptr(out), _abi.ptr(cnt), _abi.stream()))
