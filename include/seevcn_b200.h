@@ -99,6 +99,13 @@ int seevcn_resample_gather(int num_obj, int n_points, int boxes_num, int pts_num
                            const int* box_points, const int* obj_frame, const int* obj_box,
                            const int* choice, float* out, seevcn_stream_t stream);
 
+/* ref: SEE_VCN.isolate_gt_pts keeps the boxes with at least MIN_LIDAR_PTS points (see/surface_completion/SEE_VCN.py:71).
+ * box_counts (batch, boxes_num) int32 -> the (frame, box) pairs with count >= min_pts in frame-major order (the order of
+ * numpy.argwhere on the host copy of the counts): obj_frame / obj_box (capacity batch*boxes_num) int32, num_obj (1) int32.
+ * Lets the host, which only needs the NUMBER of objects to size the launches, skip uploading the list. */
+int seevcn_select_objects(int batch, int boxes_num, const int* box_counts, int min_pts,
+                          int* obj_frame, int* obj_box, int* num_obj, seevcn_stream_t stream);
+
 /* Same draw made on the device: choice[o,j] = perm_o(j), the first n_points entries of a pseudo-random
  * permutation of the tiled list (4-round Feistel network + cycle walking, keyed by seed and the object's
  * frame*T+box), so no host RNG, no `choice` upload.  seevcn_resample_perm() evaluates the same permutation
@@ -326,6 +333,15 @@ int seevcn_hard_voxelize(int num_points, int num_features, const float* points,
                          float* voxels, int* coordinates, int* num_points_per_voxel,
                          int* num_voxels, void* workspace, size_t workspace_bytes,
                          seevcn_stream_t stream);
+
+/* Copies `bytes` (multiple of 4) from device memory into PINNED host memory (cudaHostAlloc / torch pin_memory: mapped
+ * into the device address space) with SM stores on `stream` — for the few words the host needs while the GPU keeps
+ * running (box counts, number of voxels); unlike cudaMemcpyAsync it does not queue behind bulk downloads on the copy
+ * engine.  Visible to the host once an event recorded after it on `stream` has completed. */
+int seevcn_copy_to_pinned(const void* src_device, void* dst_pinned_host, size_t bytes, seevcn_stream_t stream);
+/* The reverse: a few words (e.g. the object list the host derived from the box counts) from PINNED host memory into
+ * device memory with SM loads; the pinned buffer must stay untouched until an event recorded after it has completed. */
+int seevcn_copy_from_pinned(const void* src_pinned_host, void* dst_device, size_t bytes, seevcn_stream_t stream);
 
 /* ------------------------------------------------------------------ parity metric ---- */
 

@@ -40,6 +40,7 @@ SIGNATURES = {
     "seevcn_points_in_boxes_dense_trig": (I, [I, I, P, P, P, P, P]),
     "seevcn_crop_workspace_bytes": (c_size_t, [I, I, I]),
     "seevcn_crop_points_in_boxes": (I, [I, I, I, P, P, P, P, P, P, P, c_size_t, P]),
+    "seevcn_select_objects": (I, [I, I, P, I, P, P, P, P]),
     "seevcn_resample_gather": (I, [I, I, I, I, P, P, P, P, P, P, P, P, P]),
     "seevcn_resample_gather_rng": (I, [I, I, I, I, ctypes.c_uint, P, P, P, P, P, P, P, P]),
     "seevcn_resample_perm": (ctypes.c_uint, [ctypes.c_uint] * 4),
@@ -72,6 +73,8 @@ SIGNATURES = {
     "seevcn_hard_voxelize": (I, [I, I, P, POINTER(ctypes.c_float), POINTER(ctypes.c_float), POINTER(c_int),
                                  I, I, P, P, P, P, P, c_size_t, P]),
     "seevcn_chamfer": (I, [I, I, I, P, P, P, P, P]),
+    "seevcn_copy_to_pinned": (I, [P, P, c_size_t, P]),
+    "seevcn_copy_from_pinned": (I, [P, P, c_size_t, P]),
 }
 
 

@@ -98,3 +98,42 @@ extern "C" int seevcn_prof_report(char* buf, size_t cap) {
     }
     return SEEVCN_OK;
 }
+
+// ---- small results to the host without the copy engines ----
+// The pipeline needs two tiny device results on the host while the GPU keeps running (box counts: how many objects to
+// launch for; number of voxels).  A cudaMemcpyAsync for them queues behind the multi-megabyte result downloads on the
+// same DMA engine; SM stores into pinned (UVA-mapped) host memory on the compute stream do not.
+namespace {
+__global__ void copy_words_to_host_kernel(  /* either side may be pinned host memory */
+   const unsigned* __restrict__ src, unsigned* __restrict__ dst, size_t n) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) dst[i] = src[i];
+    __threadfence_system();
+}
+}  // namespace
+
+extern "C" int seevcn_copy_to_pinned(const void* src_device, void* dst_pinned_host, size_t bytes, seevcn_stream_t stream) {
+    if (bytes == 0) return SEEVCN_OK;
+    SEEVCN_REQUIRE(src_device && dst_pinned_host, "copy_to_pinned: null pointer");
+    SEEVCN_REQUIRE(bytes % 4 == 0 && ((uintptr_t)src_device & 3) == 0 && ((uintptr_t)dst_pinned_host & 3) == 0,
+                   "copy_to_pinned: size and pointers must be multiples of 4 bytes");
+    const size_t n = bytes / 4;
+    copy_words_to_host_kernel<<<(unsigned)div_up(n, (size_t)256), 256, 0, as_stream(stream)>>>(
+        static_cast<const unsigned*>(src_device), static_cast<unsigned*>(dst_pinned_host), n);
+    SEEVCN_LAUNCH_CHECK();
+    return SEEVCN_OK;
+}
+
+// The other direction: a few words (object ids) from pinned host memory into device memory with SM loads, so the
+// upload does not queue behind the next batch's bulk H2D copy on the copy engine.
+extern "C" int seevcn_copy_from_pinned(const void* src_pinned_host, void* dst_device, size_t bytes, seevcn_stream_t stream) {
+    if (bytes == 0) return SEEVCN_OK;
+    SEEVCN_REQUIRE(src_pinned_host && dst_device, "copy_from_pinned: null pointer");
+    SEEVCN_REQUIRE(bytes % 4 == 0 && ((uintptr_t)src_pinned_host & 3) == 0 && ((uintptr_t)dst_device & 3) == 0,
+                   "copy_from_pinned: size and pointers must be multiples of 4 bytes");
+    const size_t n = bytes / 4;
+    copy_words_to_host_kernel<<<(unsigned)div_up(n, (size_t)256), 256, 0, as_stream(stream)>>>(
+        static_cast<const unsigned*>(src_pinned_host), static_cast<unsigned*>(dst_device), n);
+    SEEVCN_LAUNCH_CHECK();
+    return SEEVCN_OK;
+}

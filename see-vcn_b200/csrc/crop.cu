@@ -472,6 +472,56 @@ extern "C" int seevcn_crop_points_in_boxes(int batch_size, int boxes_num, int pt
     return SEEVCN_OK;
 }
 
+namespace {
+// single CTA: ordered compaction of the (frame, box) pairs with enough points
+__global__ void __launch_bounds__(1024)
+select_objects_kernel(int n, int boxes_num, const int* __restrict__ counts, int min_pts, int* __restrict__ obj_frame,
+                      int* __restrict__ obj_box, int* __restrict__ num_obj) {
+    __shared__ int s_warp[33];
+    __shared__ int s_base;
+    if (threadIdx.x == 0) s_base = 0;
+    __syncthreads();
+    for (int i0 = 0; i0 < n; i0 += 1024) {
+        const int i = i0 + threadIdx.x;
+        const bool ok = i < n && counts[i] >= min_pts;
+        const unsigned m = __ballot_sync(0xffffffffu, ok);
+        if (lane_id() == 0) s_warp[warp_id()] = __popc(m);
+        __syncthreads();
+        if (threadIdx.x < 32) {
+            const int c = s_warp[threadIdx.x];
+            int inc = c;
+#pragma unroll
+            for (int off = 1; off < 32; off <<= 1) { const int t = __shfl_up_sync(0xffffffffu, inc, off); if ((int)threadIdx.x >= off) inc += t; }
+            s_warp[threadIdx.x] = inc - c;
+            if (threadIdx.x == 31) s_warp[32] = inc;
+        }
+        __syncthreads();
+        if (ok) {
+            const int o = s_base + s_warp[warp_id()] + __popc(m & ((1u << lane_id()) - 1));
+            obj_frame[o] = i / boxes_num;
+            obj_box[o] = i % boxes_num;
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) s_base += s_warp[32];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) *num_obj = s_base;
+}
+}  // namespace
+
+extern "C" int seevcn_select_objects(int batch, int boxes_num, const int* box_counts, int min_pts, int* obj_frame,
+                                     int* obj_box, int* num_obj, seevcn_stream_t stream) {
+    SEEVCN_REQUIRE(batch >= 0 && boxes_num >= 0, "select_objects: negative size");
+    SEEVCN_REQUIRE((long long)batch * boxes_num < (1ll << 31), "select_objects: too many boxes");
+    SEEVCN_REQUIRE(num_obj, "select_objects: null pointer");
+    const int n = batch * boxes_num;
+    SEEVCN_REQUIRE(n == 0 || (box_counts && obj_frame && obj_box), "select_objects: null pointer");
+    select_objects_kernel<<<1, 1024, 0, as_stream(stream)>>>(n, boxes_num > 0 ? boxes_num : 1, box_counts, min_pts, obj_frame,
+                                                             obj_box, num_obj);
+    SEEVCN_LAUNCH_CHECK();
+    return SEEVCN_OK;
+}
+
 extern "C" int seevcn_resample_gather(int num_obj, int n_points, int boxes_num, int pts_num, const float* pts,
                                       const int* box_counts, const int* box_offsets, const int* box_points,
                                       const int* obj_frame, const int* obj_box, const int* choice, float* out,

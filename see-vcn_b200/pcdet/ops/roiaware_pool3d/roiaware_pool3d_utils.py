@@ -88,6 +88,21 @@ def crop_points_in_boxes(points, boxes):
     return idx, counts, offsets, box_points
 
 
+def select_objects(box_counts, min_pts):
+    """(frame, box) pairs with at least ``min_pts`` cropped points, frame-major like ``np.argwhere(counts >= min_pts)``
+    (SEE_VCN.py:71) -> obj_frame, obj_box (B*T,) int32 CUDA (first num entries valid), num (1,) int32 CUDA."""
+    _abi.require_cuda(box_counts)
+    B, T = box_counts.shape
+    dev = box_counts.device
+    obj_frame = torch.empty((B * T,), dtype=torch.int32, device=dev)
+    obj_box = torch.empty((B * T,), dtype=torch.int32, device=dev)
+    num = torch.empty((1,), dtype=torch.int32, device=dev)
+    with _abi.device_guard(dev):
+        _abi.check(_abi.lib().seevcn_select_objects(B, T, _abi.ptr(box_counts), int(min_pts), _abi.ptr(obj_frame),
+                                                    _abi.ptr(obj_box), _abi.ptr(num), _abi.stream()))
+    return obj_frame, obj_box, num
+
+
 def resample_gather(points, box_counts, box_offsets, box_points, obj_frame, obj_box, choice):
     """ResamplePoints on the device (data_transforms.py:247-262) with a host-supplied permutation.
 

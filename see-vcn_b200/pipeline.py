@@ -26,7 +26,7 @@ def resample_choice(count, n_points, rng):
 
 class _Crop:
     """An issued crop: device outputs + the box counts on their way to pinned host memory."""
-    __slots__ = ("points", "boxes", "idx", "counts", "offsets", "lists", "h_counts", "done")
+    __slots__ = ("points", "boxes", "idx", "counts", "offsets", "lists", "h_counts", "done", "obj_frame", "obj_box")
 
 
 class CompletionPipeline:
@@ -45,27 +45,39 @@ class CompletionPipeline:
         self.voxel_cfg = voxel_cfg
         self.host_rng = host_rng              # True: numpy permutation per object on the host (reference's draw)
         self.cluster_eps = cluster_eps        # SURFACE_COMPLETION.VCN.CLUSTER_EPS; None skips the largest-cluster filter
+        self._pinned_in_flight = []
         self.splice_thresh = splice_thresh    # replace_with_completed_pts point_dist_thresh (SEE_VCN.py:247); None = no splice
-        self._side = None                     # stream of the small D2H copies (box counts, number of voxels)
-
-    def _side_stream(self):
-        if self._side is None:
-            self._side = torch.cuda.Stream(self.device)
-        return self._side
 
     def _to_host_async(self, t):
-        """Device tensor -> pinned host copy on the side stream, ordered after the work queued so far on the
-        current stream.  Returns (pinned tensor, event)."""
-        compute = torch.cuda.current_stream(self.device)
-        ev = torch.cuda.Event(); ev.record(compute)
+        """Small device tensor (4-byte elements) -> pinned host copy, written by a copy kernel on the current stream
+        (``seevcn_copy_to_pinned``: SM stores, so it never waits behind the bulk result downloads on the copy engine;
+        measured: a side stream for it is worse — the tiny kernel then waits for room next to the persistent kernels).
+        Returns (pinned tensor, event)."""
+        from . import _abi
+        t = t.contiguous()
         host = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
-        side = self._side_stream()
-        done = torch.cuda.Event()
-        with torch.cuda.stream(side):
-            side.wait_event(ev)
-            host.copy_(t, non_blocking=True)
-            done.record(side)
+        with _abi.device_guard(self.device):
+            _abi.check(_abi.lib().seevcn_copy_to_pinned(_abi.ptr(t), _abi.c_void_p(host.data_ptr()),
+                                                        t.numel() * t.element_size(), _abi.stream()))
+            done = torch.cuda.Event()
+            done.record()
         return host, done
+
+    def _to_device_small(self, arr):
+        """Small host int32 array -> device tensor through pinned memory and a copy kernel on the current stream
+        (``seevcn_copy_from_pinned``): a cudaMemcpyAsync would queue behind the next batch's bulk upload."""
+        from . import _abi
+        host = torch.from_numpy(np.ascontiguousarray(arr, dtype=np.int32)).pin_memory()
+        out = torch.empty(host.shape, dtype=torch.int32, device=self.device)
+        with _abi.device_guard(self.device):
+            _abi.check(_abi.lib().seevcn_copy_from_pinned(_abi.c_void_p(host.data_ptr()), _abi.ptr(out), host.numel() * 4,
+                                                          _abi.stream()))
+            ev = torch.cuda.Event()
+            ev.record()
+        self._pinned_in_flight.append((host, ev))      # keep the pinned source alive until the kernel has read it
+        while len(self._pinned_in_flight) > 8 or (self._pinned_in_flight and self._pinned_in_flight[0][1].query()):
+            self._pinned_in_flight.pop(0)[1].synchronize()
+        return out
 
     # ---- stage A: crop.  Its box counts decide how many objects stage B launches for, so they travel to the host;
     # issuing the NEXT batch's crop before this batch's stage B (run_stream) takes that wait off the critical path.
@@ -74,7 +86,8 @@ class CompletionPipeline:
         h = _Crop()
         h.points, h.boxes = points, boxes
         h.idx, h.counts, h.offsets, h.lists = roi.crop_points_in_boxes(points, boxes)
-        h.h_counts, h.done = self._to_host_async(h.counts)
+        h.obj_frame, h.obj_box, _ = roi.select_objects(h.counts, self.min_lidar_pts)   # the list stays on the device
+        h.h_counts, h.done = self._to_host_async(h.counts)                             # the host only needs its length
         return h
 
     @torch.no_grad()
@@ -100,14 +113,12 @@ class CompletionPipeline:
             # the reference's own draw (numpy permutation on the host), for bit-for-bit comparisons
             rng = np.random.default_rng(seed)
             choice = np.stack([resample_choice(int(cnt[f, k]), self.resample_num, rng) for f, k in keep])
-            hp = torch.from_numpy(np.concatenate([keep.astype(np.int32).T.reshape(-1), choice.reshape(-1)])).pin_memory()
-            d = hp.to(points.device, non_blocking=True)
-            obj_frame, obj_box, d_choice = d[:O], d[O:2 * O], d[2 * O:].view(O, self.resample_num)
+            d_choice = self._to_device_small(choice.reshape(-1)).view(O, self.resample_num)
+            obj_frame, obj_box = h.obj_frame[:O], h.obj_box[:O]
             inp = roi.resample_gather(points, counts, offsets, lists, obj_frame.contiguous(), obj_box.contiguous(),
                                       d_choice.contiguous())
         else:
-            d = torch.from_numpy(np.ascontiguousarray(keep.astype(np.int32).T)).pin_memory().to(points.device, non_blocking=True)
-            obj_frame, obj_box = d[0], d[1]
+            obj_frame, obj_box = h.obj_frame[:O], h.obj_box[:O]    # same order as np.argwhere (seevcn_select_objects)
             inp = roi.resample_gather_rng(points, counts, offsets, lists, obj_frame, obj_box, self.resample_num, seed)
         in_dict = {"input": inp}
         if self.model_name == "VCN_CN":

@@ -542,3 +542,16 @@ def test_chamfer_kernel(cuda):
     _abi.check(_abi.lib().seevcn_chamfer(2, 700, 1300, _abi.ptr(da), _abi.ptr(db), _abi.ptr(d1), _abi.ptr(d2), _abi.stream()))
     got = (d1.mean(1) + d2.mean(1)).cpu().numpy()
     np.testing.assert_allclose(got, oracle.chamfer_l2(a, b), rtol=1e-4)
+
+
+def test_select_objects_matches_argwhere(cuda):
+    """seevcn_select_objects = np.argwhere(counts >= MIN_LIDAR_PTS) in frame-major order (SEE_VCN.py:71)."""
+    rng = np.random.default_rng(17)
+    for B, T in ((1, 1), (3, 50), (8, 300), (2, 0)):
+        counts = rng.integers(0, 60, (B, T)).astype(np.int32)
+        of, ob, num = roi.select_objects(dev(counts, cuda), 30)
+        want = np.argwhere(counts >= 30)
+        n = int(num.item())
+        assert n == len(want)
+        np.testing.assert_array_equal(of[:n].cpu().numpy(), want[:, 0])
+        np.testing.assert_array_equal(ob[:n].cpu().numpy(), want[:, 1])
