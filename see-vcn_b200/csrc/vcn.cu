@@ -319,7 +319,10 @@ int fill(float* p, size_t n, float v, cudaStream_t st) {
 
 // ----------------------------------------------------------------- workspace layout --
 constexpr int kChunkObjF32 = 16;   // objects per pass of the fp32 path (activations 2 x 32 MB at N=1024)
-constexpr int kChunkObjTC = 128;   // bf16 path: 128 x 1024 x 256 x 2 B = 64 MB of enc1 output per pass (L2-sized)
+constexpr int kChunkObjTC = 512;   // bf16 path: objects per pass (enc1 -> global FC -> enc2).  One pass for a typical batch: the
+                                   // persistent chain kernels get long tile queues and the per-pass FC launches are not repeated;
+                                   // enc2 streams enc1's bf16 output (0.5 MB/object) from HBM under its MMAs either way (ncu:
+                                   // 128-object passes did not keep it in L2)
 
 struct VcnWs {
     size_t frames, poses, pts3, pose_feat, h512, rel, g256, objbias, feat, fc_a, fc_b, coarse_cn, act_a, act_b,
