@@ -215,21 +215,30 @@ __device__ __forceinline__ int warp_excl_scan(int v, int& total) {
     return inc - v;
 }
 
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(1024)
 crop_scan_kernel(int boxes_num, int ntiles, int* __restrict__ tile_counts,
                  int* __restrict__ box_counts, int* __restrict__ box_offsets) {
     extern __shared__ int s_tot[];   // boxes_num
     const int b = blockIdx.x;
+    const int nwarps = blockDim.x >> 5;
     int* tc = tile_counts + (size_t)b * ntiles * boxes_num;
-    for (int k = warp_id(); k < boxes_num; k += 8) {
+    for (int k = warp_id(); k < boxes_num; k += nwarps) {
         int run = 0;
-        for (int t0 = 0; t0 < ntiles; t0 += 32) {
-            const int t = t0 + lane_id();
-            const int c = t < ntiles ? tc[(size_t)t * boxes_num + k] : 0;
-            int tot;
-            const int ex = warp_excl_scan(c, tot);
-            if (t < ntiles) tc[(size_t)t * boxes_num + k] = run + ex;
-            run += tot;
+        for (int t0 = 0; t0 < ntiles; t0 += 256) {          // 8 independent loads in flight per lane, then the scans
+            int c[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const int t = t0 + u * 32 + lane_id();
+                c[u] = t < ntiles ? tc[(size_t)t * boxes_num + k] : 0;
+            }
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const int t = t0 + u * 32 + lane_id();
+                int tot;
+                const int ex = warp_excl_scan(c[u], tot);
+                if (t < ntiles) tc[(size_t)t * boxes_num + k] = run + ex;
+                run += tot;
+            }
         }
         if (lane_id() == 0) { s_tot[k] = run; box_counts[(size_t)b * boxes_num + k] = run; }
     }
@@ -463,7 +472,7 @@ extern "C" int seevcn_crop_points_in_boxes(int batch_size, int boxes_num, int pt
             boxes_num, pts_num, boxes, pts, box_idx_of_points, tile_counts);
     }
     SEEVCN_LAUNCH_CHECK();
-    crop_scan_kernel<<<batch_size, 256, boxes_num * sizeof(int), st>>>(boxes_num, ntiles, tile_counts,
+    crop_scan_kernel<<<batch_size, 1024, boxes_num * sizeof(int), st>>>(boxes_num, ntiles, tile_counts,
                                                                        box_counts, box_offsets);
     SEEVCN_LAUNCH_CHECK();
     crop_scatter_kernel<<<grid, kThreads, (kThreads / 32) * boxes_num * sizeof(int), st>>>(

@@ -46,21 +46,24 @@ class CompletionPipeline:
         self.host_rng = host_rng              # True: numpy permutation per object on the host (reference's draw)
         self.cluster_eps = cluster_eps        # SURFACE_COMPLETION.VCN.CLUSTER_EPS; None skips the largest-cluster filter
         self._pinned_in_flight = []
+        self._side = None                     # stream of the small D2H copies (box counts, number of voxels)
         self.splice_thresh = splice_thresh    # replace_with_completed_pts point_dist_thresh (SEE_VCN.py:247); None = no splice
 
     def _to_host_async(self, t):
-        """Small device tensor (4-byte elements) -> pinned host copy, written by a copy kernel on the current stream
-        (``seevcn_copy_to_pinned``: SM stores, so it never waits behind the bulk result downloads on the copy engine;
-        measured: a side stream for it is worse — the tiny kernel then waits for room next to the persistent kernels).
-        Returns (pinned tensor, event)."""
-        from . import _abi
-        t = t.contiguous()
+        """Small device tensor -> pinned host copy on a side stream, ordered after the work queued so far on the current
+        stream.  Returns (pinned tensor, event).  (A copy KERNEL writing into the pinned buffer — seevcn_copy_to_pinned —
+        was tried instead of the DMA copy: same speed on most boxes, but on some the SM-initiated PCIe writes stall for
+        milliseconds next to the bulk result downloads, so the copy engine it is.)"""
+        compute = torch.cuda.current_stream(self.device)
+        ev = torch.cuda.Event(); ev.record(compute)
         host = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
-        with _abi.device_guard(self.device):
-            _abi.check(_abi.lib().seevcn_copy_to_pinned(_abi.ptr(t), _abi.c_void_p(host.data_ptr()),
-                                                        t.numel() * t.element_size(), _abi.stream()))
-            done = torch.cuda.Event()
-            done.record()
+        if self._side is None:
+            self._side = torch.cuda.Stream(self.device)
+        done = torch.cuda.Event()
+        with torch.cuda.stream(self._side):
+            self._side.wait_event(ev)
+            host.copy_(t, non_blocking=True)
+            done.record(self._side)
         return host, done
 
     def _to_device_small(self, arr):
