@@ -378,8 +378,8 @@ def run_ours(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=30)
-    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--steps", type=int, default=200)    # ~0.3 s per timed leg: box-level jitter (PCIe, host) averages out
+    ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--frames", type=int, default=8, help="frames per step per GPU")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--precision", default=os.environ.get("SEEVCN_PRECISION", "bf16"), choices=["bf16", "fp32"])

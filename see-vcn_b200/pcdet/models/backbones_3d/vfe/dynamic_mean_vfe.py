@@ -39,13 +39,15 @@ def dynamic_voxelize(points, point_cloud_range, voxel_size, grid_size, max_voxel
 
 
 def dynamic_voxelize_frames(frame_pts, obj_pts, obj_frame, point_cloud_range, voxel_size, grid_size, sort=True,
-                            frame_keep=None, obj_count=None):
+                            frame_keep=None, obj_count=None, max_voxels=None):
     """The frame pipeline's form: frame_pts (F,P,3) rows carry batch index = frame, obj_pts (O,S,3) rows carry
     obj_frame[o]; same result as ``dynamic_voxelize`` on the concatenated [batch_idx,x,y,z] matrix, which is never
     built.  After the splice step (SEE_VCN.py:247-265): ``frame_keep`` (F,P) uint8 drops the replaced frame points and
     ``obj_count`` (O,) int32 limits every object to its distinct rows.  No host sync: returns FULL-capacity tensors
     plus the device scalar M — (coords (N,4), feats (N,3), counts (N,), num_voxels (1,) int32 CUDA); rows >= M are
-    undefined."""
+    undefined.  ``max_voxels``: row capacity of the outputs (default: one row per point, which can never overflow); with a
+    smaller capacity the sort / permute passes shrink with it, rows beyond it are dropped and ``num_voxels`` still
+    reports the true M, so the caller can detect the overflow and call again."""
     frame_pts = frame_pts.contiguous()
     _abi.require_cuda(frame_pts)
     F, P, _ = frame_pts.shape
@@ -68,7 +70,7 @@ def dynamic_voxelize_frames(frame_pts, obj_pts, obj_frame, point_cloud_range, vo
         assert frame_keep.dtype == torch.uint8 and frame_keep.numel() == F * P
     N = F * P + O * S
     L = _abi.lib()
-    cap = max(N, 1)
+    cap = max(N, 1) if max_voxels is None else max(min(int(max_voxels), N), 1)
     ws = _abi.workspace(dev, L.seevcn_dynamic_voxelize_workspace_bytes(N, 3, cap), "dynvox")
     coords = torch.empty((cap, 4), dtype=torch.int32, device=dev)
     feats = torch.empty((cap, 3), dtype=torch.float32, device=dev)

@@ -46,24 +46,22 @@ class CompletionPipeline:
         self.host_rng = host_rng              # True: numpy permutation per object on the host (reference's draw)
         self.cluster_eps = cluster_eps        # SURFACE_COMPLETION.VCN.CLUSTER_EPS; None skips the largest-cluster filter
         self._pinned_in_flight = []
-        self._side = None                     # stream of the small D2H copies (box counts, number of voxels)
+        self._vox_seen = 0                    # largest voxel count seen so far (sizes the voxel outputs of later batches)
         self.splice_thresh = splice_thresh    # replace_with_completed_pts point_dist_thresh (SEE_VCN.py:247); None = no splice
 
     def _to_host_async(self, t):
-        """Small device tensor -> pinned host copy on a side stream, ordered after the work queued so far on the current
-        stream.  Returns (pinned tensor, event).  (A copy KERNEL writing into the pinned buffer — seevcn_copy_to_pinned —
-        was tried instead of the DMA copy: same speed on most boxes, but on some the SM-initiated PCIe writes stall for
-        milliseconds next to the bulk result downloads, so the copy engine it is.)"""
-        compute = torch.cuda.current_stream(self.device)
-        ev = torch.cuda.Event(); ev.record(compute)
+        """Small device tensor (4-byte elements) -> pinned host copy, written by a copy kernel on the current stream
+        (``seevcn_copy_to_pinned``).  No copy-engine stream is involved: a DMA copy for these few bytes needs a stream
+        that waits on a compute event, and a copy-engine channel parked on such a wait was seen to hold up the bulk
+        transfers next to it for milliseconds (tools/diag_latency.py).  Returns (pinned tensor, event)."""
+        from . import _abi
+        t = t.contiguous()
         host = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
-        if self._side is None:
-            self._side = torch.cuda.Stream(self.device)
-        done = torch.cuda.Event()
-        with torch.cuda.stream(self._side):
-            self._side.wait_event(ev)
-            host.copy_(t, non_blocking=True)
-            done.record(self._side)
+        with _abi.device_guard(self.device):
+            _abi.check(_abi.lib().seevcn_copy_to_pinned(_abi.ptr(t), _abi.c_void_p(host.data_ptr()),
+                                                        t.numel() * t.element_size(), _abi.stream()))
+            done = torch.cuda.Event()
+            done.record()
         return host, done
 
     def _to_device_small(self, arr):
@@ -150,8 +148,15 @@ class CompletionPipeline:
             count = out.get("clustered_count", out.get("surface_count"))
             keep = splice_frames(points, completed, out["obj_frame_dev"], count, self.splice_thresh)
             out["frame_keep"], out["completed_count"] = keep, count
+        # Output capacity: the number of voxels M is only known after the fact; sizing the outputs (and the radix sort over
+        # them) for one voxel per point wastes 3/4 of those passes on a LiDAR frame.  Capacity = 2x the largest M seen
+        # so far (first call: every point); finalize() re-runs the rare batch that overflows with full capacity.
+        n_rows = F * P + completed.shape[0] * completed.shape[1]
+        cap = n_rows if self._vox_seen == 0 else min(n_rows, max(2 * self._vox_seen, 1 << 16))
+        vox_args = (points, completed, out.get("obj_frame_dev"), keep, count)
         coords, feats, nums, num_dev = dynamic_voxelize_frames(points, completed, out.get("obj_frame_dev"), *self.voxel_cfg,
-                                                              sort=True, frame_keep=keep, obj_count=count)
+                                                              sort=True, frame_keep=keep, obj_count=count, max_voxels=cap)
+        out["_vox_args"], out["_vox_cap"] = vox_args, cap
         out["num_voxel_points"] = F * P + completed.shape[0] * completed.shape[1]
         out["_frame_points"] = points
         out["_vox_full"] = (coords, feats, nums, num_dev)
@@ -165,7 +170,17 @@ class CompletionPipeline:
         if "_vox_full" in out:
             coords, feats, nums, _ = out.pop("_vox_full")
             out["_num_done"].synchronize()
-            m = min(int(out["_h_num"][0]), coords.shape[0])
+            m = int(out["_h_num"][0])
+            pts_, comp_, ofr_, keep_, cnt_ = out.pop("_vox_args")
+            if m > out["_vox_cap"]:     # more voxels than the capacity guessed from earlier batches: redo with room for all
+                with torch.cuda.device(self.device):
+                    coords, feats, nums, num_dev = dynamic_voxelize_frames(pts_, comp_, ofr_, *self.voxel_cfg, sort=True,
+                                                                          frame_keep=keep_, obj_count=cnt_)
+                    m = int(num_dev.item())
+                    out["_done"] = torch.cuda.Event()
+                    out["_done"].record(torch.cuda.current_stream(self.device))
+            self._vox_seen = max(self._vox_seen, m)
+            m = min(m, coords.shape[0])
             out.update(voxel_coords=coords[:m], voxel_features=feats[:m], voxel_num_points=nums[:m])
         return out
 
@@ -220,7 +235,7 @@ class HostStream:
 
     The reference's driver (``sc_multiproc.py:60-94``) reads a frame from disk, completes its objects and
     writes a .pcd; here a batch of frames arrives in pinned memory and the completed clouds + voxel tensors
-    leave in pinned memory.  Three CUDA streams: the H2D copy of batch i+2 and the D2H copy of batch i-1
+    leave in pinned memory.  Three CUDA streams: the H2D copy of batch i+2 and the D2H copy of batch i-2
     overlap the kernels of batch i (the copy engines are otherwise idle; every batch still pays its own
     copies inside the caller's timed region), and batch i+1's crop is queued ahead of batch i's completion
     stage so its box counts are on the host by the time they are needed.
@@ -231,8 +246,8 @@ class HostStream:
     """
     KEYS = ("clustered", "voxel_coords", "voxel_features", "voxel_num_points")
 
-    def __init__(self, pipe, frames, pts_per_frame, boxes_per_frame, depth=3):
-        assert depth >= 3
+    def __init__(self, pipe, frames, pts_per_frame, boxes_per_frame, depth=4):
+        assert depth >= 4   # a slot is overwritten two batches after its batch was finalized (finalize may re-voxelize from it)
         self.pipe, self.depth = pipe, depth
         dev = pipe.device
         self.dev = dev
@@ -246,13 +261,13 @@ class HostStream:
                       for _ in range(depth)]
         self.s_h2d, self.s_d2h = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
         self.ev_in = [torch.cuda.Event() for _ in range(depth)]       # H2D of the slot landed
-        self.ev_free = [torch.cuda.Event() for _ in range(depth)]     # kernels finished reading the slot's inputs
         self.ev_out = [torch.cuda.Event() for _ in range(depth)]      # D2H of the slot's results landed
         self.h2d_bytes = self.d2h_bytes = 0
 
     def _upload(self, slot, pts_pin, boxes_pin):
+        # No wait on the copy stream: the batch that used this slot was finalized (its kernels are known to have
+        # finished) before run() comes back here, see the schedule below.  Copy streams never wait on compute events.
         with torch.cuda.stream(self.s_h2d):
-            self.s_h2d.wait_event(self.ev_free[slot])
             self.d_pts[slot].copy_(pts_pin, non_blocking=True)
             self.d_boxes[slot].copy_(boxes_pin, non_blocking=True)
             self.ev_in[slot].record(self.s_h2d)
@@ -260,8 +275,8 @@ class HostStream:
 
     def _download(self, slot, out):
         views = {}
+        out["_done"].synchronize()       # already complete (finalize waited for the batch); keeps the copy stream wait-free
         with torch.cuda.stream(self.s_d2h):
-            self.s_d2h.wait_event(out["_done"])
             for k in self.KEYS:
                 src = out.get(k)
                 if src is None:
@@ -299,25 +314,31 @@ class HostStream:
             compute.wait_event(self.ev_in[i % D])
             return self.pipe.crop_async(self.d_pts[i % D], self.d_boxes[i % D])
 
-        for e in self.ev_free:
-            e.record(compute)
         upload_next(); upload_next()
         if state["up"] == 0:
             return
         h, i = crop(0), 0
-        prev = pending = None          # prev: stage B queued, M not read yet; pending: D2H issued, not yet on the host
+        # prev: stage B queued, M not read yet; fin: finalized (M known), download not issued yet; pending: D2H issued.
+        # The bulk download of a batch is issued one iteration AFTER its finalize: issued right away it would sit on the
+        # D2H copy engine in front of the few bytes of box counts the next stage B launch is waiting for.
+        prev = fin = pending = None
         while h is not None:
             upload_next()                                            # batch i+2: overlaps the kernels below
             h_next = crop(i + 1) if i + 1 < state["up"] else None    # ahead of batch i's stage B
             out = self.pipe.run_from(h, seed, defer=True)
-            self.ev_free[i % D].record(compute)
-            if prev is not None:
-                res = self._download(prev[0] % D, self.pipe.finalize(prev[1]))   # overlaps this batch's kernels
+            if fin is not None:
+                res = self._download(fin[0] % D, fin[1])             # overlaps this batch's kernels
                 if pending is not None:
                     yield self._collect(pending)
-                pending = (prev[0] % D, res)
+                pending, fin = (fin[0] % D, res), None
+            if prev is not None:
+                fin = (prev[0], self.pipe.finalize(prev[1]))
             prev, h, i = (i, out), h_next, i + 1
-        res = self._download(prev[0] % D, self.pipe.finalize(prev[1]))
-        if pending is not None:
-            yield self._collect(pending)
-        yield self._collect((prev[0] % D, res))
+        for item in (fin, (prev[0], self.pipe.finalize(prev[1]))):
+            if item is None:
+                continue
+            res = self._download(item[0] % D, item[1])
+            if pending is not None:
+                yield self._collect(pending)
+            pending = (item[0] % D, res)
+        yield self._collect(pending)

@@ -419,6 +419,25 @@ def test_vcn_fused_chains_vs_layerwise_and_oracle(cuda, name, nobj, n):
     assert np.abs(fused - layer).max() < 2e-2 * scale, (np.abs(fused - layer).max(), scale)
 
 
+def test_vcn_forward_beyond_one_pass(cuda):
+    """more objects than one internal pass holds (512): the passes are independent, so the result equals the forward of
+    the two halves, and the fp32 restatement on a sample of objects from both passes"""
+    part, _, _ = synth.make_object_clouds(93, 530, 1024, 0)
+    sd = oracle.make_state_dict("VCN_VC", seed=5)
+    model = MODELS.build({"NAME": "VCN_VC"}, precision="bf16")
+    model.load_state_dict(sd)
+    model.to(cuda).eval()
+    x = dev(part, cuda)
+    full = model({"input": x})["coarse"].cpu().numpy()
+    halves = np.concatenate([model({"input": x[:300].contiguous()})["coarse"].cpu().numpy(),
+                             model({"input": x[300:].contiguous()})["coarse"].cpu().numpy()])
+    assert np.isfinite(full).all()
+    assert (rel_chamfer(full, halves, part) < 1e-4).all()
+    sel = np.array([0, 1, 255, 511, 512, 513, 529])
+    want = oracle.vcn_forward_ref(sd, part[sel], None, "VCN_VC")["coarse"].numpy()
+    assert (rel_chamfer(full[sel], want, part[sel]) < 1e-3).all()
+
+
 # ------------------------------------------------------------------ stage 6: voxelization --
 WAYMO = ([-75.2, -75.2, -2, 75.2, 75.2, 4], [0.1, 0.1, 0.15], [1504, 1504, 40])
 

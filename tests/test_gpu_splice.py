@@ -193,3 +193,23 @@ def test_pipeline_with_splice_voxelizes_the_merged_frame(cuda):
     np.testing.assert_array_equal(out["voxel_coords"].cpu().numpy(), vc)
     np.testing.assert_array_equal(out["voxel_num_points"].cpu().numpy(), vn)
     np.testing.assert_allclose(out["voxel_features"].cpu().numpy(), vf, rtol=1e-5, atol=1e-5)
+
+
+def test_pipeline_voxel_capacity_overflow_is_redone(cuda):
+    """The voxel outputs are sized from the voxel counts of earlier batches; a batch with more voxels than that is
+    voxelized again with full capacity: same result as a pipeline that never guessed."""
+    from seevcn_b200.pipeline import CompletionPipeline
+    sd = oracle.make_state_dict("VCN_VC", seed=0)
+    pts, boxes = synth.make_stream(2, first_seed=1000)
+    d_pts, d_boxes = dev(pts, cuda), dev(boxes, cuda)
+    ref = CompletionPipeline("VCN_VC", sd, cuda, sel_k=10, cluster_eps=0.3, splice_thresh=0.1).run(d_pts, d_boxes, seed=0)
+    pipe = CompletionPipeline("VCN_VC", sd, cuda, sel_k=10, cluster_eps=0.3, splice_thresh=0.1)
+    pipe._vox_seen = 10                                    # as if every earlier batch had been almost empty
+    out = pipe.run(d_pts, d_boxes, seed=0)
+    assert out["_vox_cap"] == 1 << 16 < ref["voxel_coords"].shape[0]
+    for key in ("voxel_coords", "voxel_num_points"):
+        np.testing.assert_array_equal(out[key].cpu().numpy(), ref[key].cpu().numpy())
+    np.testing.assert_allclose(out["voxel_features"].cpu().numpy(), ref["voxel_features"].cpu().numpy(), rtol=1e-6, atol=1e-6)
+    again = pipe.run(d_pts, d_boxes, seed=0)               # now sized from what it has seen: no redo, same rows
+    assert again["_vox_cap"] == 2 * ref["voxel_coords"].shape[0]
+    np.testing.assert_array_equal(again["voxel_coords"].cpu().numpy(), ref["voxel_coords"].cpu().numpy())
