@@ -48,17 +48,17 @@ __device__ __forceinline__ bool voxel_coord(const VoxGeom& g, float x, float y, 
 // acc layout per slot: [sum_0 .. sum_{C-1}, count] padded to ACCW floats (4 or 8) so one
 // slot is one 16/32-byte sector and C=3 uses a single red.global.add.v4.f32.
 template <int ACCW>
-__device__ __forceinline__ void dynvox_add(const VoxGeom& g, long long b, const float (&f)[kMaxFeat], unsigned long long hmask,
+__device__ __forceinline__ void dynvox_add(const VoxGeom& g, long long b, const float (&f)[kMaxFeat], unsigned long long nslots,
                                            unsigned long long* __restrict__ keys, float* __restrict__ acc) {
     int cx, cy, cz;
     if (!voxel_coord(g, f[0], f[1], f[2], cx, cy, cz)) return;
     const unsigned long long key =
         (unsigned long long)(((b * g.g[0] + cx) * g.g[1] + cy) * (long long)g.g[2] + cz);
-    unsigned long long slot = mix64(key) & hmask;
+    unsigned long long slot = __umul64hi(mix64(key), nslots);   // fast range reduction: any table size, no modulo
     while (true) {
         const unsigned long long prev = atomicCAS(&keys[slot], kEmpty, key);
         if (prev == kEmpty || prev == key) break;
-        slot = (slot + 1) & hmask;
+        if (++slot == nslots) slot = 0;
     }
     float* a = acc + slot * ACCW;
     if (ACCW == 4) {
@@ -71,7 +71,7 @@ __device__ __forceinline__ void dynvox_add(const VoxGeom& g, long long b, const 
 
 template <int ACCW>
 __global__ void __launch_bounds__(256)
-dynvox_insert_kernel(int n, int c, const float* __restrict__ points, VoxGeom g, unsigned long long hmask,
+dynvox_insert_kernel(int n, int c, const float* __restrict__ points, VoxGeom g, unsigned long long nslots,
                      unsigned long long* __restrict__ keys, float* __restrict__ acc) {
     const int stride = 1 + c;
     for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < n; p += gridDim.x * blockDim.x) {
@@ -80,7 +80,7 @@ dynvox_insert_kernel(int n, int c, const float* __restrict__ points, VoxGeom g, 
         const float bf = row[0];
 #pragma unroll
         for (int j = 0; j < kMaxFeat; ++j) f[j] = j < c ? row[1 + j] : 0.f;
-        dynvox_add<ACCW>(g, (long long)(int)bf /* points[:,0].int() */, f, hmask, keys, acc);
+        dynvox_add<ACCW>(g, (long long)(int)bf /* points[:,0].int() */, f, nslots, keys, acc);
     }
 }
 
@@ -91,7 +91,7 @@ dynvox_insert_frames_kernel(int n_frame_pts, int pts_per_frame, const float* __r
                             const unsigned char* __restrict__ frame_keep, int n_obj_pts,
                             int pts_per_obj, const float* __restrict__ obj_pts, const int* __restrict__ obj_frame,
                             const int* __restrict__ obj_count,
-                            VoxGeom g, unsigned long long hmask, unsigned long long* __restrict__ keys,
+                            VoxGeom g, unsigned long long nslots, unsigned long long* __restrict__ keys,
                             float* __restrict__ acc) {
     const int n = n_frame_pts + n_obj_pts;
     for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < n; p += gridDim.x * blockDim.x) {
@@ -108,7 +108,7 @@ dynvox_insert_frames_kernel(int n_frame_pts, int pts_per_frame, const float* __r
         float f[kMaxFeat];
 #pragma unroll
         for (int j = 0; j < kMaxFeat; ++j) f[j] = j < 3 ? row[j] : 0.f;
-        dynvox_add<4>(g, b, f, hmask, keys, acc);
+        dynvox_add<4>(g, b, f, nslots, keys, acc);
     }
 }
 
@@ -326,8 +326,9 @@ struct DynWs {
 
 DynWs dyn_layout(int n, int c, int max_voxels) {
     DynWs w{};
-    unsigned long long h = 1024;
-    while (h < 2ull * (unsigned long long)(n > 0 ? n : 1)) h <<= 1;
+    // 1.5 slots per point (load factor <= 2/3 even if every point opens its own voxel; ~0.2 on LiDAR frames).  Not a power
+    // of two: the slot comes from a multiply-high, so the table, its memsets and the finalize scan are not rounded up 2x.
+    unsigned long long h = ((unsigned long long)(n > 0 ? n : 1) * 3 / 2 + 1024 + 255) & ~255ull;
     w.nslots = h;
     w.accw = (c + 1 <= 4) ? 4 : 8;
     size_t o = 0;
@@ -416,17 +417,17 @@ int dynvox_run(const char* what, int num_points, int num_features, const DynSrc&
     if (!src.points) {
         dynvox_insert_frames_kernel<<<grid_ins, 256, 0, st>>>(src.n_frame_pts, src.pts_per_frame, src.frame_pts, src.frame_keep,
                                                              src.n_obj_pts, src.pts_per_obj, src.obj_pts, src.obj_frame, src.obj_count,
-                                                             g, w.nslots - 1, keys, acc);
+                                                             g, w.nslots, keys, acc);
         SEEVCN_LAUNCH_CHECK();
         dynvox_finalize_kernel<4><<<grid_fin, 256, 0, st>>>(w.nslots, num_features, g, keys, acc, max_voxels, o_coords,
                                                            o_feat, o_cnt, o_keys, key32, num_voxels);
     } else if (w.accw == 4) {
-        dynvox_insert_kernel<4><<<grid_ins, 256, 0, st>>>(num_points, num_features, src.points, g, w.nslots - 1, keys, acc);
+        dynvox_insert_kernel<4><<<grid_ins, 256, 0, st>>>(num_points, num_features, src.points, g, w.nslots, keys, acc);
         SEEVCN_LAUNCH_CHECK();
         dynvox_finalize_kernel<4><<<grid_fin, 256, 0, st>>>(w.nslots, num_features, g, keys, acc, max_voxels, o_coords,
                                                            o_feat, o_cnt, o_keys, key32, num_voxels);
     } else {
-        dynvox_insert_kernel<8><<<grid_ins, 256, 0, st>>>(num_points, num_features, src.points, g, w.nslots - 1, keys, acc);
+        dynvox_insert_kernel<8><<<grid_ins, 256, 0, st>>>(num_points, num_features, src.points, g, w.nslots, keys, acc);
         SEEVCN_LAUNCH_CHECK();
         dynvox_finalize_kernel<8><<<grid_fin, 256, 0, st>>>(w.nslots, num_features, g, keys, acc, max_voxels, o_coords,
                                                            o_feat, o_cnt, o_keys, key32, num_voxels);

@@ -438,6 +438,29 @@ def test_vcn_forward_beyond_one_pass(cuda):
     assert (rel_chamfer(full[sel], want, part[sel]) < 1e-3).all()
 
 
+def test_vcn_forward_dense_decoder_c4_shape(cuda):
+    """BASELINE.json configs[3] shape: 2048 input points per object, 16,384-point decoder (shape_fc.4: 1024 -> 49,152),
+    then the 16,384-reference kNN surface selection on the output.  The reference class ties the encoder width to
+    number_coarse (VCN_VC.py:130) and so only runs with 1024; the decoder is widened here the way §8(a6) counts it."""
+    nc, n, nobj = 16384, 2048, 3
+    part, _, _ = synth.make_object_clouds(97, nobj, n, 0)
+    sd = oracle.make_state_dict("VCN_VC", seed=7, num_coarse=nc)
+    model = MODELS.build({"NAME": "VCN_VC"}, precision="bf16")
+    model.number_coarse = nc
+    model.shape_fc[4] = torch.nn.Linear(1024, 3 * nc)
+    model.load_state_dict(sd)
+    model.to(cuda).eval()
+    x = dev(part, cuda)
+    got = model({"input": x})["coarse"]
+    assert tuple(got.shape) == (nobj, nc, 3)
+    want = oracle.vcn_forward_ref(sd, part, None, "VCN_VC")["coarse"].numpy()
+    assert (rel_chamfer(got.cpu().numpy(), want, part) < 1e-3).all()
+    surf, cnt = get_partial_mesh_batch(x, got, k=20, surface_pts=n, return_count=True)
+    wsurf, wcnt = oracle.get_partial_mesh_batch(part, got.cpu().numpy(), k=20, surface_pts=n)
+    np.testing.assert_array_equal(cnt.cpu().numpy(), wcnt)
+    np.testing.assert_array_equal(surf.cpu().numpy(), wsurf)
+
+
 # ------------------------------------------------------------------ stage 6: voxelization --
 WAYMO = ([-75.2, -75.2, -2, 75.2, 75.2, 4], [0.1, 0.1, 0.15], [1504, 1504, 40])
 
