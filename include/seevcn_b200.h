@@ -151,7 +151,7 @@ int seevcn_knn(int b, int r, int q, int k, const float* ref_pts, const float* qu
  * point; out = complete[sorted(S)] repeated cyclically to surface_pts rows.
  * partial (B,Np,3), complete (B,R,3) -> out (B,surface_pts,3), sel_count (B) int32 = |S|.
  * R <= 16384, Np <= 4096.  workspace: seevcn_knn_surface_select_workspace_bytes(b, n_partial, r) bytes of
- * 16-byte aligned device scratch (axis-sorted copies of the clouds, the union bit masks the CTAs of one object share). */
+ * 16-byte aligned device scratch (Morton-ordered copies of the clouds, per-block bounding boxes, the union bit masks). */
 size_t seevcn_knn_surface_select_workspace_bytes(int b, int n_partial, int r);
 int seevcn_knn_surface_select(int b, int n_partial, int r, int k, int surface_pts,
                               const float* partial, const float* complete,
