@@ -154,13 +154,6 @@ knn_kernel(int r, int q, int k, const float* __restrict__ ref_pts, const float* 
     }
 }
 
-__device__ __forceinline__ unsigned hash3(float x, float y, float z) {
-    unsigned h = __float_as_uint(x) * 0x9E3779B1u;
-    h ^= __float_as_uint(y) * 0x85EBCA77u + (h << 6) + (h >> 2);
-    h ^= __float_as_uint(z) * 0xC2B2AE3Du + (h << 6) + (h >> 2);
-    return h ^ (h >> 15);
-}
-
 // ascending bitonic sort of s[0..len), len a power of two, by the whole CTA (ends with a barrier)
 template <int T>
 __device__ void bitonic_sort(u64* s, int len) {
@@ -181,10 +174,10 @@ __device__ void bitonic_sort(u64* s, int len) {
 // (1) knn_prepare_kernel, one CTA per object: sorts the completed points by the Morton code of their position in
 // the cloud's bounding box (bitonic sort of (code, index) keys in shared memory), writes them as float4
 // (x, y, z, original index) and, for every block of 32 consecutive sorted points — a compact patch of the cloud —
-// its bounding box; de-duplicates the object's queries with a shared-memory hash set keyed by the exact
-// coordinates (duplicate queries cannot change a union — the reference's np.unique(partial) at sampling.py:31
-// is the same optimisation; resampled clouds are mostly duplicates) and writes the unique ones in Morton order
-// too, so that the 32 queries of a warp are neighbours in space.
+// its bounding box; sorts the object's queries by Morton code too and drops the copies of a point, which sit in
+// one run of equal codes (duplicate queries cannot change a union — the reference's np.unique(partial) at
+// sampling.py:31 is the same optimisation; resampled clouds are mostly duplicates), so that the 32 queries of a
+// warp are distinct neighbours in space.
 //
 // (2) knn_scan_kernel, grid (query chunks, objects): one thread per unique query, warps independent (no CTA
 // barrier).  A warp walks the blocks in lockstep — every lane reads the same point, one broadcast load per
@@ -217,20 +210,19 @@ __device__ __forceinline__ unsigned morton30(float x, float y, float z, const fl
     return spread10((unsigned)ix) | (spread10((unsigned)iy) << 1) | (spread10((unsigned)iz) << 2);
 }
 
-// prepare smem: keys max(rp2, qp2) u64 | partial SoA 3*np f32 | hash table H i32
+// prepare smem: keys max(rp2, qp2) u64 | partial SoA 3*np f32
 template <int T>
 __global__ void __launch_bounds__(T)
-knn_prepare_kernel(int np, int r, int rp2, int qp2, int hash_size, const float* __restrict__ partial,
+knn_prepare_kernel(int np, int r, int rp2, int qp2, const float* __restrict__ partial,
                    const float* __restrict__ complete, float4* __restrict__ ws_refs, float4* __restrict__ ws_box,
                    float4* __restrict__ ws_q, int* __restrict__ ws_meta) {
     extern __shared__ __align__(16) unsigned char s_raw[];
     u64* keys = reinterpret_cast<u64*>(s_raw);
     float* qx = reinterpret_cast<float*>(keys + max(rp2, qp2));
     float* qy = qx + np; float* qz = qy + np;
-    int* tab = reinterpret_cast<int*>(qz + np);
     __shared__ float s_lo[6][T / 32], s_hi[6][T / 32];   // 0..2 completed cloud, 3..5 queries
     __shared__ float s_org[6], s_inv[6];
-    __shared__ int s_run;
+    __shared__ int s_cnt[T / 32];
 
     const int b = blockIdx.x;
     const float* cp = complete + (size_t)b * r * 3;
@@ -257,8 +249,6 @@ knn_prepare_kernel(int np, int r, int rp2, int qp2, int hash_size, const float* 
         }
         if (lane_id() == 0) { s_lo[c][warp_id()] = lo[c]; s_hi[c][warp_id()] = hi[c]; }
     }
-    for (int i = threadIdx.x; i < hash_size; i += T) tab[i] = -1;
-    if (threadIdx.x == 0) s_run = 0;
     __syncthreads();
     if (threadIdx.x < 6) {
         const int c = threadIdx.x;
@@ -301,41 +291,40 @@ knn_prepare_kernel(int np, int r, int rp2, int qp2, int hash_size, const float* 
     }
     __syncthreads();
 
-    // hash-set insert keyed by the exact coordinates; a slot ends up holding the LOWEST query index of its key
-    for (int qi = threadIdx.x; qi < np; qi += T) {
-        const float x = qx[qi], y = qy[qi], z = qz[qi];
-        unsigned h = hash3(x, y, z) & (hash_size - 1);
-        while (true) {
-            const int prev = atomicCAS(&tab[h], -1, qi);
-            if (prev == -1) break;
-            if (qx[prev] == x && qy[prev] == y && qz[prev] == z) { atomicMin(&tab[h], qi); break; }   // duplicate query
-            h = (h + 1) & (hash_size - 1);
-        }
-    }
-    __syncthreads();
-    // representatives (lowest index of equal coordinates) -> sort keys; the sort makes their order deterministic
-    for (int qi = threadIdx.x; qi < np; qi += T) {
-        const float x = qx[qi], y = qy[qi], z = qz[qi];
-        unsigned h = hash3(x, y, z) & (hash_size - 1);
-        while (true) {
-            const int cur = tab[h];
-            if (qx[cur] == x && qy[cur] == y && qz[cur] == z) {
-                if (cur == qi) keys[atomicAdd(&s_run, 1)] = ((u64)morton30(x, y, z, s_org + 3, s_inv + 3) << 32) | (unsigned)qi;
-                break;
-            }
-            h = (h + 1) & (hash_size - 1);
-        }
-    }
-    __syncthreads();
-    const int nuniq = s_run;
-    for (int p = nuniq + threadIdx.x; p < qp2; p += T) keys[p] = kInfKey;
+    // Queries: sort ALL of them by (Morton code, index).  Equal coordinates have equal codes, so the copies of a point
+    // sit in one run of equal codes; the first of them in that run (lowest index) represents it.  Representatives are
+    // compacted in sorted order straight into the workspace — no hash table, no atomics, no second sort.
+    for (int p = threadIdx.x; p < qp2; p += T)
+        keys[p] = p < np ? ((u64)morton30(qx[p], qy[p], qz[p], s_org + 3, s_inv + 3) << 32) | (unsigned)p : kInfKey;
     __syncthreads();
     bitonic_sort<T>(keys, qp2);
     float4* wq = ws_q + (size_t)b * np;
-    for (int p = threadIdx.x; p < nuniq; p += T) {
-        const int qi = (int)(unsigned)keys[p];
-        wq[p] = make_float4(qx[qi], qy[qi], qz[qi], 0.f);
+    int base = 0;
+    for (int p0 = 0; p0 < np; p0 += T) {
+        const int p = p0 + threadIdx.x;
+        bool rep = false;
+        float x = 0.f, y = 0.f, z = 0.f;
+        if (p < np) {
+            const u64 key = keys[p];
+            const unsigned code = (unsigned)(key >> 32);
+            const int qi = (int)(unsigned)key;
+            x = qx[qi]; y = qy[qi]; z = qz[qi];
+            rep = true;
+            for (int j = p - 1; j >= 0 && (unsigned)(keys[j] >> 32) == code; --j) {
+                const int qj = (int)(unsigned)keys[j];
+                if (qx[qj] == x && qy[qj] == y && qz[qj] == z) { rep = false; break; }   // an earlier copy represents it
+            }
+        }
+        const unsigned m = __ballot_sync(0xffffffffu, rep);
+        if (lane_id() == 0) s_cnt[warp_id()] = __popc(m);
+        __syncthreads();
+        int before = 0, total = 0;
+        for (int w = 0; w < T / 32; ++w) { const int c = s_cnt[w]; if (w < warp_id()) before += c; total += c; }
+        if (rep) wq[base + before + __popc(m & ((1u << lane_id()) - 1))] = make_float4(x, y, z, 0.f);
+        base += total;
+        __syncthreads();
     }
+    const int nuniq = base;
     if (threadIdx.x == 0) { ws_meta[2 * b] = nuniq; ws_meta[2 * b + 1] = nblk; }
 }
 
@@ -579,13 +568,12 @@ extern "C" int seevcn_knn_surface_select(int b, int n_partial, int r, int k, int
     {
         constexpr int TP = 512;
         const int rp2 = next_pow2(r), qp2 = next_pow2(n_partial > 0 ? n_partial : 1);
-        const int hash_size = next_pow2(2 * (n_partial > 0 ? n_partial : 1));
-        const size_t smem = (size_t)(rp2 > qp2 ? rp2 : qp2) * 8 + (size_t)n_partial * 12 + (size_t)hash_size * 4;
+        const size_t smem = (size_t)(rp2 > qp2 ? rp2 : qp2) * 8 + (size_t)n_partial * 12;
         auto kern = knn_prepare_kernel<TP>;
         if (smem > 40 * 1024)
             SEEVCN_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         SEEVCN_PROF("knn_prepare_kernel", st);
-        kern<<<b, TP, smem, st>>>(n_partial, r, rp2, qp2, hash_size, partial, complete, ws_refs, ws_box, ws_q, ws_meta);
+        kern<<<b, TP, smem, st>>>(n_partial, r, rp2, qp2, partial, complete, ws_refs, ws_box, ws_q, ws_meta);
         SEEVCN_LAUNCH_CHECK();
     }
     {

@@ -235,19 +235,19 @@ class HostStream:
 
     The reference's driver (``sc_multiproc.py:60-94``) reads a frame from disk, completes its objects and
     writes a .pcd; here a batch of frames arrives in pinned memory and the completed clouds + voxel tensors
-    leave in pinned memory.  Three CUDA streams: the H2D copy of batch i+2 and the D2H copy of batch i-2
+    leave in pinned memory.  Three CUDA streams: the H2D copy of batch i+3 and the D2H copies of batches i-2, i-3
     overlap the kernels of batch i (the copy engines are otherwise idle; every batch still pays its own
     copies inside the caller's timed region), and batch i+1's crop is queued ahead of batch i's completion
     stage so its box counts are on the host by the time they are needed.
 
         hs = HostStream(pipe, frames, pts_per_frame, boxes_per_frame)
         for res in hs.run(batches):      # batches: iterable of (points_pinned (F,P,3), boxes_pinned (F,T,7))
-            res["clustered"], res["voxel_coords"], ...   # pinned host views, valid until `depth - 1` batches later
+            res["clustered"], res["voxel_coords"], ...   # pinned host views, valid for the next `depth - 4` batches (copy them if they must live longer)
     """
     KEYS = ("clustered", "voxel_coords", "voxel_features", "voxel_num_points")
 
-    def __init__(self, pipe, frames, pts_per_frame, boxes_per_frame, depth=4):
-        assert depth >= 4   # a slot is overwritten two batches after its batch was finalized (finalize may re-voxelize from it)
+    def __init__(self, pipe, frames, pts_per_frame, boxes_per_frame, depth=5):
+        assert depth >= 5   # uploads run 3 batches ahead: a slot is reused only after its batch was finalized (finalize may re-voxelize from it)
         self.pipe, self.depth = pipe, depth
         dev = pipe.device
         self.dev = dev
@@ -314,31 +314,30 @@ class HostStream:
             compute.wait_event(self.ev_in[i % D])
             return self.pipe.crop_async(self.d_pts[i % D], self.d_boxes[i % D])
 
-        upload_next(); upload_next()
+        upload_next(); upload_next(); upload_next()
         if state["up"] == 0:
             return
         h, i = crop(0), 0
-        # prev: stage B queued, M not read yet; fin: finalized (M known), download not issued yet; pending: D2H issued.
+        # prev: stage B queued, M not read yet; fin: finalized (M known), download not issued yet; pending: D2H issued
+        # (up to two in flight, so a slow transfer does not stop the launches).
         # The bulk download of a batch is issued one iteration AFTER its finalize: issued right away it would sit on the
         # D2H copy engine in front of the few bytes of box counts the next stage B launch is waiting for.
-        prev = fin = pending = None
+        prev = fin = None
+        pending = []
         while h is not None:
-            upload_next()                                            # batch i+2: overlaps the kernels below
+            upload_next()                                            # batch i+3: overlaps the kernels below
             h_next = crop(i + 1) if i + 1 < state["up"] else None    # ahead of batch i's stage B
             out = self.pipe.run_from(h, seed, defer=True)
             if fin is not None:
-                res = self._download(fin[0] % D, fin[1])             # overlaps this batch's kernels
-                if pending is not None:
-                    yield self._collect(pending)
-                pending, fin = (fin[0] % D, res), None
+                pending.append((fin[0] % D, self._download(fin[0] % D, fin[1])))   # overlaps this batch's kernels
+                fin = None
+                if len(pending) > 2:
+                    yield self._collect(pending.pop(0))
             if prev is not None:
                 fin = (prev[0], self.pipe.finalize(prev[1]))
             prev, h, i = (i, out), h_next, i + 1
         for item in (fin, (prev[0], self.pipe.finalize(prev[1]))):
-            if item is None:
-                continue
-            res = self._download(item[0] % D, item[1])
-            if pending is not None:
-                yield self._collect(pending)
-            pending = (item[0] % D, res)
-        yield self._collect(pending)
+            if item is not None:
+                pending.append((item[0] % D, self._download(item[0] % D, item[1])))
+        for p in pending:
+            yield self._collect(p)
