@@ -5,7 +5,7 @@ ref: detector3d/pcdet/models/backbones_3d/vfe/dynamic_mean_vfe.py:14-76
 import torch
 
 from ..... import _abi
-from .vfe_template import VFETemplate
+from .vfe_template import VFETemplate, require_keys
 
 
 def dynamic_voxelize(points, point_cloud_range, voxel_size, grid_size, max_voxels=None, sort=True, workspace=None,
@@ -103,6 +103,7 @@ class DynamicMeanVFE(VFETemplate):
         """batch_dict['points'] (sum N, 1+C) [batch_idx, x, y, z, ...] ->
         ['voxel_features'] (M, C) mean of all in-voxel points, ['voxel_coords'] (M, 4) int32 [b,z,y,x],
         plus ['voxel_num_points'] (M,) int32 (the reference computes and drops unq_cnt, :63)."""
+        require_keys(batch_dict, 'points')
         coords, feats, counts = dynamic_voxelize(batch_dict['points'], self.point_cloud_range, self.voxel_size,
                                                  self.grid_size, sort=self.sort, batch_size=int(batch_dict.get('batch_size', 0)))
         batch_dict['voxel_features'] = feats.contiguous()

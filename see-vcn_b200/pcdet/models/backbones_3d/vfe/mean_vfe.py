@@ -2,7 +2,7 @@
 import torch
 
 from ..... import _abi
-from .vfe_template import VFETemplate
+from .vfe_template import VFETemplate, require_keys
 
 
 class MeanVFE(VFETemplate):
@@ -17,6 +17,7 @@ class MeanVFE(VFETemplate):
     def forward(self, batch_dict, **kwargs):
         """batch_dict['voxels'] (M, T, C), ['voxel_num_points'] (M,) -> ['voxel_features'] (M, C)
         = voxels.sum(1) / clamp_min(num_points, 1)"""
+        require_keys(batch_dict, 'voxels', 'voxel_num_points')
         voxels = batch_dict['voxels'].contiguous()
         num = batch_dict['voxel_num_points'].to(torch.float32).contiguous()
         _abi.require_cuda(voxels, num)
