@@ -42,3 +42,30 @@ def test_training_mode_is_rejected():
     model.train()
     with pytest.raises(RuntimeError):
         model._pack()
+
+
+def test_pcd_wire_format_roundtrip_and_reference_header(tmp_path):
+    """Binary PCD as open3d writes it for SEE_VCN.save_pcd (SEE_VCN.py:267-280): our header for N points equals the
+    header of the reference's demo frame byte for byte (tests/golden/pcd_header.txt, N = 26715), the payload is
+    N x 3 float32, and the reader returns what was written; extra fields and the ascii flavour are read too."""
+    import os
+    import numpy as np
+    from seevcn_b200.see.surface_completion.pcd_io import pcd_header, read_pcd, write_pcd
+    here = os.path.dirname(os.path.abspath(__file__))
+    ref_header = open(os.path.join(here, "golden", "pcd_header.txt"), "rb").read()
+    assert pcd_header(26715).encode("ascii") == ref_header
+    first = np.load(os.path.join(here, "golden", "pcd_demo_first64.npy"))
+    path = str(tmp_path / "frame.pcd")
+    write_pcd(path, np.concatenate([first, np.ones((64, 1), np.float32)], axis=1))   # a 4th column is dropped, as in save_pcd
+    raw = open(path, "rb").read()
+    assert raw.startswith(pcd_header(64).encode("ascii")) and len(raw) == len(pcd_header(64)) + 64 * 12
+    np.testing.assert_array_equal(read_pcd(path), first)
+    # x y z intensity, binary: the reader picks the requested columns
+    hdr = ("VERSION 0.7\nFIELDS x y z intensity\nSIZE 4 4 4 4\nTYPE F F F F\nCOUNT 1 1 1 1\nWIDTH 64\nHEIGHT 1\n"
+           "VIEWPOINT 0 0 0 1 0 0 0\nPOINTS 64\nDATA binary\n")
+    four = np.concatenate([first, np.arange(64, dtype=np.float32)[:, None]], axis=1)
+    open(path, "wb").write(hdr.encode() + four.astype("<f4").tobytes())
+    np.testing.assert_array_equal(read_pcd(path), first)
+    np.testing.assert_array_equal(read_pcd(path, ("intensity",))[:, 0], np.arange(64, dtype=np.float32))
+    open(path, "w").write(hdr.replace("binary", "ascii") + "\n".join(" ".join(repr(float(v)) for v in row) for row in four) + "\n")
+    np.testing.assert_array_equal(read_pcd(path), first)
