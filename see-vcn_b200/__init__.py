@@ -7,9 +7,11 @@ Layout
   pcdet/ops/...                 points_in_boxes_gpu/cpu, furthest_point_sample, gather/grouping, knn
   pcdet/models/backbones_3d/vfe MeanVFE, DynamicMeanVFE
   pcdet/datasets/processor      VoxelGeneratorWrapper
-  see/surface_completion/...    VCN_VC / VCN_CN forward, VCN.inference
-  pipeline.py                   frame-level crop -> complete -> select -> voxelize driver
-  dist.py                       frame sharding over ranks + all-gather-v of results
+  see/surface_completion/...    VCN_VC / VCN_CN forward, VCN.inference, kNN surface / largest cluster, the splice step
+                                (SEE_VCN.replace_with_completed_pts), the .pcd wire format (pcd_io)
+  pipeline.py                   frame-level crop -> complete -> select -> cluster -> splice -> voxelize driver,
+                                HostStream (pinned host buffers in / out)
+  dist.py                       frame sharding over ranks + all-gather of results (static-capacity async form)
 
 There is no CPU fallback: every op raises if the CUDA library is missing or the device is
 not sm_100.
