@@ -154,19 +154,26 @@ knn_kernel(int r, int q, int k, const float* __restrict__ ref_pts, const float* 
     }
 }
 
-// ascending bitonic sort of s[0..len), len a power of two, by the whole CTA (ends with a barrier)
+// ascending bitonic sort of s[0..len), len a power of two, by the whole CTA (ends with a barrier).  Pair t of a stage
+// with stride j <= 32 lies in the aligned 64-element chunk that the 32 consecutive pairs of one warp cover, so those
+// stages (45 of the 55 for 1024 keys) only need a warp barrier; a CTA barrier separates them from the wide stages.
 template <int T>
 __device__ void bitonic_sort(u64* s, int len) {
+    bool wide_prev = true;                       // callers arrive behind a CTA barrier
     for (int k = 2; k <= len; k <<= 1)
         for (int j = k >> 1; j > 0; j >>= 1) {
+            const bool wide = j > 32;
+            if (wide && !wide_prev) __syncthreads();
             for (int t = threadIdx.x; t < (len >> 1); t += T) {
                 const int i = ((t & ~(j - 1)) << 1) | (t & (j - 1));
                 const int p = i | j;
                 const u64 a = s[i], b = s[p];
                 if ((a > b) == ((i & k) == 0)) { s[i] = b; s[p] = a; }
             }
-            __syncthreads();
+            if (wide) __syncthreads(); else __syncwarp();
+            wide_prev = wide;
         }
+    __syncthreads();
 }
 
 // Surface selection = union over the object's queries of their k nearest completed points.  Three kernels.
