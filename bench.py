@@ -256,7 +256,7 @@ def run_ours(args):
         l0 = _abi.lib().seevcn_launch_count()
         _abi.prof_enable(True)
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        n_obj = n_pts = 0
+        n_obj = 0
         last = None
         e0.record()
         gathered = None
@@ -265,12 +265,16 @@ def run_ours(args):
                 if gathered is not None:
                     gathered.wait()
                 gathered = sdist.all_gather_padded(out.get("clustered", out["surface"]), F * boxes_h.shape[1], async_op=True)
-            n_obj += out["input"].shape[0]; n_pts += out["num_voxel_points"]
+            n_obj += out["input"].shape[0]
             last = out
         if gathered is not None:
             gathered.wait()
         e1.record()
         e1.synchronize()
+        # rows actually voxelized (spliced-out points, cyclic repeats and out-of-range points are not): the voxel counts
+        # sum to it; every step runs the same frames
+        n_pts = int(last["voxel_num_points"].sum().item()) * steps
+        last["num_voxel_points"] = n_pts // max(steps, 1)
         _abi.prof_enable(False)
         prof = _abi.prof_report()
         launches = _abi.lib().seevcn_launch_count() - l0

@@ -163,16 +163,21 @@ int seevcn_knn_surface_select(int b, int n_partial, int r, int k, int surface_pt
  * min_points = 2 at see/surface_completion/models/VCN.py:95-98.  min_points in {1, 2}: DBSCAN is then exactly
  * connected components of the eps-graph (strict d < eps, float64), isolated points are noise when
  * min_points = 2.  pts (B,n,3), n <= 8192 -> out (B,total_pts,3): members of the largest component in
- * ascending row order, repeated cyclically; out_count (B) = members (0: everything was noise, rows zero).
+ * ascending row order, repeated cyclically; out_count (B) = member rows (0: everything was noise, rows zero);
+ * out_distinct (B) or NULL = how many of the clustered rows are members, i.e. the leading rows of `out` before the
+ * cyclic repetition starts (== out_count unless the input was tiled and clustered through the periodic entry).
  * PARITY UNPINNED (open3d is not vendored). */
 int seevcn_largest_cluster(int b, int n, int total_pts, double eps, int min_points, const float* pts,
-                           float* out, int* out_count, seevcn_stream_t stream);
+                           float* out, int* out_count, int* out_distinct, seevcn_stream_t stream);
 
 /* Same result, for clouds the caller knows to be tiled: period (B) int32 DEVICE, pts[b][r] == pts[b][r % period[b]]
  * (the output of seevcn_knn_surface_select with period = sel_count).  Only the period[b] distinct rows are
- * clustered, each weighted by its multiplicity; eps > 0. */
+ * clustered, each weighted by its multiplicity (out_count is the weighted size, as np.bincount sees it on the tiled
+ * cloud); out_distinct is the number of distinct member rows — what np.unique(clustered) keeps (SEE_VCN.py:113,244) and
+ * what the splice / voxelization stages take as the object's row count.  eps > 0. */
 int seevcn_largest_cluster_periodic(int b, int n, int total_pts, double eps, int min_points, const float* pts,
-                                    const int* period, float* out, int* out_count, seevcn_stream_t stream);
+                                    const int* period, float* out, int* out_count, int* out_distinct,
+                                    seevcn_stream_t stream);
 
 /* ------------------------------------------- stages 2+5: VCN forward (canonicalise+MLP) */
 
@@ -274,22 +279,23 @@ int seevcn_mean_vfe(int num_voxels, int max_points, int num_features, const floa
 
 /* ref: DynamicMeanVFE.forward  detector3d/pcdet/models/backbones_3d/vfe/dynamic_mean_vfe.py:37-76
  * points (N,1+C) f32 rows [batch_idx,x,y,z,...]; pc_range[6], voxel_size[3], grid_size[3]
- * are HOST arrays (grid constants, like the python attributes of the reference module).
- * Sort-free hashed scatter-mean.  Outputs (capacity max_voxels rows each):
+ * are HOST arrays (grid constants, like the python attributes of the reference module); batch_size is
+ * batch_dict['batch_size'] (>= 1; rows whose batch index lies outside [0, batch_size) are ignored).
+ * Outputs (capacity max_voxels rows each):
  *   voxel_coords   (M,4) int32 [b,z,y,x]
  *   voxel_features (M,C) f32   mean of all in-voxel points
- *   voxel_counts   (M)   int32
- *   num_voxels     (1)   int32 (device)  M
- * Row order is the hash-table order unless sorted != 0, in which case rows are ordered by
- * the reference's merge key b*XYZ + x*YZ + y*Z + z like torch.unique (64-bit, so batch >= 24
- * on the Waymo grid does not overflow as the reference's int32 key does).
- * batch_hint: upper bound on the batch indices + 1 (batch_dict['batch_size']); only narrows the radix sort
- * to the key bits in use, <= 0 means unknown.
- * workspace: seevcn_dynamic_voxelize_workspace_bytes(N, C, max_voxels). */
-size_t seevcn_dynamic_voxelize_workspace_bytes(int num_points, int num_features, int max_voxels);
+ *   voxel_counts   (M)   int32 (the reference computes unq_cnt and drops it, :63)
+ *   num_voxels     (1)   int32 (device)  M; rows beyond max_voxels are dropped, M still reports all of them
+ * Rows are ALWAYS ordered by the reference's merge key b*XYZ + x*YZ + y*Z + z, i.e. torch.unique order (64-bit, so
+ * batch >= 24 on the Waymo grid does not overflow as the reference's int32 key does); `sorted` is kept for source
+ * compatibility and ignored.  No sort and no hash table: points are bucketed by the high key bits (counting pass +
+ * look-back scan + scatter) and a warp per bucket ranks its voxels with an occupancy bitmap.  xyz means are accumulated
+ * as integers relative to the voxel origin: bit-reproducible run to run, equal to the float64 mean rounded to fp32.
+ * workspace: seevcn_dynamic_voxelize_workspace_bytes(N, C, batch_size, grid_size) bytes (0: batch x grid too large). */
+size_t seevcn_dynamic_voxelize_workspace_bytes(int num_points, int num_features, int batch_size, const int* grid_size);
 int seevcn_dynamic_voxelize(int num_points, int num_features, const float* points,
                             const float* pc_range, const float* voxel_size, const int* grid_size,
-                            int max_voxels, int sorted, int batch_hint,
+                            int max_voxels, int sorted, int batch_size,
                             int* voxel_coords, float* voxel_features, int* voxel_counts,
                             int* num_voxels, void* workspace, size_t workspace_bytes,
                             seevcn_stream_t stream);
@@ -298,7 +304,7 @@ int seevcn_dynamic_voxelize(int num_points, int num_features, const float* point
  * batch index = frame, and the completed object clouds obj_pts (O,S,3), batch index obj_frame[o] (O int32) — so the
  * [batch_idx,x,y,z] matrix the reference concatenates on the host (detector3d/pcdet/datasets/dataset.py:187-192
  * after SEE_VCN.py:247-265 merged the completed points into the frame) is never materialised.  C = 3.
- * workspace: seevcn_dynamic_voxelize_workspace_bytes(F*P + O*S, 3, max_voxels). */
+ * workspace: seevcn_dynamic_voxelize_workspace_bytes(F*P + O*S, 3, F, grid_size). */
 int seevcn_dynamic_voxelize_frames(int num_frames, int pts_per_frame, const float* frame_pts,
                                    int num_obj, int pts_per_obj, const float* obj_pts, const int* obj_frame,
                                    const float* pc_range, const float* voxel_size, const int* grid_size,

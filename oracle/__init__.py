@@ -162,6 +162,13 @@ def get_largest_cluster_batch(pc, eps=0.4, min_points=1, total_pts=1024):
     return out, cnt
 
 
+def distinct_rows(clustered, counts):
+    """How many of an object's clustered rows np.unique keeps (SEE_VCN.py:113,244 applies np.unique to the stacked
+    clustered clouds): the number of distinct rows among the first counts[o] rows of clustered[o].  (B,) int32."""
+    return np.asarray([len(np.unique(clustered[o][: int(counts[o])], axis=0)) if counts[o] > 0 else 0
+                       for o in range(len(clustered))], np.int32)
+
+
 # --------------------------------------------------------------------------- splice --
 def nearest_dist(points, completed, brute=False):
     """Distance (float64) from every row of points (P,3) to its nearest row of completed (K,3): what
@@ -205,7 +212,8 @@ def all_instances(clustered, counts=None):
 # ------------------------------------------------------------------------- voxelize --
 def dynamic_voxelize(points, pc_range, voxel_size, grid_size):
     """ref: dynamic_mean_vfe.py:49-76.  points (N,1+C) -> coords (M,4) [b,z,y,x], feats (M,C), counts (M,)
-    (torch_scatter absent -> fp32 sequential sum / count; last-bit order effects are inside the 1e-5 bar)."""
+    (torch_scatter absent -> the order-free value its fp32 atomic sums approximate: float64 sum / count rounded to
+    fp32; checked against the reference module itself, run with a scatter_mean stub, in tests/test_oracle.py)."""
     points = _c(points)
     N, C1 = points.shape
     C = C1 - 1

@@ -264,10 +264,13 @@ int orc_dynamic_voxelize(int N, int C, const float* points, const float* range, 
     int m = 0;
     for (int i = 0; i < n;) {
         int j = i;
-        float sum[16] = {0};
+        /* scatter_mean (third-party torch_scatter, absent): sum / count per voxel.  The CUDA implementation adds
+         * fp32 values with atomics in arrival order, so its last bits vary from run to run; the order-free value it
+         * approximates is restated here: float64 sum, one division, one rounding to fp32. */
+        double sum[16] = {0};
         while (j < n && ki[j].key == ki[i].key) {
             const float* row = points + (long long)ki[j].idx * (1 + C);
-            for (int f = 0; f < C; ++f) sum[f] += row[1 + f];
+            for (int f = 0; f < C; ++f) sum[f] += (double)row[1 + f];
             ++j;
         }
         const long long key = ki[i].key;
@@ -275,7 +278,7 @@ int orc_dynamic_voxelize(int N, int C, const float* points, const float* range, 
         coords[m * 4 + 3] = (int)((key / ((long long)grid[1] * grid[2])) % grid[0]);
         coords[m * 4 + 2] = (int)((key / grid[2]) % grid[1]);
         coords[m * 4 + 1] = (int)(key % grid[2]);
-        for (int f = 0; f < C; ++f) feats[(long long)m * C + f] = sum[f] / (float)(j - i);
+        for (int f = 0; f < C; ++f) feats[(long long)m * C + f] = (float)(sum[f] / (double)(j - i));
         counts[m] = j - i;
         ++m; i = j;
     }

@@ -50,8 +50,8 @@ SIGNATURES = {
     "seevcn_knn": (I, [I, I, I, I, P, P, P, P, P]),
     "seevcn_knn_surface_select_workspace_bytes": (c_size_t, [I, I, I]),
     "seevcn_knn_surface_select": (I, [I, I, I, I, I, P, P, P, P, P, c_size_t, P]),
-    "seevcn_largest_cluster": (I, [I, I, I, ctypes.c_double, I, P, P, P, P]),
-    "seevcn_largest_cluster_periodic": (I, [I, I, I, ctypes.c_double, I, P, P, P, P, P]),
+    "seevcn_largest_cluster": (I, [I, I, I, ctypes.c_double, I, P, P, P, P, P]),
+    "seevcn_largest_cluster_periodic": (I, [I, I, I, ctypes.c_double, I, P, P, P, P, P, P]),
     "seevcn_vcn_create": (I, [POINTER(VcnParams), POINTER(c_void_p), P]),
     "seevcn_vcn_destroy": (None, [P]),
     "seevcn_vcn_workspace_bytes": (c_size_t, [P, I, I]),
@@ -60,7 +60,7 @@ SIGNATURES = {
     "seevcn_linear_bf16_workspace_bytes": (c_size_t, [I, I, I]),
     "seevcn_linear_bf16": (I, [I, I, I, P, P, P, P, I, I, P, P, P, c_size_t, P]),
     "seevcn_mean_vfe": (I, [I, I, I, P, P, P, P]),
-    "seevcn_dynamic_voxelize_workspace_bytes": (c_size_t, [I, I, I]),
+    "seevcn_dynamic_voxelize_workspace_bytes": (c_size_t, [I, I, I, POINTER(c_int)]),
     "seevcn_dynamic_voxelize": (I, [I, I, P, POINTER(ctypes.c_float), POINTER(ctypes.c_float), POINTER(c_int),
                                     I, I, I, P, P, P, P, P, c_size_t, P]),
     "seevcn_dynamic_voxelize_frames": (I, [I, I, P, I, I, P, P, POINTER(ctypes.c_float), POINTER(ctypes.c_float), POINTER(c_int),

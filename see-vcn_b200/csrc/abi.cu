@@ -21,7 +21,7 @@ static std::atomic<unsigned long long> g_launches{0};
 void seevcn_count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 extern "C" unsigned long long seevcn_launch_count(void) { return g_launches.load(); }
 
-extern "C" int seevcn_abi_version(void) { return 1; }
+extern "C" int seevcn_abi_version(void) { return 2; }
 extern "C" const char* seevcn_last_error(void) { return g_err; }
 
 extern "C" int seevcn_check_device(int dev) {
@@ -32,6 +32,19 @@ extern "C" int seevcn_check_device(int dev) {
         return SEEVCN_E_UNSUPPORTED;
     }
     return SEEVCN_OK;
+}
+
+// SM count of the current device, cached per device (no process-wide "the device" assumption).
+int seevcn_num_sms() {
+    static std::atomic<int> cache[64];
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 148;
+    int v = cache[dev].load(std::memory_order_relaxed);
+    if (v <= 0) {
+        if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || v <= 0) v = 148;
+        cache[dev].store(v, std::memory_order_relaxed);
+    }
+    return v;
 }
 
 // ---- optional per-kernel timing with CUDA events on the launching stream (bench.py's roofline leg) ----

@@ -55,7 +55,7 @@ __device__ __forceinline__ bool exact_adjacent(const float* sx, const float* sy,
 __global__ void __launch_bounds__(kThreads)
 largest_cluster_kernel(int n, int total_pts, double eps2, float lo, float hi, int min_points,
                        const float* __restrict__ pts, const int* __restrict__ period,
-                       float* __restrict__ out, int* __restrict__ out_count) {
+                       float* __restrict__ out, int* __restrict__ out_count, int* __restrict__ out_distinct) {
     extern __shared__ __align__(16) unsigned char s_raw[];
     const int b = blockIdx.x, t = threadIdx.x;
     // rows repeat with period m (pts[r] == pts[r % m], the tiling of the kNN surface selection): cluster the
@@ -161,7 +161,10 @@ largest_cluster_kernel(int n, int total_pts, double eps2, float lo, float hi, in
     // period keeps a prefix of the list, so rank -> (q, k) = (rank / c, rank % c) for every rank < count
     const int c = best >= 0 ? s_run : 0;
     const int count = best >= 0 ? s_bestsize : 0;
-    if (t == 0) out_count[b] = count;
+    if (t == 0) {
+        out_count[b] = count;                      // member ROWS (a tiled row counts every time it appears): np.bincount's size
+        if (out_distinct) out_distinct[b] = c;     // members among the clustered (distinct) rows = leading rows of `out` that differ
+    }
     float* o = out + (size_t)b * total_pts * 3;
     for (int f = t; f < total_pts * 3; f += kThreads) {
         float v = 0.f;
@@ -177,7 +180,7 @@ largest_cluster_kernel(int n, int total_pts, double eps2, float lo, float hi, in
 }  // namespace
 
 static int largest_cluster_launch(int b, int n, int total_pts, double eps, int min_points, const float* pts,
-                                  const int* period, float* out, int* out_count, seevcn_stream_t stream) {
+                                  const int* period, float* out, int* out_count, int* out_distinct, seevcn_stream_t stream) {
     SEEVCN_REQUIRE(b >= 0 && n >= 0 && total_pts >= 0, "largest_cluster: negative size");
     SEEVCN_REQUIRE(n <= kMaxN, "largest_cluster: n=%d > %d points per object", n, kMaxN);
     SEEVCN_REQUIRE(min_points >= 1 && min_points <= 2,
@@ -186,31 +189,27 @@ static int largest_cluster_launch(int b, int n, int total_pts, double eps, int m
     SEEVCN_REQUIRE(pts && out && out_count, "largest_cluster: null pointer");
     const int n4 = (n + 3) & ~3;
     const size_t smem = (size_t)n4 * 24 + 16;
-    static bool attr = false;
-    if (!attr) {
-        SEEVCN_CUDA_CHECK(cudaFuncSetAttribute(largest_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                               kMaxN * 24 + 16));
-        attr = true;
-    }
+    // per device and cheap: set on every launch
+    SEEVCN_CUDA_CHECK(cudaFuncSetAttribute(largest_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxN * 24 + 16));
     const double e2 = eps * eps;
     // fp32 screen: below `lo` certainly adjacent, at or above `hi` certainly not (fp32 error of the
     // distance <= ~4 ulp = 2.4e-7 relative); in between the float64 test decides
     const float lo = (float)(e2 * (1.0 - 1e-5)), hi = (float)(e2 * (1.0 + 1e-5));
     SEEVCN_PROF("largest_cluster", as_stream(stream));
     largest_cluster_kernel<<<b, kThreads, smem, as_stream(stream)>>>(n, total_pts, e2, lo, hi, min_points, pts, period, out,
-                                                                    out_count);
+                                                                    out_count, out_distinct);
     SEEVCN_LAUNCH_CHECK();
     return SEEVCN_OK;
 }
 
 extern "C" int seevcn_largest_cluster(int b, int n, int total_pts, double eps, int min_points, const float* pts,
-                                      float* out, int* out_count, seevcn_stream_t stream) {
-    return largest_cluster_launch(b, n, total_pts, eps, min_points, pts, nullptr, out, out_count, stream);
+                                      float* out, int* out_count, int* out_distinct, seevcn_stream_t stream) {
+    return largest_cluster_launch(b, n, total_pts, eps, min_points, pts, nullptr, out, out_count, out_distinct, stream);
 }
 
 extern "C" int seevcn_largest_cluster_periodic(int b, int n, int total_pts, double eps, int min_points, const float* pts,
-                                               const int* period, float* out, int* out_count, seevcn_stream_t stream) {
+                                               const int* period, float* out, int* out_count, int* out_distinct, seevcn_stream_t stream) {
     SEEVCN_REQUIRE(period || b == 0, "largest_cluster_periodic: null period");
     SEEVCN_REQUIRE(eps > 0.0, "largest_cluster_periodic: eps must be > 0 (duplicate rows are merged)");
-    return largest_cluster_launch(b, n, total_pts, eps, min_points, pts, period, out, out_count, stream);
+    return largest_cluster_launch(b, n, total_pts, eps, min_points, pts, period, out, out_count, out_distinct, stream);
 }

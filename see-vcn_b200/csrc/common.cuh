@@ -6,7 +6,8 @@
 #include <stdio.h>
 #include "../../include/seevcn_b200.h"
 
-#define SEEVCN_NUM_SMS 148   // B200: 2 dies x 74 SMs
+// Multiprocessors of the CURRENT device (148 on B200: 2 dies x 74), queried once per device (abi.cu).
+int seevcn_num_sms();
 
 void seevcn_set_error(const char* fmt, ...);
 

@@ -170,13 +170,17 @@ splice_mask_kernel(int pts_per_frame, const float* __restrict__ frame_pts, int n
                 int base = 0;
                 if (lane_id() == 0) base = atomicAdd(&s_nwork, __popc(m));
                 base = __shfl_sync(0xffffffffu, base, 0);
-                if (base + __popc(m) <= kWorkCap) {
-                    if (in) s_work[base + __popc(m & ((1u << lane_id()) - 1))] = ((unsigned)i << 8) | (unsigned)j;
-                } else {                                                  // queue full: scan here, one point at a time
+                // every slot below kWorkCap is written by exactly one lane (slots are handed out contiguously), so the
+                // consumer loop below never reads a hole; lanes whose slot falls beyond the queue scan right here
+                const int slot = base + __popc(m & ((1u << lane_id()) - 1));
+                const bool queued = in && slot < kWorkCap;
+                if (queued) s_work[slot] = ((unsigned)i << 8) | (unsigned)j;
+                unsigned rest = __ballot_sync(0xffffffffu, in && !queued);
+                if (rest) {                                               // queue full: one point at a time, whole warp
                     const float* rows = obj_pts + (size_t)(c0 + j) * pts_per_obj * 3;
-                    while (m) {
-                        const int src_lane = __ffs(m) - 1;
-                        m &= m - 1;
+                    while (rest) {
+                        const int src_lane = __ffs(rest) - 1;
+                        rest &= rest - 1;
                         const float x = __shfl_sync(0xffffffffu, px[e], src_lane);
                         const float y = __shfl_sync(0xffffffffu, py[e], src_lane);
                         const float z = __shfl_sync(0xffffffffu, pz[e], src_lane);

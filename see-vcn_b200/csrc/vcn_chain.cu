@@ -504,12 +504,9 @@ int make_tmap(CUtensorMap* m, const void* base, uint64_t rows, uint64_t kpad, ui
 template <int MODE>
 int launch_chain(const CUtensorMap& tw1, const CUtensorMap& tw2, const CUtensorMap& tx, const ChainArgs& a, cudaStream_t st) {
     constexpr int smem = chain_smem_bytes<MODE>();
-    static bool attr_set = false;
-    if (!attr_set) {
-        SEEVCN_CUDA_CHECK(cudaFuncSetAttribute(vcn_chain_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        attr_set = true;
-    }
-    const int grid = a.num_tiles < SEEVCN_NUM_SMS ? a.num_tiles : SEEVCN_NUM_SMS;
+    // per device and cheap: set on every launch (a process-wide "done" flag would skip the second GPU of a process)
+    SEEVCN_CUDA_CHECK(cudaFuncSetAttribute(vcn_chain_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    const int grid = a.num_tiles < seevcn_num_sms() ? a.num_tiles : seevcn_num_sms();
     ChainArgs b = a;
     static int dbg = -1;
     if (dbg < 0) { const char* e = getenv("SEEVCN_CHAIN_DBG"); dbg = e ? atoi(e) : 0; }

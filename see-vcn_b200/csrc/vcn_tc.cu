@@ -302,11 +302,8 @@ int vcn_linear_tc(const LinearW& L, int rows, const __nv_bfloat16* X, int ldx, c
     if (rows == 0) return SEEVCN_OK;
     SEEVCN_REQUIRE(L.kpad % BK == 0 && ldx >= L.kpad, "vcn_linear_tc: K=%d must be padded to %d (ldx %d)", L.cin, BK, ldx);
     SEEVCN_REQUIRE((reinterpret_cast<uintptr_t>(X) & 15) == 0 && (ldx * 2) % 16 == 0, "vcn_linear_tc: X not 16-byte aligned");
-    static bool attr_set = false;
-    if (!attr_set) {
-        SEEVCN_CUDA_CHECK(cudaFuncSetAttribute(vcn_linear_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-        attr_set = true;
-    }
+    // per device and cheap: set on every launch (a process-wide "done" flag would skip the second GPU of a process)
+    SEEVCN_CUDA_CHECK(cudaFuncSetAttribute(vcn_linear_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
     CUtensorMap tw, tx;
     int rc = make_tmap(&tw, L.w16, (uint64_t)L.cout, (uint64_t)L.kpad, (uint64_t)L.kpad, BM);
     if (rc != SEEVCN_OK) return rc;
@@ -318,7 +315,7 @@ int vcn_linear_tc(const LinearW& L, int rows, const __nv_bfloat16* X, int ldx, c
     a.num_tiles = a.num_m_tiles * div_up(rows, BN);
     a.bias = L.b; a.obj_bias = obj_bias; a.Y = Y; a.ldy = ldy; a.Yf32 = Yf32; a.ldyf = L.cout; a.colmax = colmax;
     a.ksplit = 1; a.kb_per_split = a.kblocks; a.part = nullptr;
-    const int grid = a.num_tiles < SEEVCN_NUM_SMS ? a.num_tiles : SEEVCN_NUM_SMS;
+    const int grid = a.num_tiles < seevcn_num_sms() ? a.num_tiles : seevcn_num_sms();
     vcn_linear_tc_kernel<<<grid, NUM_THREADS, SMEM_BYTES, st>>>(tw, tx, a);
     SEEVCN_LAUNCH_CHECK();
     return SEEVCN_OK;
@@ -362,7 +359,7 @@ fc_reduce_kernel(int rows, int cout, int ksplit, const float* __restrict__ part,
 
 static int fc_ksplit(int rows, int cout, int kblocks, int* kb_per_split) {
     const int mn = div_up(cout, BM) * div_up(rows, BN);
-    int ksplit = SEEVCN_NUM_SMS / mn;                       // fill the machine once
+    int ksplit = seevcn_num_sms() / mn;                       // fill the machine once
     ksplit = ksplit < 1 ? 1 : ksplit > 16 ? 16 : ksplit;
     ksplit = ksplit > kblocks ? kblocks : ksplit;
     *kb_per_split = div_up(kblocks, ksplit);
@@ -379,11 +376,8 @@ int vcn_fc_tc(const LinearW& L, int rows, const __nv_bfloat16* X, int ldx, int a
               float* part, cudaStream_t st) {
     if (rows == 0) return SEEVCN_OK;
     SEEVCN_REQUIRE(L.kpad % BK == 0 && ldx >= L.kpad && L.cout % 4 == 0, "vcn_fc_tc: bad layer shape");
-    static bool attr_set = false;
-    if (!attr_set) {
-        SEEVCN_CUDA_CHECK(cudaFuncSetAttribute(vcn_linear_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-        attr_set = true;
-    }
+    // per device and cheap: set on every launch (a process-wide "done" flag would skip the second GPU of a process)
+    SEEVCN_CUDA_CHECK(cudaFuncSetAttribute(vcn_linear_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
     CUtensorMap tw, tx;
     int rc = make_tmap(&tw, L.w16, (uint64_t)L.cout, (uint64_t)L.kpad, (uint64_t)L.kpad, BM);
     if (rc != SEEVCN_OK) return rc;
@@ -396,7 +390,7 @@ int vcn_fc_tc(const LinearW& L, int rows, const __nv_bfloat16* X, int ldx, int a
     a.ksplit = fc_ksplit(rows, L.cout, a.kblocks, &a.kb_per_split);
     a.num_tiles = mn * a.ksplit;
     a.part = part;
-    const int grid = a.num_tiles < SEEVCN_NUM_SMS ? a.num_tiles : SEEVCN_NUM_SMS;
+    const int grid = a.num_tiles < seevcn_num_sms() ? a.num_tiles : seevcn_num_sms();
     vcn_linear_tc_kernel<<<grid, NUM_THREADS, SMEM_BYTES, st>>>(tw, tx, a);
     SEEVCN_LAUNCH_CHECK();
     const int total = rows * (L.cout / 4);

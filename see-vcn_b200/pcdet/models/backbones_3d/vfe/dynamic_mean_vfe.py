@@ -1,4 +1,4 @@
-"""DynamicMeanVFE on the B200 path: sort-free hashed scatter-mean.
+"""DynamicMeanVFE on the B200 path: sort-free bucketed scatter-mean (rows in torch.unique order, deterministic means).
 
 ref: detector3d/pcdet/models/backbones_3d/vfe/dynamic_mean_vfe.py:14-76
 """
@@ -12,7 +12,8 @@ def dynamic_voxelize(points, point_cloud_range, voxel_size, grid_size, max_voxel
                      batch_size=0):
     """points (N, 1+C) float32 CUDA rows [batch_idx, x, y, z, ...] ->
     voxel_coords (M, 4) int32 [b, z, y, x], voxel_features (M, C) float32, voxel_counts (M,) int32.
-    ``sort=True`` orders rows by the reference's merge key (torch.unique order)."""
+    Rows always come out ordered by the reference's merge key (torch.unique order); ``sort`` is ignored.
+    ``batch_size`` = batch_dict['batch_size']; 0 derives it from the batch column (one extra host sync)."""
     points = points.contiguous()
     _abi.require_cuda(points)
     assert points.dtype == torch.float32 and points.dim() == 2
@@ -22,7 +23,11 @@ def dynamic_voxelize(points, point_cloud_range, voxel_size, grid_size, max_voxel
     if max_voxels is None:
         max_voxels = max(N, 1)
     L = _abi.lib()
-    ws_bytes = L.seevcn_dynamic_voxelize_workspace_bytes(N, C, max_voxels)
+    if int(batch_size) <= 0:
+        batch_size = int(points[:, 0].max().item()) + 1 if N > 0 else 1
+    ws_bytes = L.seevcn_dynamic_voxelize_workspace_bytes(N, C, int(batch_size), _abi.iarray(grid_size))
+    if ws_bytes == 0:
+        raise RuntimeError("dynamic_voxelize: batch_size x grid too large")
     if workspace is None or workspace.numel() < ws_bytes:
         workspace = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
     coords = torch.empty((max_voxels, 4), dtype=torch.int32, device=dev)
@@ -45,9 +50,8 @@ def dynamic_voxelize_frames(frame_pts, obj_pts, obj_frame, point_cloud_range, vo
     built.  After the splice step (SEE_VCN.py:247-265): ``frame_keep`` (F,P) uint8 drops the replaced frame points and
     ``obj_count`` (O,) int32 limits every object to its distinct rows.  No host sync: returns FULL-capacity tensors
     plus the device scalar M — (coords (N,4), feats (N,3), counts (N,), num_voxels (1,) int32 CUDA); rows >= M are
-    undefined.  ``max_voxels``: row capacity of the outputs (default: one row per point, which can never overflow); with a
-    smaller capacity the sort / permute passes shrink with it, rows beyond it are dropped and ``num_voxels`` still
-    reports the true M, so the caller can detect the overflow and call again."""
+    undefined.  ``max_voxels``: row capacity of the outputs (default: one row per point, which can never overflow); rows
+    beyond a smaller capacity are dropped and ``num_voxels`` still reports the true M."""
     frame_pts = frame_pts.contiguous()
     _abi.require_cuda(frame_pts)
     F, P, _ = frame_pts.shape
@@ -71,7 +75,7 @@ def dynamic_voxelize_frames(frame_pts, obj_pts, obj_frame, point_cloud_range, vo
     N = F * P + O * S
     L = _abi.lib()
     cap = max(N, 1) if max_voxels is None else max(min(int(max_voxels), N), 1)
-    ws = _abi.workspace(dev, L.seevcn_dynamic_voxelize_workspace_bytes(N, 3, cap), "dynvox")
+    ws = _abi.workspace(dev, L.seevcn_dynamic_voxelize_workspace_bytes(N, 3, max(F, 1), _abi.iarray(grid_size)), "dynvox")
     coords = torch.empty((cap, 4), dtype=torch.int32, device=dev)
     feats = torch.empty((cap, 3), dtype=torch.float32, device=dev)
     counts = torch.empty((cap,), dtype=torch.int32, device=dev)

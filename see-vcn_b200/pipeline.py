@@ -46,7 +46,6 @@ class CompletionPipeline:
         self.host_rng = host_rng              # True: numpy permutation per object on the host (reference's draw)
         self.cluster_eps = cluster_eps        # SURFACE_COMPLETION.VCN.CLUSTER_EPS; None skips the largest-cluster filter
         self._pinned_in_flight = []
-        self._vox_seen = 0                    # largest voxel count seen so far (sizes the voxel outputs of later batches)
         self.splice_thresh = splice_thresh    # replace_with_completed_pts point_dist_thresh (SEE_VCN.py:247); None = no splice
 
     def _to_host_async(self, t):
@@ -129,8 +128,10 @@ class CompletionPipeline:
                                                     return_count=True)
         out.update(input=inp, coarse=coarse, surface=surface, surface_count=sel_count, obj_frame_dev=obj_frame)
         if self.cluster_eps is not None:   # models/VCN.py:95-98
-            out["clustered"], out["clustered_count"] = get_largest_cluster_batch(
-                surface, eps=self.cluster_eps, min_points=2, total_pts=coarse.shape[1], period=sel_count, return_count=True)
+            # clustered_count: member rows of the tiled cloud (bincount size); clustered_distinct: the rows np.unique keeps
+            out["clustered"], out["clustered_count"], out["clustered_distinct"] = get_largest_cluster_batch(
+                surface, eps=self.cluster_eps, min_points=2, total_pts=coarse.shape[1], period=sel_count, return_count=True,
+                return_distinct=True)
         return out
 
     # ---- stage B: complete + voxelize.  The number of voxels M is data dependent; it travels to the host on the side
@@ -145,19 +146,13 @@ class CompletionPipeline:
         if self.splice_thresh is not None and completed.shape[0] > 0:
             # SEE_VCN.py:244,247-265: the frame the detector sees = distinct completed points ++ raw points farther
             # than thresh from all of them.  The mask feeds the voxelizer directly; the merged cloud is not built.
-            count = out.get("clustered_count", out.get("surface_count"))
+            count = out.get("clustered_distinct", out.get("surface_count"))    # distinct rows only (SEE_VCN.py:113,244)
             keep = splice_frames(points, completed, out["obj_frame_dev"], count, self.splice_thresh)
             out["frame_keep"], out["completed_count"] = keep, count
-        # Output capacity: the number of voxels M is only known after the fact; sizing the outputs (and the radix sort over
-        # them) for one voxel per point wastes 3/4 of those passes on a LiDAR frame.  Capacity = 2x the largest M seen
-        # so far (first call: every point); finalize() re-runs the rare batch that overflows with full capacity.
-        n_rows = F * P + completed.shape[0] * completed.shape[1]
-        cap = n_rows if self._vox_seen == 0 else min(n_rows, max(2 * self._vox_seen, 1 << 16))
-        vox_args = (points, completed, out.get("obj_frame_dev"), keep, count)
+        # The number of voxels M is only known after the fact: the outputs have room for one voxel per row (allocation
+        # only; the voxelizer's passes scale with the rows and the voxels that exist, not with the capacity).
         coords, feats, nums, num_dev = dynamic_voxelize_frames(points, completed, out.get("obj_frame_dev"), *self.voxel_cfg,
-                                                              sort=True, frame_keep=keep, obj_count=count, max_voxels=cap)
-        out["_vox_args"], out["_vox_cap"] = vox_args, cap
-        out["num_voxel_points"] = F * P + completed.shape[0] * completed.shape[1]
+                                                              frame_keep=keep, obj_count=count)
         out["_frame_points"] = points
         out["_vox_full"] = (coords, feats, nums, num_dev)
         out["_h_num"], out["_num_done"] = self._to_host_async(num_dev)
@@ -170,17 +165,7 @@ class CompletionPipeline:
         if "_vox_full" in out:
             coords, feats, nums, _ = out.pop("_vox_full")
             out["_num_done"].synchronize()
-            m = int(out["_h_num"][0])
-            pts_, comp_, ofr_, keep_, cnt_ = out.pop("_vox_args")
-            if m > out["_vox_cap"]:     # more voxels than the capacity guessed from earlier batches: redo with room for all
-                with torch.cuda.device(self.device):
-                    coords, feats, nums, num_dev = dynamic_voxelize_frames(pts_, comp_, ofr_, *self.voxel_cfg, sort=True,
-                                                                          frame_keep=keep_, obj_count=cnt_)
-                    m = int(num_dev.item())
-                    out["_done"] = torch.cuda.Event()
-                    out["_done"].record(torch.cuda.current_stream(self.device))
-            self._vox_seen = max(self._vox_seen, m)
-            m = min(m, coords.shape[0])
+            m = min(int(out["_h_num"][0]), coords.shape[0])
             out.update(voxel_coords=coords[:m], voxel_features=feats[:m], voxel_num_points=nums[:m])
         return out
 

@@ -26,7 +26,7 @@ def test_header_symbols_are_exported_and_bound():
 
 def test_version_and_error_string():
     L = _abi.lib()
-    assert L.seevcn_abi_version() == 1
+    assert L.seevcn_abi_version() == 2
     # argument validation happens before any CUDA call: safe without a GPU
     rc = L.seevcn_knn(1, 8, 8, 100, None, None, None, None, None)
     assert rc == 1 and b"outside [1,64]" in L.seevcn_last_error()

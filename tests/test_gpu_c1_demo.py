@@ -65,15 +65,19 @@ def test_c1_demo_frame_end_to_end(cuda):
     np.testing.assert_array_equal(out["surface"].cpu().numpy(), surf)
     clus, ccnt = oracle.get_largest_cluster_batch(surf, eps=0.3, min_points=2, total_pts=1024)
     np.testing.assert_array_equal(out["clustered"].cpu().numpy(), clus)
-    np.testing.assert_array_equal(out["completed_count"].cpu().numpy(), ccnt)
+    np.testing.assert_array_equal(out["clustered_count"].cpu().numpy(), ccnt)
+    dcnt = oracle.distinct_rows(clus, ccnt)                             # what np.unique keeps (SEE_VCN.py:113,244)
+    np.testing.assert_array_equal(out["completed_count"].cpu().numpy(), dcnt)
+    assert (dcnt < ccnt).any()                                          # tiled clouds: fewer distinct rows than rows
     # splice: the merged frame the reference would save as .pcd (SEE_VCN.py:247-280)
     keep, merged, m_cnt, c_cnt = splice_frames(d_pts, out["clustered"], out["obj_frame_dev"], out["completed_count"], 0.1, merged=True)
-    sc = np.concatenate([clus[o][: ccnt[o]] for o in range(len(clus))])
+    sc = np.concatenate([clus[o][: dcnt[o]] for o in range(len(clus))])
+    assert len(sc) == len(oracle.all_instances(clus, ccnt))            # same rows as the reference's np.unique, object order
     want_merged, want_keep = oracle.replace_with_completed_pts(pts, sc, 0.1)
     np.testing.assert_array_equal(keep[0].cpu().numpy().astype(bool), want_keep)
     frame = merged[0, : int(m_cnt[0])].cpu().numpy()
     np.testing.assert_array_equal(frame, want_merged)
-    assert int(c_cnt[0]) == ccnt.sum() and 0 < (~want_keep).sum() < len(pts)
+    assert int(c_cnt[0]) == dcnt.sum() and 0 < (~want_keep).sum() < len(pts)
     # detector front end of the KITTI configs: hard voxel generator + MeanVFE (data_processor.py:15-60, mean_vfe.py:14-31)
     gen = VoxelGeneratorWrapper(KITTI[1], KITTI[0], 3, 5, 16000)
     v, c, n = gen.generate(frame)

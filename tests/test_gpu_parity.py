@@ -3,6 +3,7 @@ oracle on the same seeded inputs, against the committed goldens, against the ref
 kernels compiled for sm_100a (oracle/_ref, when present), and size-independent properties at
 BASELINE.json's full sizes.  Run with `pytest -m gpu`."""
 import ctypes
+import os
 
 import numpy as np
 import pytest
@@ -295,14 +296,22 @@ def test_largest_cluster_periodic_vs_oracle(cuda, scale):
     pc[4, 990:1000] = 500.0 + 3.0 * np.arange(10, dtype=np.float32)[:, None]
     pc[4] = np.tile(pc[4, :1000], (2, 1))[:1024]
     for eps, mp, total in ((0.3, 2, 1024), (0.2, 1, 1024), (0.3, 2, 2500)):
-        out, cnt = get_largest_cluster_batch(dev(pc, cuda), eps=eps, min_points=mp, total_pts=total, return_count=True,
-                                             period=dev(periods, cuda))
+        out, cnt, dis = get_largest_cluster_batch(dev(pc, cuda), eps=eps, min_points=mp, total_pts=total, return_count=True,
+                                                  period=dev(periods, cuda), return_distinct=True)
         plain, pcnt = get_largest_cluster_batch(dev(pc, cuda), eps=eps, min_points=mp, total_pts=total, return_count=True)
         want, wcnt = oracle.get_largest_cluster_batch(pc, eps=eps, min_points=mp, total_pts=total)
         np.testing.assert_array_equal(pcnt.cpu().numpy(), wcnt)
         np.testing.assert_array_equal(plain.cpu().numpy(), want)
         np.testing.assert_array_equal(cnt.cpu().numpy(), wcnt)
         np.testing.assert_array_equal(out.cpu().numpy(), want)
+        # distinct member rows = what np.unique(clustered) keeps (SEE_VCN.py:113,244); with period << 1024 far fewer than cnt
+        wdis = oracle.distinct_rows(want, np.minimum(wcnt, total))
+        np.testing.assert_array_equal(dis.cpu().numpy(), wdis)
+        assert (wdis[:3] < wcnt[:3]).all()
+        for b in range(len(pc)):   # and they are exactly the leading rows of the output
+            lead = out[b, : int(dis[b])].cpu().numpy()
+            assert len(np.unique(lead, axis=0)) == len(lead)
+            np.testing.assert_array_equal(np.unique(lead, axis=0), np.unique(want[b][: min(int(wcnt[b]), total)], axis=0))
 
 
 def test_vcn_inference_wrapper(cuda, golden):
@@ -483,11 +492,71 @@ def test_dynamic_voxelize_vs_oracle(cuda, nframes):
     np.testing.assert_array_equal(out["voxel_num_points"].cpu().numpy(), want_n)
     np.testing.assert_allclose(out["voxel_features"].cpu().numpy(), want_f, rtol=1e-5, atol=1e-5)
     assert len(want_c) > 50000
-    # unsorted (hash order) output is the same set of rows
+    # sort=False is accepted and ignored: rows always come out in the reference's order; batch_size derived from the rows
     c, f, n = dynamic_voxelize(dev(points, cuda), *WAYMO, sort=False)
-    order = np.lexsort(c.cpu().numpy()[:, [1, 2, 3, 0]].T)   # lexsort: last key is primary -> b, x, y, z (coords are b,z,y,x)
-    np.testing.assert_array_equal(c.cpu().numpy()[order], want_c)
-    np.testing.assert_array_equal(n.cpu().numpy()[order], want_n)
+    np.testing.assert_array_equal(c.cpu().numpy(), want_c)
+    np.testing.assert_array_equal(n.cpu().numpy(), want_n)
+    # bit-reproducible: integer accumulation does not depend on the order the points arrive in
+    np.testing.assert_array_equal(f.cpu().numpy(), out["voxel_features"].cpu().numpy())
+    perm = np.random.default_rng(0).permutation(len(points))
+    c2, f2, n2 = dynamic_voxelize(dev(points[perm], cuda), *WAYMO, batch_size=nframes)
+    np.testing.assert_array_equal(c2.cpu().numpy(), want_c)
+    np.testing.assert_array_equal(f2.cpu().numpy(), f.cpu().numpy())
+
+
+def test_dynamic_voxelize_vs_reference_module_golden(cuda):
+    """a9 pinned by the reference's own code: tests/golden/make_golden_dynvfe.py executed DynamicMeanVFE.forward
+    (dynamic_mean_vfe.py:37-76; scatter_mean stubbed by index_add_/bincount) and committed its outputs."""
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "golden_dynvfe_v1.npz"))
+    KITTI = ([0.0, -40.0, -3.0, 70.4, 40.0, 1.0], [0.1, 0.1, 0.15], [704, 800, 27])
+    for tag, cfg, c in (("A", WAYMO, 3), ("B", KITTI, 5)):
+        vfe = DynamicMeanVFE({}, c, cfg[1], cfg[2], cfg[0])
+        assert vfe.get_output_feature_dim() == c
+        out = vfe({"points": dev(g[f"{tag}_points"], cuda), "batch_size": 2})
+        np.testing.assert_array_equal(out["voxel_coords"].cpu().numpy(), g[f"{tag}_voxel_coords"])
+        np.testing.assert_allclose(out["voxel_features"].cpu().numpy(), g[f"{tag}_voxel_features"], rtol=1e-5, atol=1e-6)
+
+
+@pytest.mark.parametrize("logw", [10, 12, 16])
+def test_dynamic_voxelize_bucket_widths(cuda, logw, monkeypatch):
+    """Every bucket width the kernels support gives the same rows (SEEVCN_VOX_LOGW is the tuning knob)."""
+    monkeypatch.setenv("SEEVCN_VOX_LOGW", str(logw))
+    pts, _ = synth.make_stream(2, n_beams=32, n_az=1090, n_boxes=10)
+    points = np.concatenate([np.concatenate([np.full((pts.shape[1], 1), b, np.float32), pts[b]], axis=1) for b in range(2)])
+    want_c, want_f, want_n = oracle.dynamic_voxelize(points, *WAYMO)
+    c, f, n = dynamic_voxelize(dev(points, cuda), *WAYMO, batch_size=2)
+    np.testing.assert_array_equal(c.cpu().numpy(), want_c)
+    np.testing.assert_array_equal(n.cpu().numpy(), want_n)
+    np.testing.assert_allclose(f.cpu().numpy(), want_f, rtol=1e-6, atol=1e-6)
+
+
+def test_dynamic_voxelize_dense_voxels_vs_float64_mean(cuda):
+    """Thousands of points in one voxel (what a collapsed completed cloud produces): the mean equals the float64 mean
+    at 1e-6 and is identical run to run; more voxels in a bucket than one accumulation pass holds; voxel cap."""
+    rng = np.random.default_rng(5)
+    blobs = []
+    for centre, n in (((61.234, -33.71, 1.03), 6000), ((-70.01, 74.9, -1.9), 4500), ((0.01, 0.02, 0.03), 5000)):
+        lo = np.floor((np.array(centre) - WAYMO[0][:3]) / WAYMO[1]) * WAYMO[1] + WAYMO[0][:3]
+        blobs.append(lo + rng.uniform(0.001, 0.999, (n, 3)) * WAYMO[1])
+    # 700 occupied voxels inside one 16384-key bucket (a y run at fixed x): several accumulation passes of 64 rows
+    run = np.stack([np.full(2100, 10.03), -20.0 + 0.1 * (np.arange(2100) % 700) + 0.05, np.full(2100, 0.51)], axis=1)
+    run += rng.uniform(-0.02, 0.02, run.shape)
+    xyz = np.concatenate(blobs + [run]).astype(np.float32)
+    points = np.concatenate([np.zeros((len(xyz), 1), np.float32), xyz], axis=1)
+    points = points[rng.permutation(len(points))]
+    want_c, want_f, want_n = oracle.dynamic_voxelize(points, *WAYMO)          # float64 sums
+    assert want_n.max() >= 4096
+    c, f, n = dynamic_voxelize(dev(points, cuda), *WAYMO, batch_size=1)
+    np.testing.assert_array_equal(c.cpu().numpy(), want_c)
+    np.testing.assert_array_equal(n.cpu().numpy(), want_n)
+    np.testing.assert_allclose(f.cpu().numpy(), want_f, rtol=1e-6, atol=1e-7)
+    for _ in range(3):
+        c2, f2, n2 = dynamic_voxelize(dev(points, cuda), *WAYMO, batch_size=1)
+        np.testing.assert_array_equal(f2.cpu().numpy(), f.cpu().numpy())
+    # capacity: rows beyond max_voxels are dropped, the leading rows are the same
+    c3, f3, n3 = dynamic_voxelize(dev(points, cuda), *WAYMO, batch_size=1, max_voxels=100)
+    np.testing.assert_array_equal(c3.cpu().numpy(), want_c[:100])
+    np.testing.assert_array_equal(f3.cpu().numpy(), f.cpu().numpy()[:100])
 
 
 def test_dynamic_voxelize_frames_matches_concatenated_matrix(cuda):
@@ -549,7 +618,7 @@ def test_dynamic_voxelize_properties_full_size(cuda):
     """C5-size: counts sum to the in-range points, means lie inside their voxel, voxels are unique."""
     pts, _ = synth.make_stream(8)
     points = np.concatenate([np.concatenate([np.full((pts.shape[1], 1), b, np.float32), pts[b]], axis=1) for b in range(8)])
-    c, f, n = dynamic_voxelize(dev(points, cuda), *WAYMO, sort=False)
+    c, f, n = dynamic_voxelize(dev(points, cuda), *WAYMO, batch_size=8)
     c, f, n = c.cpu().numpy(), f.cpu().numpy(), n.cpu().numpy()
     lo, vs, gs = np.array(WAYMO[0][:3], np.float32), np.array(WAYMO[1], np.float32), np.array(WAYMO[2])
     pc = np.floor((points[:, 1:4] - lo) / vs)

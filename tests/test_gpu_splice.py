@@ -135,6 +135,30 @@ def test_splice_candidate_queue_overflow(cuda):
         np.testing.assert_array_equal(merged[f, : int(m_cnt[f])].cpu().numpy(), want_merged[f])
 
 
+def test_splice_candidate_queue_overflow_ragged(cuda):
+    """Ragged ballots: only ~70% of the points lie inside each of six object bounds, so the warps' queue reservations
+    are not multiples of 32 and one of them straddles the end of the 2048-entry queue (round-1 advisor finding: the
+    straddling warp used to leave unwritten slots that the consumer loop then read)."""
+    rng = np.random.default_rng(33)
+    pts = rng.uniform(0, 1, (2, 1500, 3)).astype(np.float32)
+    objs = []
+    for o in range(12):
+        lo = rng.uniform(-0.1, 0.15, 3); hi = rng.uniform(0.8, 1.1, 3)
+        corners = np.array([[x, y, z] for x in (lo[0], hi[0]) for y in (lo[1], hi[1]) for z in (lo[2], hi[2])], np.float32)
+        near = pts[o // 6, rng.integers(0, 1500, 56)] + rng.normal(0, 0.03, (56, 3)).astype(np.float32)
+        objs.append(np.concatenate([corners, near]))
+    objs = np.stack(objs).astype(np.float32)
+    frame = np.repeat(np.arange(2), 6).astype(np.int32)
+    inside = [((pts[0] >= o[:8].min(0) - 0.1) & (pts[0] <= o[:8].max(0) + 0.1)).all(1).sum() for o in objs[:6]]
+    assert sum(inside) > 2048 + 1024 and any(c % 32 for c in inside)
+    want_keep, want_merged = _want(pts, objs, frame, None, 0.1)
+    for _ in range(3):
+        keep, merged, m_cnt, _c = splice_frames(dev(pts, cuda), dev(objs, cuda), dev(frame, cuda), None, 0.1, merged=True)
+        np.testing.assert_array_equal(keep.cpu().numpy().astype(bool), want_keep)
+    for f in range(2):
+        np.testing.assert_array_equal(merged[f, : int(m_cnt[f])].cpu().numpy(), want_merged[f])
+
+
 def test_replace_with_completed_pts_reference_entry(cuda):
     rng = np.random.default_rng(8)
     pts = rng.uniform(-10, 10, (5000, 3)).astype(np.float32)
@@ -195,21 +219,18 @@ def test_pipeline_with_splice_voxelizes_the_merged_frame(cuda):
     np.testing.assert_allclose(out["voxel_features"].cpu().numpy(), vf, rtol=1e-5, atol=1e-5)
 
 
-def test_pipeline_voxel_capacity_overflow_is_redone(cuda):
-    """The voxel outputs are sized from the voxel counts of earlier batches; a batch with more voxels than that is
-    voxelized again with full capacity: same result as a pipeline that never guessed."""
+def test_pipeline_voxels_are_bit_reproducible(cuda):
+    """Two runs of the whole pipeline give bit-identical voxel tensors: the scatter-mean accumulates integers relative
+    to the voxel origin, so the arrival order of the points (atomics) cannot show (round 1 summed absolute fp32
+    coordinates and differed by ~1e-6 relative between runs on voxels holding thousands of completed points)."""
     from seevcn_b200.pipeline import CompletionPipeline
     sd = oracle.make_state_dict("VCN_VC", seed=0)
     pts, boxes = synth.make_stream(2, first_seed=1000)
     d_pts, d_boxes = dev(pts, cuda), dev(boxes, cuda)
-    ref = CompletionPipeline("VCN_VC", sd, cuda, sel_k=10, cluster_eps=0.3, splice_thresh=0.1).run(d_pts, d_boxes, seed=0)
     pipe = CompletionPipeline("VCN_VC", sd, cuda, sel_k=10, cluster_eps=0.3, splice_thresh=0.1)
-    pipe._vox_seen = 10                                    # as if every earlier batch had been almost empty
-    out = pipe.run(d_pts, d_boxes, seed=0)
-    assert out["_vox_cap"] == 1 << 16 < ref["voxel_coords"].shape[0]
-    for key in ("voxel_coords", "voxel_num_points"):
-        np.testing.assert_array_equal(out[key].cpu().numpy(), ref[key].cpu().numpy())
-    np.testing.assert_allclose(out["voxel_features"].cpu().numpy(), ref["voxel_features"].cpu().numpy(), rtol=1e-6, atol=1e-6)
-    again = pipe.run(d_pts, d_boxes, seed=0)               # now sized from what it has seen: no redo, same rows
-    assert again["_vox_cap"] == 2 * ref["voxel_coords"].shape[0]
-    np.testing.assert_array_equal(again["voxel_coords"].cpu().numpy(), ref["voxel_coords"].cpu().numpy())
+    ref = pipe.run(d_pts, d_boxes, seed=0)
+    assert int(ref["voxel_num_points"].max()) > 100        # collapsed completed clouds: many points per voxel
+    for _ in range(3):
+        out = pipe.run(d_pts, d_boxes, seed=0)
+        for key in ("voxel_coords", "voxel_num_points", "voxel_features"):
+            np.testing.assert_array_equal(out[key].cpu().numpy(), ref[key].cpu().numpy())

@@ -1,5 +1,7 @@
 """The oracle against the golden vectors produced by executing the reference itself
 (tests/golden/make_golden.py), plus internal consistency checks.  CPU only."""
+import os
+
 import numpy as np
 import pytest
 import torch
@@ -129,6 +131,19 @@ def test_dynamic_voxelize_matches_torch_restatement():
     np.testing.assert_array_equal(n0, n1)
     np.testing.assert_allclose(f0, f1, rtol=1e-5, atol=1e-5)
     assert len(c0) > 1000 and n0.sum() < len(points)   # some points fall outside z range
+
+
+def test_dynamic_voxelize_matches_reference_module():
+    """oracle.dynamic_voxelize against the reference's own DynamicMeanVFE.forward (dynamic_mean_vfe.py:37-76), executed
+    by tests/golden/make_golden_dynvfe.py: coords bit-exact in torch.unique order, means at the north-star 1e-5."""
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "golden_dynvfe_v1.npz"))
+    for tag, cfg in (("A", ([-75.2, -75.2, -2.0, 75.2, 75.2, 4.0], [0.1, 0.1, 0.15], [1504, 1504, 40])),
+                     ("B", ([0.0, -40.0, -3.0, 70.4, 40.0, 1.0], [0.1, 0.1, 0.15], [704, 800, 27]))):
+        c, f, n = oracle.dynamic_voxelize(g[f"{tag}_points"], *cfg)
+        np.testing.assert_array_equal(c, g[f"{tag}_voxel_coords"])
+        np.testing.assert_allclose(f, g[f"{tag}_voxel_features"], rtol=1e-5, atol=1e-6)
+        assert n.sum() < len(g[f"{tag}_points"]) or tag == "A"      # B has points outside the range
+    assert n.max() >= 10                                            # B: many points per voxel
 
 
 def test_hard_voxelize_semantics():
