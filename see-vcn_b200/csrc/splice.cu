@@ -102,7 +102,7 @@ splice_mask_kernel(int pts_per_frame, const float* __restrict__ frame_pts, int n
     __shared__ __align__(16) float s_pts[kTilePts * 3 + 8];
     __shared__ ObjBound s_obj[kObjChunk];
     __shared__ unsigned s_work[kWorkCap];          // candidate (point, object) pairs of the tile: (point << 8) | object
-    __shared__ unsigned char s_removed[kTilePts];
+    __shared__ unsigned s_removed[kTilePts / 32];   // bit i: point i of the tile is replaced (set with atomicOr only)
     __shared__ int s_range[2];
     __shared__ int s_nwork;
     __shared__ int s_cnt[kThreads / 32];
@@ -112,7 +112,7 @@ splice_mask_kernel(int pts_per_frame, const float* __restrict__ frame_pts, int n
     const int npts = min(kTilePts, pts_per_frame - p0);
     const float* src = frame_pts + ((size_t)f * pts_per_frame + p0) * 3;
     const int mis = stage_floats(s_pts, src, npts * 3);
-    for (int i = threadIdx.x; i < kTilePts; i += kThreads) s_removed[i] = 0;
+    for (int i = threadIdx.x; i < kTilePts / 32; i += kThreads) s_removed[i] = 0u;
     if (threadIdx.x == 0) s_range[0] = lower_bound_frame(bounds, num_obj, f);
     if (threadIdx.x == 32) s_range[1] = lower_bound_frame(bounds, num_obj, f + 1);
     __syncthreads();
@@ -185,7 +185,7 @@ splice_mask_kernel(int pts_per_frame, const float* __restrict__ frame_pts, int n
                         const float y = __shfl_sync(0xffffffffu, py[e], src_lane);
                         const float z = __shfl_sync(0xffffffffu, pz[e], src_lane);
                         const bool near = warp_near_object(x, y, z, rows, b.count, t2_in, t2_out, thresh);
-                        if (near && lane_id() == src_lane) s_removed[i] = 1;
+                        if (near && lane_id() == src_lane) atomicOr(&s_removed[i >> 5], 1u << (i & 31));
                     }
                 }
             }
@@ -195,11 +195,11 @@ splice_mask_kernel(int pts_per_frame, const float* __restrict__ frame_pts, int n
         for (int w = warp_id(); w < nwork; w += kThreads / 32) {
             const unsigned ent = s_work[w];
             const int i = (int)(ent >> 8), j = (int)(ent & 255u);
-            if (*reinterpret_cast<volatile unsigned char*>(&s_removed[i])) continue;   // another object already replaced it
+            if ((atomicOr(&s_removed[i >> 5], 0u) >> (i & 31)) & 1u) continue;   // another object already replaced it (warp-uniform)
             const float x = s_pts[mis + i * 3], y = s_pts[mis + i * 3 + 1], z = s_pts[mis + i * 3 + 2];
             const bool near = warp_near_object(x, y, z, obj_pts + (size_t)(c0 + j) * pts_per_obj * 3, s_obj[j].count, t2_in,
                                                t2_out, thresh);
-            if (near && lane_id() == 0) s_removed[i] = 1;
+            if (near && lane_id() == 0) atomicOr(&s_removed[i >> 5], 1u << (i & 31));
         }
     }
     __syncthreads();
@@ -209,7 +209,7 @@ splice_mask_kernel(int pts_per_frame, const float* __restrict__ frame_pts, int n
     for (int e = 0; e < kPtsPerThread; ++e) {
         const int i = wbase + e * 32;
         if (i < npts) {
-            const unsigned k = s_removed[i] ? 0u : 1u;
+            const unsigned k = ((s_removed[i >> 5] >> (i & 31)) & 1u) ? 0u : 1u;
             keep[(size_t)f * pts_per_frame + p0 + i] = (unsigned char)k;
             kept += (int)k;
         }

@@ -33,6 +33,14 @@ def main():
     for r in sorted(s["rows"], key=lambda r: -f(r, "# Samples"))[:top]:
         print("%6.2f%% smp %6.2f%% inst thr=%4.1f  %s" % (100 * f(r, "# Samples") / max(tot_s, 1), 100 * f(r, "Instructions Executed") / max(tot_i, 1),
                                                    f(r, "Avg. Threads Executed"), r[h["Source"]].strip()[:90]))
+    print("--- by instructions executed")
+    for r in sorted(s["rows"], key=lambda r: -f(r, "Instructions Executed"))[:top]:
+        print("%6.2f%% smp %6.2f%% inst thr=%4.1f  %s" % (100 * f(r, "# Samples") / max(tot_s, 1), 100 * f(r, "Instructions Executed") / max(tot_i, 1),
+                                                   f(r, "Avg. Threads Executed"), r[h["Source"]].strip()[:90]))
+
+
+def by_inst():
+    pass
 
 
 if __name__ == "__main__":
