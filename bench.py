@@ -1,19 +1,26 @@
 #!/usr/bin/env python
 """bench.py — SEE-VCN object-completion + voxelization hot path on B200.
 
-  python bench.py [--gpus N] [--steps K] [--warmup W] [--frames F] [--impl ours|reference]
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--frames F] [--impl ours|reference] [--config C2|C3|C4|C5]
 
-A step = one pass of the hot path (crop -> resample -> VCN forward -> kNN surface select ->
-largest-cluster filter -> splice (raw points replaced by the completed ones) -> dynamic voxelization) over a batch of F synthetic Waymo-like frames (BASELINE.json configs[1]:
-64 beams x 2812 azimuth steps = 180k pts, 50 car boxes, 1024 pts/object) per GPU.  Frames shard
-across ranks with no collective on the data path; one all-gather-v of the completed clouds per
-step (static capacity, asynchronous, no host sync) stands for "collect for the detector" when N > 1 (weak scaling: F frames per GPU).
+A step = one pass of the hot path (crop -> resample -> VCN forward -> kNN surface select -> largest-cluster filter ->
+splice (raw points replaced by the completed ones) -> voxelization) over one batch of synthetic input per GPU.
+--config selects the BASELINE.json configuration (default C2, the one the headline metric is quoted on):
+  C2  synthetic Waymo-like 64-beam frames (180k pts, 50 boxes, 1024 pts/object), F frames per step and GPU (weak scaling)
+  C3  a batch of 256 nuScenes-like 32-beam frames (35k pts, 20 boxes) frame-sharded over the ranks (strong scaling);
+      a step = the rank's share of the 256 frames, in sub-batches of 32
+  C4  dense-crowd stress: 200 objects x 2048 input points per step and GPU, 16,384-point decoder, FPS 16,384 -> 1,024,
+      kNN surface selection over the 16,384 completed points, largest-cluster filter
+  C5  the pre-detector pipeline of the SECOND-IoU configs: C2 + merged frame clouds -> range mask -> hard voxels
+      (5 pts/voxel, 90k voxels/frame) -> MeanVFE; metric = voxelized Mpts/s
+Frames / objects shard across ranks with no collective on the data path; when N > 1 every step's completed clouds and
+voxel tensors are collected on every rank ("for the detector"): peer-memory copies over NVLink on the copy engines
+(symmetric memory), NCCL all-gather as the fallback.
 
-Prints ONE JSON line (rank 0).  `value` = completed objects/s with inputs resident in HBM;
-`e2e` = same through the public API from pinned HOST buffers (H2D + D2H inside the timed region);
-`roofline` = the dominant kernel (vcn_chain_kernel<2>, the enc2 tcgen05 chain) timed by the library's
-CUDA-event scopes inside the timed region, against the measured bf16 peak; `stages` = every launch
-group the same way; `cpu_baseline` = the oracle port of the same path timed on the host cores.
+Prints ONE JSON line (rank 0).  `value` = the metric with inputs resident in HBM; `e2e` = same through the public API
+from pinned HOST buffers (H2D + D2H inside the timed region); `roofline` = the dominant kernel timed by the library's
+CUDA-event scopes inside the timed region; `stages` = every launch group the same way; `cpu_baseline` = the oracle port
+of the same path timed on the host cores.
 """
 import argparse
 import json
@@ -28,14 +35,32 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-METRIC = "completed objects/sec"
 SEL_K = 20               # SURFACE_COMPLETION.VCN.SEL_K_NEAREST (see/surface_completion/cfgs/WAY-GT_VCN-VC.yaml:13)
 CLUSTER_EPS = 0.3        # SURFACE_COMPLETION.VCN.CLUSTER_EPS   (WAY-GT_VCN-VC.yaml:14)
 SPLICE_THRESH = 0.1      # replace_with_completed_pts(point_dist_thresh=0.1)          (see/surface_completion/SEE_VCN.py:247)
+MIN_LIDAR_PTS = 30       # SURFACE_COMPLETION.MIN_LIDAR_PTS
 RESAMPLE = 1024
+HARD_MAX_PTS, HARD_MAX_VOX = 5, 90000     # sc_waymo_dataset.yaml:39-45 (test split)
 FLOP_PER_OBJ = 2.0 * (959040 * 1024 + 5771776)   # VCN_VC, N = 1024 -> 1.976 GFLOP
+FLOP_PER_OBJ_C4 = 2.0 * (959040 * 2048 + 528896 + 2 * 1024 * 1024 + 1024 * 49152)   # §8d: 4.034 GFLOP
 FLOP_ENC2_REF = 2.0 * (512 * 512 + 512 * 1024) * 1024    # enc2 as the reference graph states it
 FLOP_ENC2_EXEC = 2.0 * (256 * 512 + 512 * 1024) * 1024   # enc2 as executed: the global half folded into a per-object bias
+FP32_TFLOPS = 148 * 128 * 2 * 1.965e9 / 1e12             # fp32 FMA peak of the SMs at the max clock: 74.4 TFLOP/s
+
+CONFIGS = {
+    "C2": {"metric": "completed objects/sec", "unit": "objects/s", "scaling": "weak", "gen": {},
+           "workload": "C2: synthetic Waymo-like 64-beam frame (180k pts, 50 car boxes, 1024 pts/object), random-init VCN_VC"},
+    "C3": {"metric": "completed objects/sec", "unit": "objects/s", "scaling": "strong", "total_frames": 256, "sub_batch": 32,
+           "gen": {"n_beams": 32, "n_az": 1090, "n_boxes": 20, "el_lo": -30.0, "el_hi": 10.0},
+           "workload": "C3: batch of 256 synthetic nuScenes-like 32-beam frames (35k pts, 20 car boxes each) frame-sharded "
+                       "over the ranks, random-init VCN_VC"},
+    "C4": {"metric": "completed objects/sec", "unit": "objects/s", "scaling": "weak", "objects": 200, "n_in": 2048, "n_coarse": 16384,
+           "workload": "C4: dense-crowd stress, 200 objects x 2048 input pts, 16384 completed pts/object (FPS 16384->1024, kNN over "
+                       "16384, largest cluster), random-init VCN_VC with the 16384-point decoder"},
+    "C5": {"metric": "voxelized Mpts/sec", "unit": "Mpts/s", "scaling": "weak", "gen": {},
+           "workload": "C5: SEE-VCN pre-detector pipeline on C2 frames feeding the SECOND-IoU grid (0.1 x 0.1 x 0.15 m): completion + "
+                       "splice + range mask + hard voxels (5 pts/voxel, 90k voxels/frame) + MeanVFE"},
+}
 
 
 def peaks():
@@ -43,8 +68,8 @@ def peaks():
     if os.path.exists(path):
         p = json.load(open(path))
         return {"hbm_gbs": p["hbm_gbs"], "bf16_tflops": p["bf16_tflops"], "bf16_tflops_sustained": p["bf16_tflops_sustained"],
-                "source": "measured"}
-    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "source": "fallback"}
+                "fp32_tflops": FP32_TFLOPS, "source": "measured"}
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "fp32_tflops": FP32_TFLOPS, "source": "fallback"}
 
 
 class ClockSampler(threading.Thread):
@@ -96,16 +121,26 @@ class ClockSampler(threading.Thread):
                 "reasons": sorted(self.reasons), "samples": len(self.sm), "source": self.source}
 
 
-def make_inputs(frames, seed0):
+def make_inputs(frames, seed0, **gen):
     from seevcn_b200 import synth
-    return synth.make_stream(frames, first_seed=seed0)
+    return synth.make_stream(frames, first_seed=seed0, **gen)
+
+
+def frames_per_step(args, cfg, world):
+    """(frames per pipeline batch, pipeline batches per step) on one rank."""
+    if cfg.get("total_frames"):
+        per_rank = cfg["total_frames"] // world
+        sub = min(cfg["sub_batch"], per_rank)
+        return sub, per_rank // sub
+    return args.frames, 1
 
 
 # ---------------------------------------------------------------------------- CPU path --
-def cpu_path_once(pts, boxes, sd, threads):
-    """The oracle port of the whole step on host cores -> (#objects, seconds, #voxelised points)."""
+def cpu_path_frames(pts, boxes, sd, threads, hard_vox=False):
+    """The oracle port of the whole frame step on host cores -> (#objects, seconds, #voxelised points)."""
     import torch
     import oracle
+    from seevcn_b200.pipeline import WAYMO_VOXEL_CFG
     torch.set_num_threads(threads)
     t0 = time.perf_counter()
     idx = oracle.points_in_boxes_gpu(pts, boxes)
@@ -113,7 +148,7 @@ def cpu_path_once(pts, boxes, sd, threads):
     clouds, fid = [], []
     for f in range(pts.shape[0]):
         cnt = np.bincount(idx[f][idx[f] >= 0], minlength=boxes.shape[1])
-        for k in np.nonzero(cnt >= 30)[0]:
+        for k in np.nonzero(cnt >= MIN_LIDAR_PTS)[0]:
             clouds.append(oracle.resample_points(pts[f][idx[f] == k], RESAMPLE, rng)[0]); fid.append(f)
     n_obj = len(clouds)
     frame_sc = [None] * pts.shape[0]
@@ -128,243 +163,346 @@ def cpu_path_once(pts, boxes, sd, threads):
             sel = np.nonzero(fid == f)[0]
             if len(sel):
                 frame_sc[f] = oracle.all_instances(surf[sel], cnt[sel])
-    rows = []
+    rows, n_vox_pts = [], 0
     for f in range(pts.shape[0]):       # SEE_VCN.py:247-265 splice, then the [batch_idx, x, y, z] rows of dataset.py:187-192
         merged, _ = oracle.replace_with_completed_pts(pts[f], frame_sc[f] if frame_sc[f] is not None and len(frame_sc[f]) else None,
                                                       SPLICE_THRESH)
-        rows.append(np.concatenate([np.full((len(merged), 1), f, np.float32), merged], axis=1))
-    vox = np.concatenate(rows).astype(np.float32)
-    from seevcn_b200.pipeline import WAYMO_VOXEL_CFG
-    oracle.dynamic_voxelize(vox, *WAYMO_VOXEL_CFG)
-    return n_obj, time.perf_counter() - t0, len(vox)
+        if hard_vox:                    # data_processor.py:78-143 + mean_vfe.py:14-31 per frame
+            rg = WAYMO_VOXEL_CFG[0]
+            m = merged[(merged[:, 0] >= rg[0]) & (merged[:, 0] <= rg[3]) & (merged[:, 1] >= rg[1]) & (merged[:, 1] <= rg[4])]
+            v, c, n = oracle.hard_voxelize(m, *WAYMO_VOXEL_CFG, HARD_MAX_PTS, HARD_MAX_VOX)
+            oracle.mean_vfe(v, n.astype(np.float32))
+            n_vox_pts += len(m)
+        else:
+            rows.append(np.concatenate([np.full((len(merged), 1), f, np.float32), merged], axis=1))
+    if not hard_vox:
+        vox = np.concatenate(rows).astype(np.float32)
+        _, _, n = oracle.dynamic_voxelize(vox, *WAYMO_VOXEL_CFG)
+        n_vox_pts = int(n.sum())
+    return n_obj, time.perf_counter() - t0, n_vox_pts
 
 
-def cpu_baseline(sample_frames, sd, threads, budget_s=12.0):
-    """Bounded sample: passes of the whole path over `sample_frames` synthetic C2 frames until ~budget_s of CPU work."""
-    pts, boxes = make_inputs(sample_frames, 5000)
-    cpu_path_once(pts[:1], boxes[:1], sd, threads)   # warm-up (thread pools, page-in)
+def cpu_path_c4(part, sd, threads):
+    """The oracle port of the C4 step (objects only) on host cores -> (#objects, seconds, 0)."""
+    import torch
+    import oracle
+    torch.set_num_threads(threads)
+    t0 = time.perf_counter()
+    with torch.no_grad():
+        coarse = oracle.vcn_forward_ref(sd, part, None, "VCN_VC")["coarse"].numpy()
+    idx = oracle.furthest_point_sample(coarse, 1024)                                    # VCN_VC.py:169 / metrics.py:229
+    oracle.gather_operation(np.ascontiguousarray(coarse.transpose(0, 2, 1)), idx)
+    surf, _ = oracle.get_partial_mesh_batch(part, coarse, k=SEL_K, surface_pts=RESAMPLE)
+    oracle.get_largest_cluster_batch(surf, eps=CLUSTER_EPS, min_points=2, total_pts=coarse.shape[1])
+    return part.shape[0], time.perf_counter() - t0, 0
+
+
+def cpu_sample(cfg_name, threads, frames=None, objects=None):
+    """Inputs + closure for one bounded CPU pass of the configuration's workload."""
+    import oracle
+    cfg = CONFIGS[cfg_name]
+    if cfg_name == "C4":
+        from seevcn_b200 import synth
+        n = objects or 8
+        part, _, _ = synth.make_object_clouds(4000, n, cfg["n_in"], 0)
+        sd = oracle.make_state_dict("VCN_VC", 0, num_coarse=cfg["n_coarse"])
+        return (lambda: cpu_path_c4(part, sd, threads)), f"{n} objects x {cfg['n_in']} pts -> {cfg['n_coarse']} completed pts"
+    f = frames or (2 if cfg_name != "C3" else 8)
+    pts, boxes = make_inputs(f, 5000 if frames is None else 1000, **cfg["gen"])
+    sd = oracle.make_state_dict("VCN_VC", 0)
+    return (lambda: cpu_path_frames(pts, boxes, sd, threads, hard_vox=cfg_name == "C5")), f"{f} frames x {pts.shape[1]} pts"
+
+
+def cpu_baseline(cfg_name, threads, budget_s=12.0, frames=None, objects=None, warm=True, passes_wanted=None):
+    """Bounded sample: passes of the whole path until ~budget_s of CPU work (or exactly passes_wanted)."""
+    cfg = CONFIGS[cfg_name]
+    run, what = cpu_sample(cfg_name, threads, frames, objects)
+    if warm:
+        run()                                              # warm-up (thread pools, page-in)
     n_obj = n_vox = passes = 0
     sec = 0.0
-    while sec < budget_s:
-        n, s, v = cpu_path_once(pts, boxes, sd, threads)
+    while (sec < budget_s) if passes_wanted is None else (passes < passes_wanted):
+        n, s, v = run()
         n_obj += n; sec += s; n_vox += v; passes += 1
-    return {"value": n_obj / sec, "unit": "objects/s", "cores": threads, "kind": "port",
-            "sample": f"{passes} passes x {sample_frames} frames x 180k pts, {n_obj} objects in {sec:.1f} s "
-                      "(oracle/: C + torch fp32, OpenMP/intra-op threads)",
-            "voxelized_mpts_per_s": n_vox / sec / 1e6}
+    value = n_vox / sec / 1e6 if cfg["unit"] == "Mpts/s" else n_obj / sec
+    return {"value": value, "unit": cfg["unit"], "cores": threads, "kind": "port",
+            "sample": f"{passes} passes x {what}, {n_obj} objects in {sec:.1f} s (oracle/: C + torch fp32, OpenMP/intra-op threads)",
+            "objects_per_s": n_obj / sec, "voxelized_mpts_per_s": n_vox / sec / 1e6, "_ms_per_pass": 1e3 * sec / max(passes, 1),
+            "_what": what}
+
+
+def host_threads():
+    """Threads the CPU legs actually use: the cores this process may run on."""
+    try:
+        return len(os.sched_getaffinity(0))
+    except AttributeError:
+        return os.cpu_count() or 1
 
 
 def run_reference(args):
-    """--impl reference: the reference path's CPU implementation (oracle port; the reference's python
-    cannot travel to the GPU box) on all host threads; each step = a bounded sample of the workload."""
+    """--impl reference: the reference path's CPU implementation (oracle port; the reference's python cannot travel to the
+    GPU box) on all host threads; each step = a bounded sample of the configuration's workload: the SAME frames per step
+    as our arm for C2 / C5 (so both arms name one config), 8 of the 256 frames for C3, 8 of the 200 objects for C4."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    import oracle
-    threads = os.cpu_count() or 1
-    sd = oracle.make_state_dict("VCN_VC", seed=0)
-    sample_frames = 1
-    pts, boxes = make_inputs(sample_frames, 1000)
-    for _ in range(max(args.warmup, 1)):
-        cpu_path_once(pts, boxes, sd, threads)
-    tot_obj, tot_sec, tot_vox = 0, 0.0, 0
-    for _ in range(args.steps):
-        n, s, v = cpu_path_once(pts, boxes, sd, threads)
-        tot_obj += n; tot_sec += s; tot_vox += v
-    val = tot_obj / tot_sec
-    sample = f"{sample_frames} frame x 180k pts per step ({tot_obj // max(args.steps, 1)} objects), oracle port, {threads} threads"
+    cfg = CONFIGS[args.config]
+    threads = host_threads()
+    frames = args.frames if args.config in ("C2", "C5") else None
+    r = cpu_baseline(args.config, threads, frames=frames, warm=args.warmup > 0, passes_wanted=max(args.steps, 1))
+    ms, what = r.pop("_ms_per_pass"), r.pop("_what")
+    config = {"workload": cfg["workload"], "sel_k": SEL_K, "cluster_eps": CLUSTER_EPS, "splice_thresh": SPLICE_THRESH,
+              "sample_per_step": what}
+    if args.config in ("C2", "C5"):
+        config["frames_per_step_per_gpu"] = args.frames
     print(json.dumps({
-        "impl": "reference", "metric": METRIC, "value": val, "unit": "objects/s", "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": 1e3 * tot_sec / max(args.steps, 1), "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "C2: synthetic Waymo-like 64-beam frame (180k pts, 50 car boxes, 1024 pts/object)",
-                   "frames_per_step": sample_frames, "sel_k": SEL_K, "cluster_eps": CLUSTER_EPS, "splice_thresh": SPLICE_THRESH},
-        "voxelized_mpts_per_sec": tot_vox / tot_sec / 1e6,
-        "cpu_baseline": {"value": val, "unit": "objects/s", "cores": threads, "kind": "port", "sample": sample},
-        "e2e": {"value": val, "unit": "objects/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "impl": "reference", "metric": cfg["metric"], "value": r["value"], "unit": cfg["unit"], "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": cfg["scaling"],
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config,
+        "voxelized_mpts_per_sec": r["voxelized_mpts_per_s"], "objects_per_sec": r["objects_per_s"],
+        "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")},
+        "e2e": {"value": r["value"], "unit": cfg["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
 
 
 # ---------------------------------------------------------------------------- GPU path --
-def run_ours(args):
+def seeded_state_dict(num_coarse=1024):
+    """Seeded random init of the VCN_VC architecture (no checkpoints offline), BatchNorm running stats randomised so the
+    folding is exercised.  Generated without the oracle package."""
     import torch
-    import torch.distributed as dist
-    from seevcn_b200 import _abi
-    from seevcn_b200.pipeline import CompletionPipeline
-    from seevcn_b200 import dist as sdist
-
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    torch.cuda.set_device(local)
-    dev = torch.device("cuda", local)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
-
-    # weights: seeded random init of the VCN_VC architecture (no checkpoints offline).  Generated without
-    # the oracle package: same generator stream as oracle.make_state_dict, restated in the product pipeline.
     from seevcn_b200.see.surface_completion.models.vcn.models.build import MODELS
     torch.manual_seed(0)
-    ref_model = MODELS.build({"NAME": "VCN_VC"})
-    for m in ref_model.modules():
-        if isinstance(m, torch.nn.BatchNorm1d):
-            m.running_mean.normal_(0, 0.1); m.running_var.uniform_(0.5, 1.5)
-    sd = ref_model.state_dict()
-    pipe = CompletionPipeline("VCN_VC", sd, dev, sel_k=SEL_K, precision=args.precision, cluster_eps=CLUSTER_EPS,
-                              splice_thresh=SPLICE_THRESH)
+    m = MODELS.build({"NAME": "VCN_VC"})
+    if num_coarse != 1024:
+        m.number_coarse = num_coarse
+        m.shape_fc[4] = torch.nn.Linear(1024, 3 * num_coarse)
+    for mod in m.modules():
+        if isinstance(mod, torch.nn.BatchNorm1d):
+            mod.running_mean.normal_(0, 0.1); mod.running_var.uniform_(0.5, 1.5)
+    return m.state_dict()
 
-    F = args.frames
-    pts_h, boxes_h = make_inputs(F, 1000 + rank * F)         # rank r owns frames [r*F, (r+1)*F)
-    pts_pin = torch.from_numpy(pts_h).pin_memory()
-    boxes_pin = torch.from_numpy(boxes_h).pin_memory()
-    pts_d, boxes_d = pts_pin.to(dev), boxes_pin.to(dev)
-    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)   # > 126 MB L2
 
-    from seevcn_b200.pipeline import HostStream
-    hs = HostStream(pipe, F, pts_h.shape[1], boxes_h.shape[1])
+class Dist:
+    """Rank bookkeeping + the timing helpers of the contract (barrier + synchronize on both sides, max over ranks)."""
 
-    def resident_batches(n):
-        for _ in range(n):
-            flush.fill_(1)                                   # L2 flush before every batch (on the compute stream, timed)
-            yield pts_d, boxes_d
+    def __init__(self):
+        import torch
+        import torch.distributed as dist
+        self.torch, self.dist = torch, dist
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.local = int(os.environ.get("LOCAL_RANK", "0"))
+        torch.cuda.set_device(self.local)
+        self.dev = torch.device("cuda", self.local)
+        if self.world > 1:
+            dist.init_process_group("nccl", device_id=self.dev)
 
-    def e2e_batches(n):
-        for _ in range(n):
-            flush.fill_(1)
-            yield pts_pin, boxes_pin
+    def sync_all(self):
+        self.torch.cuda.synchronize()
+        if self.world > 1:
+            self.dist.barrier()
+        self.torch.cuda.synchronize()
 
-    def sync_all():
-        torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    def reduce_max_sum(ms, count):
-        t = torch.tensor([ms], device=dev, dtype=torch.float64)
-        c = torch.tensor([float(count)], device=dev, dtype=torch.float64)
-        if world > 1:
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)         # max over ranks
-            dist.all_reduce(c)
+    def max_sum(self, ms, count):
+        t = self.torch.tensor([ms], device=self.dev, dtype=self.torch.float64)
+        c = self.torch.tensor([float(count)], device=self.dev, dtype=self.torch.float64)
+        if self.world > 1:
+            self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)         # max over ranks
+            self.dist.all_reduce(c)
         return t.item(), c.item()
 
+    def gather_floats(self, vals):
+        """Per-rank list of floats -> list of lists on every rank (diagnostics: per-rank step and stage times)."""
+        t = self.torch.tensor(vals, device=self.dev, dtype=self.torch.float64)
+        if self.world == 1:
+            return [t.tolist()]
+        out = [self.torch.zeros_like(t) for _ in range(self.world)]
+        self.dist.all_gather(out, t)
+        return [o.tolist() for o in out]
+
+    def close(self):
+        if self.world > 1:
+            self.dist.destroy_process_group()
+
+
+def stage_table(prof, steps, ms_total, alg, pk):
+    stages = []
+    for name, (cnt, tot_ms) in prof.items():
+        bound, work = alg.get(name, (None, None))
+        row = {"group": name, "launches_per_step": cnt / steps, "ms_per_step": tot_ms / steps, "share_of_step": tot_ms / ms_total,
+               "bound": bound}
+        if work is not None and tot_ms > 0:
+            rate = work * steps / (tot_ms / 1e3)
+            if bound == "hbm":
+                row.update(achieved=rate / 1e9, unit="GB/s", frac=rate / 1e9 / pk["hbm_gbs"])
+            elif bound == "tensor":
+                row.update(achieved=rate / 1e12, unit="TFLOP/s", frac=rate / 1e12 / pk["bf16_tflops"])
+            else:   # "alu": pair evaluations (8 flop each) against the fp32 FMA peak of the SMs
+                row.update(achieved=rate / 1e12, unit="TFLOP/s fp32", frac=rate / 1e12 / pk["fp32_tflops"])
+        stages.append(row)
+    return stages
+
+
+def ncu_traffic(kernel):
+    tpath = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    if os.path.exists(tpath):
+        return json.load(open(tpath)).get(kernel, {}).get("dram_bytes_per_launch")
+    return None
+
+
+def run_frames(args):
+    """C2 / C3 / C5: the frame pipeline."""
+    import torch
+    from seevcn_b200 import _abi
+    from seevcn_b200.pipeline import CompletionPipeline, HostStream
+    from seevcn_b200 import dist as sdist
+    cfg = CONFIGS[args.config]
+    D = Dist()
+    dev, world, rank = D.dev, D.world, D.rank
+    hard = args.config == "C5"
+    pipe = CompletionPipeline("VCN_VC", seeded_state_dict(), dev, sel_k=SEL_K, precision=args.precision, cluster_eps=CLUSTER_EPS,
+                              splice_thresh=SPLICE_THRESH, min_lidar_pts=MIN_LIDAR_PTS,
+                              hard_voxels=(HARD_MAX_PTS, HARD_MAX_VOX) if hard else None)
+    F, nb = frames_per_step(args, cfg, world)             # frames per pipeline batch, batches per step
+    frames_rank = F * nb
+    pts_h, boxes_h = make_inputs(frames_rank, 1000 + rank * frames_rank, **cfg["gen"])   # rank r owns frames [r*n, (r+1)*n)
+    P_pts, T_box = pts_h.shape[1], boxes_h.shape[1]
+    pts_pin = [torch.from_numpy(pts_h[b * F:(b + 1) * F]).pin_memory() for b in range(nb)]
+    boxes_pin = [torch.from_numpy(boxes_h[b * F:(b + 1) * F]).pin_memory() for b in range(nb)]
+    pts_d = [p.to(dev) for p in pts_pin]
+    boxes_d = [b.to(dev) for b in boxes_pin]
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)   # > 126 MB L2
+    hs = HostStream(pipe, F, P_pts, T_box)
+
+    def batches(n_steps, srcs_p, srcs_b):
+        for _ in range(n_steps):
+            for b in range(nb):
+                flush.fill_(1)                               # L2 flush before every batch (on the compute stream, timed)
+                yield srcs_p[b], srcs_b[b]
+
+    # "collect for the detector" (N > 1): completed clouds + voxel tensors of every rank on every rank
+    gather = None
+    if world > 1 and not args.no_gather:
+        gather = sdist.FrameGather(dev, world, rank, max_obj=F * T_box, rows_per_obj=RESAMPLE, frames=F,
+                                   max_rows=F * P_pts + F * T_box * RESAMPLE, hard=hard, hard_pts=HARD_MAX_PTS,
+                                   hard_max_vox=HARD_MAX_VOX, backend=args.gather)
+
+    def stream(n_steps, srcs_p, srcs_b):
+        b = 0
+        for out in pipe.run_stream(batches(n_steps, srcs_p, srcs_b)):
+            if gather is not None:
+                gather.push(out, frame_offset=rank * frames_rank + (b % nb) * F)
+            b += 1
+            yield out
+        if gather is not None:
+            gather.wait()
+
     def timed_resident(steps, warmup):
-        """K batches streamed through pipe.run_stream with the inputs resident in HBM; the timed region holds the
-        K L2 flushes too.  The library's event scopes (seevcn_prof_*) time each launch group on the launching stream."""
-        for out in pipe.run_stream(resident_batches(warmup)):
+        """steps x nb batches streamed through pipe.run_stream with the inputs resident in HBM; the timed region holds the
+        L2 flushes too.  The library's event scopes (seevcn_prof_*) time each launch group on the launching stream."""
+        for _ in stream(warmup, pts_d, boxes_d):
             pass
-        sync_all()
+        D.sync_all()
         l0 = _abi.lib().seevcn_launch_count()
         _abi.prof_enable(True)
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         n_obj = 0
-        last = None
         e0.record()
-        gathered = None
-        for out in pipe.run_stream(resident_batches(steps)):
-            if world > 1:   # "collect for the detector": static-capacity all-gather, no host sync, overlaps the next batch
-                if gathered is not None:
-                    gathered.wait()
-                gathered = sdist.all_gather_padded(out.get("clustered", out["surface"]), F * boxes_h.shape[1], async_op=True)
+        for out in stream(steps, pts_d, boxes_d):
             n_obj += out["input"].shape[0]
-            last = out
-        if gathered is not None:
-            gathered.wait()
         e1.record()
         e1.synchronize()
-        # rows actually voxelized (spliced-out points, cyclic repeats and out-of-range points are not): the voxel counts
-        # sum to it; every step runs the same frames
-        n_pts = int(last["voxel_num_points"].sum().item()) * steps
-        last["num_voxel_points"] = n_pts // max(steps, 1)
         _abi.prof_enable(False)
         prof = _abi.prof_report()
         launches = _abi.lib().seevcn_launch_count() - l0
-        sync_all()
-        ms, objs = reduce_max_sum(e0.elapsed_time(e1), n_obj)
-        _, pts = reduce_max_sum(0.0, n_pts)
-        return ms, objs, pts, last, launches, prof
+        # rows actually voxelized (spliced-out points, cyclic repeats and out-of-range points are not): the voxel counts sum
+        # to it.  Counted on one untimed pass over the rank's batches (every step runs the same frames).
+        n_pts = n_vox = 0
+        for out in pipe.run_stream(batches(1, pts_d, boxes_d)):
+            n_pts += int(out["voxel_num_points"].sum().item()) if not hard else pipe.hard_points_in(out, pipe.voxel_cfg)
+            n_vox += int(out["voxel_coords"].shape[0]) if not hard else int(out["hard_num_voxels"].sum().item())
+        D.sync_all()
+        my_ms = e0.elapsed_time(e1)
+        ms, objs = D.max_sum(my_ms, n_obj)
+        _, pts = D.max_sum(0.0, n_pts * steps)
+        return ms, objs, pts, launches, prof, n_pts, n_vox, my_ms
 
     def timed_e2e(steps, warmup):
         """Public host-buffer API: pinned host frames in, pinned host results out, every batch's H2D and D2H
         inside the timed region (copies of neighbouring batches overlap the kernels, see HostStream)."""
-        for _ in hs.run(e2e_batches(warmup)):
+        for _ in hs.run(batches(warmup, pts_pin, boxes_pin)):
             pass
-        sync_all()
+        D.sync_all()
         hs.h2d_bytes = hs.d2h_bytes = 0
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         n_obj = 0
         e0.record()
-        for res in hs.run(e2e_batches(steps)):
+        for res in hs.run(batches(steps, pts_pin, boxes_pin)):
             n_obj += res["clustered"].shape[0]
         e1.record()                                          # after the last D2H has landed on the host
         e1.synchronize()
-        sync_all()
-        ms, objs = reduce_max_sum(e0.elapsed_time(e1), n_obj)
+        D.sync_all()
+        ms, objs = D.max_sum(e0.elapsed_time(e1), n_obj)
         return ms, objs, hs.h2d_bytes // steps, hs.d2h_bytes // steps
 
-    sampler = ClockSampler(local)
+    sampler = ClockSampler(D.local)
     if rank == 0:
         sampler.start()
-    ms_res, n_obj_res, n_vox_pts, out, launches, prof = timed_resident(args.steps, args.warmup)
-    n_voxels = out["voxel_coords"].shape[0]
-    obj_rank0 = out["input"].shape[0]
+    ms_res, n_obj_res, n_vox_pts, launches, prof, pts_step_rank0, vox_step_rank0, my_ms = timed_resident(args.steps, args.warmup)
+    obj_rank0 = int(round(n_obj_res / args.steps / world))
     ms_e2e, n_obj_e2e, h2d, d2h = timed_e2e(args.steps, max(args.warmup, 3))
     clocks = sampler.summary() if rank == 0 else None
+    # per-rank diagnostics (scaling attribution): step time and the main stage groups of every rank
+    keys = ("vcn_forward", "vcn_chain_pose", "vcn_chain_enc2", "knn_surface_select", "dynamic_voxelize", "crop", "splice")
+    per_rank = D.gather_floats([my_ms / args.steps] + [prof.get(k, (0, 0.0))[1] / args.steps for k in keys]) if world > 1 else None
 
     if rank == 0:
         pk = peaks()
         steps = args.steps
-        value = n_obj_res / (ms_res / 1e3)
-        e2e = n_obj_e2e / (ms_e2e / 1e3)
         step_ms = ms_res / steps
-        # per launch group, from the library's CUDA events inside the timed region (rank 0)
-        P_pts = pts_h.shape[1]
+        obj_s, obj_s_e2e = n_obj_res / (ms_res / 1e3), n_obj_e2e / (ms_e2e / 1e3)
+        mpts_s = n_vox_pts / (ms_res / 1e3) / 1e6
+        mpts_s_e2e = mpts_s * ms_res / ms_e2e
+        value, e2e = (mpts_s, mpts_s_e2e) if cfg["unit"] == "Mpts/s" else (obj_s, obj_s_e2e)
+        fr = frames_rank
         alg = {   # algorithmic work per STEP on this rank (SURVEY.md §8d per-unit figures x units), and the bound
-            "points_in_boxes_kernel": ("hbm", 16.0 * F * P_pts + 28.0 * F * boxes_h.shape[1]),
+            "points_in_boxes_kernel": ("hbm", 16.0 * fr * P_pts + 28.0 * fr * T_box),
             "vcn_chain_pose": ("tensor", 2.0 * (64 * 128 + 128 * 1024) * RESAMPLE * obj_rank0),
             "vcn_chain_enc1": ("tensor", 2.0 * (128 * 256) * RESAMPLE * obj_rank0),
             "vcn_chain_enc2": ("tensor", FLOP_ENC2_EXEC * obj_rank0),
             "vcn_forward": ("tensor", FLOP_PER_OBJ * obj_rank0),
-            "dynamic_voxelize": ("hbm", 16.0 * out["num_voxel_points"] + 32.0 * n_voxels),
-            "knn_surface_select": ("alu", None), "knn_prepare_kernel": ("alu", None), "knn_scan_kernel": ("alu", None), "knn_emit_kernel": ("hbm", None),
-            "largest_cluster": ("alu", None), "crop": ("hbm", None),
-            "splice": ("hbm", 13.0 * F * P_pts + 12.0 * RESAMPLE * obj_rank0),
+            "knn_scan_kernel": ("alu", 8.0 * RESAMPLE * RESAMPLE * obj_rank0),    # upper bound: every (query, reference) pair once
+            "dynamic_voxelize": ("hbm", 16.0 * pts_step_rank0 + 32.0 * vox_step_rank0),
+            "hard_voxelize": ("hbm", 12.0 * pts_step_rank0 + (12.0 + 4.0 + 60.0) * vox_step_rank0),
+            "mean_vfe": ("hbm", (60.0 + 4.0 + 12.0) * vox_step_rank0),
+            "splice": ("hbm", 13.0 * fr * P_pts + 12.0 * RESAMPLE * obj_rank0),
         }
-        stages = []
-        for name, (cnt, tot_ms) in prof.items():
-            bound, work = alg.get(name, (None, None))
-            row = {"group": name, "launches_per_step": cnt / steps, "ms_per_step": tot_ms / steps, "share_of_step": tot_ms / ms_res,
-                   "bound": bound}
-            if work is not None and tot_ms > 0:
-                rate = work * steps / (tot_ms / 1e3)
-                if bound == "hbm":
-                    row.update(achieved=rate / 1e9, unit="GB/s", frac=rate / 1e9 / pk["hbm_gbs"])
-                else:
-                    row.update(achieved=rate / 1e12, unit="TFLOP/s", frac=rate / 1e12 / pk["bf16_tflops"])
-            stages.append(row)
+        stages = stage_table(prof, steps, ms_res, alg, pk)
         cnt2, ms2 = prof.get("vcn_chain_enc2", (0, 0.0))
         achieved = FLOP_ENC2_EXEC * obj_rank0 * steps / (ms2 / 1e3) / 1e12 if ms2 > 0 else None
         peak = pk["bf16_tflops"]
-        traffic = None
-        tpath = os.path.join(ROOT, "profiles", "ncu_traffic.json")
-        if os.path.exists(tpath):
-            traffic = json.load(open(tpath)).get("vcn_chain_kernel<2>", {}).get("dram_bytes_per_launch")
-        import oracle   # cpu_baseline leg only (rank 0, N = 1)
-        cpu = cpu_baseline(2, oracle.make_state_dict("VCN_VC", 0), os.cpu_count() or 1) if world == 1 and not args.no_cpu else None
+        cpu = None
+        if world == 1 and not args.no_cpu:
+            cpu = cpu_baseline(args.config, host_threads())
+            cpu.pop("_ms_per_pass"); cpu.pop("_what")
         line = {
-            "metric": METRIC, "value": value, "unit": "objects/s", "n_gpus": world, "steps": steps, "warmup": args.warmup,
-            "ms_per_step": step_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "metric": cfg["metric"], "value": value, "unit": cfg["unit"], "n_gpus": world, "steps": steps, "warmup": args.warmup,
+            "ms_per_step": step_ms, "higher_is_better": True, "scaling": cfg["scaling"], "vs_baseline": None,
             "dtype": "bf16" if args.precision == "bf16" else "f32", "data": "synthetic",
-            "config": {"workload": "C2: synthetic Waymo-like 64-beam frame (180k pts, 50 car boxes, 1024 pts/object), random-init VCN_VC",
-                       "frames_per_step_per_gpu": F, "objects_per_step": int(round(n_obj_res / steps)), "sel_k": SEL_K,
-                       "cluster_eps": CLUSTER_EPS, "splice_thresh": SPLICE_THRESH, "l2": "flushed (256 MB write) before every step, inside the timed region",
-                       "parallelism": f"frame-sharded x{world}"},
-            "voxelized_mpts_per_sec": n_vox_pts / (ms_res / 1e3) / 1e6, "voxels_per_step_rank0": int(n_voxels),
-            "e2e": {"value": e2e, "unit": "objects/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-                    "ms_per_step": ms_e2e / steps},
+            "config": {"workload": cfg["workload"], "frames_per_step_per_gpu": fr, "frames_per_pipeline_batch": F,
+                       "objects_per_step": int(round(n_obj_res / steps)), "sel_k": SEL_K,
+                       "cluster_eps": CLUSTER_EPS, "splice_thresh": SPLICE_THRESH,
+                       "l2": "flushed (256 MB write) before every pipeline batch, inside the timed region",
+                       "parallelism": f"frame-sharded x{world}",
+                       "gather": (gather.describe() if gather is not None else None)},
+            "objects_per_sec": obj_s, "voxelized_mpts_per_sec": mpts_s, "voxels_per_step_rank0": int(vox_step_rank0),
+            "voxelized_points_per_step_rank0": int(pts_step_rank0),
+            "e2e": {"value": e2e, "unit": cfg["unit"], "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+                    "ms_per_step": ms_e2e / steps, "objects_per_sec": obj_s_e2e},
             "gpu_launches": int(launches),
             "roofline": {"kernel": "vcn_chain_kernel<2> (enc2: mlp_conv2.0 local half + mlp_conv2.3 + max-pool, tcgen05)",
                          "bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
-                         "frac": achieved / peak if achieved else None, "traffic": traffic,
+                         "frac": achieved / peak if achieved else None, "traffic": ncu_traffic("vcn_chain_kernel<2>"),
                          "peak_source": pk["source"] + " burst bf16 (cuBLAS); sustained is %.0f" % pk["bf16_tflops_sustained"],
                          "launches": cnt2, "us_per_launch": 1e3 * ms2 / cnt2 if cnt2 else None,
                          "flop_per_object": FLOP_ENC2_EXEC,
@@ -374,26 +512,137 @@ def run_ours(args):
             "stages": stages,
             "cpu_baseline": cpu, "clocks": clocks,
         }
+        if per_rank is not None:
+            line["per_rank_ms"] = {"columns": ["step"] + list(keys), "rows": per_rank}
         print(json.dumps(line))
-    if world > 1:
-        dist.destroy_process_group()
+    D.close()
+
+
+def run_c4(args):
+    """C4: dense-crowd stress on per-object clouds (no crop): VCN with the 16,384-point decoder, FPS, gather, kNN, cluster."""
+    import torch
+    from seevcn_b200 import _abi, synth
+    from seevcn_b200.see.surface_completion.models.vcn.models.build import MODELS
+    from seevcn_b200.see.surface_completion.models.vcn.utils.sampling import get_partial_mesh_batch, get_largest_cluster_batch
+    from seevcn_b200.pcdet.ops.pointnet2.pointnet2_batch import pointnet2_utils as pn2
+    cfg = CONFIGS["C4"]
+    D = Dist()
+    dev, world, rank = D.dev, D.world, D.rank
+    O, N, NC = cfg["objects"], cfg["n_in"], cfg["n_coarse"]
+    model = MODELS.build({"NAME": "VCN_VC"}, precision=args.precision)
+    model.number_coarse = NC
+    model.shape_fc[4] = torch.nn.Linear(1024, 3 * NC)
+    model.load_state_dict(seeded_state_dict(NC))
+    model.to(dev).eval()
+    part_h, _, _ = synth.make_object_clouds(4000 + rank, O, N, 0)
+    part_pin = torch.from_numpy(part_h).pin_memory()
+    part_d = part_pin.to(dev)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    out_pin = {"clustered": torch.empty((O, NC, 3), dtype=torch.float32).pin_memory(),
+               "sampled": torch.empty((O, 3, 1024), dtype=torch.float32).pin_memory()}
+
+    def step(src, host_out):
+        flush.fill_(1)
+        x = src.to(dev, non_blocking=True) if not src.is_cuda else src
+        coarse = model({"input": x})["coarse"]                                          # (O, 16384, 3)
+        idx = pn2.furthest_point_sample(coarse, 1024)                                   # VCN_VC.py:169 / utils/misc.py:29-36
+        sampled = pn2.gather_operation(coarse.transpose(1, 2).contiguous(), idx)        # (O, 3, 1024)
+        surf, cnt = get_partial_mesh_batch(x, coarse, k=SEL_K, surface_pts=RESAMPLE, return_count=True)
+        clus = get_largest_cluster_batch(surf, eps=CLUSTER_EPS, min_points=2, total_pts=NC, period=cnt)
+        if host_out:
+            out_pin["clustered"].copy_(clus, non_blocking=True)
+            out_pin["sampled"].copy_(sampled, non_blocking=True)
+            torch.cuda.current_stream().synchronize()
+        return clus
+
+    def timed(steps, warmup, src, host_out):
+        for _ in range(warmup):
+            step(src, host_out)
+        D.sync_all()
+        l0 = _abi.lib().seevcn_launch_count()
+        _abi.prof_enable(True)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            step(src, host_out)
+        e1.record()
+        e1.synchronize()
+        _abi.prof_enable(False)
+        prof = _abi.prof_report()
+        launches = _abi.lib().seevcn_launch_count() - l0
+        D.sync_all()
+        ms, objs = D.max_sum(e0.elapsed_time(e1), O * steps)
+        return ms, objs, launches, prof
+
+    sampler = ClockSampler(D.local)
+    if rank == 0:
+        sampler.start()
+    ms_res, n_obj, launches, prof = timed(args.steps, args.warmup, part_d, False)
+    ms_e2e, n_obj_e2e, _, _ = timed(args.steps, max(args.warmup, 3), part_pin, True)
+    clocks = sampler.summary() if rank == 0 else None
+    if rank == 0:
+        pk = peaks()
+        steps = args.steps
+        alg = {
+            "vcn_forward": ("tensor", FLOP_PER_OBJ_C4 * O),
+            "vcn_chain_enc2": ("tensor", 2.0 * (256 * 512 + 512 * 1024) * N * O),
+            "fps": ("hbm", (12.0 * NC + 4.0 * 1024) * O),
+            "knn_scan_kernel": ("alu", 8.0 * N * NC * O),          # upper bound: every (query, reference) pair once
+            "gather_points": ("hbm", (4.0 + 24.0) * 1024 * O),
+        }
+        stages = stage_table(prof, steps, ms_res, alg, pk)
+        cnt_f, ms_f = prof.get("fps", (0, 0.0))
+        fps_bytes = (12.0 * NC + 4.0 * 1024) * O
+        achieved = fps_bytes * steps / (ms_f / 1e3) / 1e9 if ms_f > 0 else None
+        cpu = None
+        if world == 1 and not args.no_cpu:
+            cpu = cpu_baseline("C4", host_threads())
+            cpu.pop("_ms_per_pass"); cpu.pop("_what")
+        h2d = part_pin.numel() * 4
+        d2h = sum(t.numel() * 4 for t in out_pin.values())
+        print(json.dumps({
+            "metric": cfg["metric"], "value": n_obj / (ms_res / 1e3), "unit": cfg["unit"], "n_gpus": world, "steps": steps,
+            "warmup": args.warmup, "ms_per_step": ms_res / steps, "higher_is_better": True, "scaling": cfg["scaling"],
+            "vs_baseline": None, "dtype": "bf16" if args.precision == "bf16" else "f32", "data": "synthetic",
+            "config": {"workload": cfg["workload"], "objects_per_step_per_gpu": O, "sel_k": SEL_K, "cluster_eps": CLUSTER_EPS,
+                       "l2": "flushed (256 MB write) before every step, inside the timed region", "parallelism": f"object-sharded x{world}"},
+            "e2e": {"value": n_obj_e2e / (ms_e2e / 1e3), "unit": cfg["unit"], "h2d_bytes_per_step": int(h2d),
+                    "d2h_bytes_per_step": int(d2h), "ms_per_step": ms_e2e / steps},
+            "gpu_launches": int(launches),
+            "roofline": {"kernel": "fps_kernel (16384 -> 1024 per object: 1023 serial rounds, one CTA per object)", "bound": "hbm",
+                         "achieved": achieved, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": achieved / pk["hbm_gbs"] if achieved else None,
+                         "traffic": ncu_traffic("fps_kernel"), "peak_source": pk["source"] + " HBM copy",
+                         "launches": cnt_f, "us_per_launch": 1e3 * ms_f / cnt_f if cnt_f else None,
+                         "rounds_per_s": 1023.0 * O * steps / (ms_f / 1e3) if ms_f > 0 else None,
+                         "note": "compulsory bytes 12 N + 4 M per object (SURVEY.md §8d); the kernel is a serial on-chip latency "
+                                 "chain (M - 1 dependent argmax rounds), not a bandwidth problem"},
+            "stages": stages, "cpu_baseline": cpu, "clocks": clocks,
+        }))
+    D.close()
 
 
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=200)    # ~0.3 s per timed leg: box-level jitter (PCIe, host) averages out
+    ap.add_argument("--steps", type=int, default=None)   # C2: 200 steps = ~0.3 s per timed leg: box-level jitter averages out
     ap.add_argument("--warmup", type=int, default=5)
-    ap.add_argument("--frames", type=int, default=8, help="frames per step per GPU")
+    ap.add_argument("--frames", type=int, default=8, help="frames per step per GPU (C2, C5)")
+    ap.add_argument("--config", default="C2", choices=sorted(CONFIGS))
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--precision", default=os.environ.get("SEEVCN_PRECISION", "bf16"), choices=["bf16", "fp32"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-gather", action="store_true", help="N > 1: skip the end-of-path collect (attribution runs)")
+    ap.add_argument("--gather", default="auto", choices=["auto", "peer", "nccl"], help="N > 1: how the results are collected")
     args = ap.parse_args()
+    if args.steps is None:
+        args.steps = {"C2": 200, "C3": 20, "C4": 20, "C5": 100}[args.config] if args.impl == "ours" else 3
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":
         run_reference(args)
+    elif args.config == "C4":
+        run_c4(args)
     else:
-        run_ours(args)
+        run_frames(args)
 
 
 if __name__ == "__main__":

@@ -276,6 +276,11 @@ int seevcn_splice(int num_frames, int pts_per_frame, const float* frame_pts,
 int seevcn_mean_vfe(int num_voxels, int max_points, int num_features, const float* voxels,
                     const float* voxel_num_points, float* voxel_features,
                     seevcn_stream_t stream);
+/* Same with the int32 counts the voxel generator produces (the reference casts them to float on the way to the GPU,
+ * detector3d/pcdet/models/__init__.py:34). */
+int seevcn_mean_vfe_int(int num_voxels, int max_points, int num_features, const float* voxels,
+                        const int* voxel_num_points, float* voxel_features,
+                        seevcn_stream_t stream);
 
 /* ref: DynamicMeanVFE.forward  detector3d/pcdet/models/backbones_3d/vfe/dynamic_mean_vfe.py:37-76
  * points (N,1+C) f32 rows [batch_idx,x,y,z,...]; pc_range[6], voxel_size[3], grid_size[3]
@@ -339,6 +344,21 @@ int seevcn_hard_voxelize(int num_points, int num_features, const float* points,
                          float* voxels, int* coordinates, int* num_points_per_voxel,
                          int* num_voxels, void* workspace, size_t workspace_bytes,
                          seevcn_stream_t stream);
+
+/* The batched form the frame pipeline uses (the reference voxelizes frame by frame in DataLoader workers and pads the
+ * per-frame coordinates with the batch index when collating, detector3d/pcdet/datasets/dataset.py:193-198):
+ * points (F, stride, C) f32, row q of frame f takes part iff q < counts[f] (counts (F) int32 DEVICE, NULL = all rows).
+ * Per frame: first-seen voxel order, cap max_voxels, first max_points points per voxel.  Outputs, padded per frame:
+ *   voxels (F, max_voxels, max_points, C), coordinates (F, max_voxels, 4) int32 [frame, z, y, x],
+ *   num_points_per_voxel (F, max_voxels) int32, num_voxels (F) int32 (device); slots >= num_voxels[f] are undefined.
+ * The x/y range mask of data_processor.py:78-91 is implied: the grid spans POINT_CLOUD_RANGE, so a point outside the
+ * range is outside the grid.  workspace: seevcn_hard_voxelize_frames_workspace_bytes(F, stride, max_points, max_voxels). */
+size_t seevcn_hard_voxelize_frames_workspace_bytes(int num_frames, int stride, int max_points, int max_voxels);
+int seevcn_hard_voxelize_frames(int num_frames, int stride, int num_features, const float* points, const int* counts,
+                                const float* pc_range, const float* voxel_size, const int* grid_size,
+                                int max_points, int max_voxels,
+                                float* voxels, int* coordinates, int* num_points_per_voxel, int* num_voxels,
+                                void* workspace, size_t workspace_bytes, seevcn_stream_t stream);
 
 /* Copies `bytes` (multiple of 4) from device memory into PINNED host memory (cudaHostAlloc / torch pin_memory: mapped
  * into the device address space) with SM stores on `stream` — for the few words the host needs while the GPU keeps

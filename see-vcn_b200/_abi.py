@@ -60,6 +60,7 @@ SIGNATURES = {
     "seevcn_linear_bf16_workspace_bytes": (c_size_t, [I, I, I]),
     "seevcn_linear_bf16": (I, [I, I, I, P, P, P, P, I, I, P, P, P, c_size_t, P]),
     "seevcn_mean_vfe": (I, [I, I, I, P, P, P, P]),
+    "seevcn_mean_vfe_int": (I, [I, I, I, P, P, P, P]),
     "seevcn_dynamic_voxelize_workspace_bytes": (c_size_t, [I, I, I, POINTER(c_int)]),
     "seevcn_dynamic_voxelize": (I, [I, I, P, POINTER(ctypes.c_float), POINTER(ctypes.c_float), POINTER(c_int),
                                     I, I, I, P, P, P, P, P, c_size_t, P]),
@@ -72,6 +73,9 @@ SIGNATURES = {
     "seevcn_hard_voxelize_workspace_bytes": (c_size_t, [I, I, I]),
     "seevcn_hard_voxelize": (I, [I, I, P, POINTER(ctypes.c_float), POINTER(ctypes.c_float), POINTER(c_int),
                                  I, I, P, P, P, P, P, c_size_t, P]),
+    "seevcn_hard_voxelize_frames_workspace_bytes": (c_size_t, [I, I, I, I]),
+    "seevcn_hard_voxelize_frames": (I, [I, I, I, P, P, POINTER(ctypes.c_float), POINTER(ctypes.c_float), POINTER(c_int),
+                                        I, I, P, P, P, P, P, c_size_t, P]),
     "seevcn_chamfer": (I, [I, I, I, P, P, P, P, P]),
     "seevcn_copy_to_pinned": (I, [P, P, c_size_t, P]),
     "seevcn_copy_from_pinned": (I, [P, P, c_size_t, P]),

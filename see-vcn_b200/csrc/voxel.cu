@@ -589,9 +589,11 @@ dynvox_reduce_kernel(int logw, VoxGeom g, VoxGeomD gd, const int4* __restrict__ 
     }
 }
 
-// ref: mean_vfe.py:23-29.  One thread per (voxel, feature).
+// ref: mean_vfe.py:23-29.  One thread per (voxel, feature).  NP = float (the reference's voxel_num_points after
+// load_data_to_gpu) or int (straight from the voxel generator).
+template <typename NP>
 __global__ void __launch_bounds__(256)
-mean_vfe_kernel(int m, int t, int c, const float* __restrict__ voxels, const float* __restrict__ num_points,
+mean_vfe_kernel(int m, int t, int c, const float* __restrict__ voxels, const NP* __restrict__ num_points,
                 float* __restrict__ out) {
     const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= (long long)m * c) return;
@@ -599,7 +601,7 @@ mean_vfe_kernel(int m, int t, int c, const float* __restrict__ voxels, const flo
     const float* src = voxels + (size_t)v * t * c + j;
     float s = 0.f;
     for (int i = 0; i < t; ++i) s = __fadd_rn(s, src[(size_t)i * c]);   // torch.sum over dim 1, sequential for t<=~32
-    const float norm = fmaxf(num_points[v], 1.0f);                     // clamp_min(1.0)
+    const float norm = fmaxf((float)num_points[v], 1.0f);              // clamp_min(1.0)
     out[e] = __fdiv_rn(s, norm);
 }
 
@@ -619,22 +621,27 @@ __device__ __forceinline__ unsigned long long mix64(unsigned long long k) {
 //     minimum it has seen and forwards the loser, so the list ends as the T smallest point
 //     indices in ascending order, independent of execution order (deterministic)
 //  5. gather rows.
+// All kernels take F frames of `stride` rows each (the single-frame entry is F = 1); row q of frame f takes part iff
+// q < counts[f] (counts == NULL: all rows).  Voxel ids, caps and outputs are per frame: slot f * max_voxels + id.
 __global__ void __launch_bounds__(256)
-hardvox_insert_kernel(int n, int c, const float* __restrict__ points, VoxGeom g, unsigned long long hmask,
-                      unsigned long long* __restrict__ keys, int* __restrict__ first, int* __restrict__ slot_of_point) {
-    const int p = blockIdx.x * blockDim.x + threadIdx.x;
-    if (p >= n) return;
+hardvox_insert_kernel(int frames, int stride, int c, const float* __restrict__ points, const int* __restrict__ counts, VoxGeom g,
+                      unsigned long long hmask, unsigned long long* __restrict__ keys, int* __restrict__ first,
+                      int* __restrict__ slot_of_point) {
+    const long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= (long long)frames * stride) return;
+    const int f = (int)(p / stride), q = (int)(p - (long long)f * stride);
     const float* row = points + (size_t)p * c;
     int cx, cy, cz;
-    if (!voxel_coord(g, row[0], row[1], row[2], cx, cy, cz)) { slot_of_point[p] = -1; return; }
-    const unsigned long long key = (unsigned long long)(((long long)cx * g.g[1] + cy) * (long long)g.g[2] + cz);
+    if ((counts && q >= counts[f]) || !voxel_coord(g, row[0], row[1], row[2], cx, cy, cz)) { slot_of_point[p] = -1; return; }
+    const unsigned long long key =
+        (unsigned long long)((((long long)f * g.g[0] + cx) * g.g[1] + cy) * (long long)g.g[2] + cz);
     unsigned long long slot = mix64(key) & hmask;
     while (true) {
         const unsigned long long prev = atomicCAS(&keys[slot], kEmpty, key);
         if (prev == kEmpty || prev == key) break;
         slot = (slot + 1) & hmask;
     }
-    atomicMin(&first[slot], p);
+    atomicMin(&first[slot], (int)p);
     slot_of_point[p] = (int)slot;
 }
 
@@ -646,23 +653,28 @@ hardvox_flag_kernel(int n, const int* __restrict__ first, const int* __restrict_
     flag[p] = (s >= 0 && first[s] == p) ? 1 : 0;
 }
 
+// coords4 != 0: coordinates (F, max_voxels, 4) [frame, z, y, x] (the collated form); else (max_voxels, 3) zyx.
 __global__ void __launch_bounds__(256)
-hardvox_assign_kernel(int n, int max_voxels, VoxGeom g, const unsigned long long* __restrict__ keys,
+hardvox_assign_kernel(int frames, int stride, int max_voxels, VoxGeom g, const unsigned long long* __restrict__ keys,
                       const int* __restrict__ slot_of_point, const int* __restrict__ flag, const int* __restrict__ rank,
-                      int* __restrict__ vid_of_slot, int* __restrict__ coordinates, int* __restrict__ num_voxels) {
-    const int p = blockIdx.x * blockDim.x + threadIdx.x;
-    if (p >= n) return;
-    if (p == n - 1) *num_voxels = min(rank[p] + flag[p], max_voxels);
+                      int* __restrict__ vid_of_slot, int coords4, int* __restrict__ coordinates, int* __restrict__ num_voxels) {
+    const long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= (long long)frames * stride) return;
+    const int f = (int)(p / stride), q = (int)(p - (long long)f * stride);
+    const int frame_rank0 = rank[(size_t)f * stride];          // voxels opened by earlier frames
+    if (q == stride - 1) num_voxels[f] = min(rank[p] + flag[p] - frame_rank0, max_voxels);
     if (!flag[p]) return;
     const int s = slot_of_point[p];
-    const int vid = rank[p];
+    const int vid = rank[p] - frame_rank0;                     // first-seen order inside the frame
     if (vid >= max_voxels) return;   // vid_of_slot stays -1
-    vid_of_slot[s] = vid;
+    const size_t o = (size_t)f * max_voxels + vid;
+    vid_of_slot[s] = (int)o;
     const unsigned long long key = keys[s];
     const int z = (int)(key % (unsigned long long)g.g[2]);
     const int y = (int)((key / (unsigned long long)g.g[2]) % (unsigned long long)g.g[1]);
-    const int x = (int)(key / ((unsigned long long)g.g[2] * g.g[1]));
-    coordinates[vid * 3 + 0] = z; coordinates[vid * 3 + 1] = y; coordinates[vid * 3 + 2] = x;
+    const int x = (int)((key / ((unsigned long long)g.g[2] * g.g[1])) % (unsigned long long)g.g[0]);
+    if (coords4) reinterpret_cast<int4*>(coordinates)[o] = make_int4(f, z, y, x);
+    else { coordinates[o * 3 + 0] = z; coordinates[o * 3 + 1] = y; coordinates[o * 3 + 2] = x; }
 }
 
 __global__ void __launch_bounds__(256)
@@ -684,21 +696,23 @@ hardvox_pick_kernel(int n, int t, const int* __restrict__ slot_of_point, const i
 }
 
 __global__ void __launch_bounds__(256)
-hardvox_gather_kernel(int max_voxels, int t, int c, const float* __restrict__ points, const int* __restrict__ num_voxels,
+hardvox_gather_kernel(int frames, int max_voxels, int t, int c, const float* __restrict__ points, const int* __restrict__ num_voxels,
                       const int* __restrict__ sel, const int* __restrict__ cnt, float* __restrict__ voxels,
                       int* __restrict__ num_points_per_voxel) {
     const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    const int m = *num_voxels;
-    if (e >= (long long)m * t) return;
-    const int vid = (int)(e / t), j = (int)(e - (long long)vid * t);
-    const int k = min(cnt[vid], t);
-    if (j == 0) num_points_per_voxel[vid] = k;
+    if (e >= (long long)frames * max_voxels * t) return;
+    const long long slot = e / t;
+    const int j = (int)(e - slot * t);
+    const int f = (int)(slot / max_voxels), vid = (int)(slot - (long long)f * max_voxels);
+    if (vid >= num_voxels[f]) return;
+    const int k = min(cnt[slot], t);
+    if (j == 0) num_points_per_voxel[slot] = k;
     float* dst = voxels + (size_t)e * c;
     if (j < k) {
         const float* src = points + (size_t)sel[e] * c;
-        for (int f = 0; f < c; ++f) dst[f] = src[f];
+        for (int ff = 0; ff < c; ++ff) dst[ff] = src[ff];
     } else {
-        for (int f = 0; f < c; ++f) dst[f] = 0.f;
+        for (int ff = 0; ff < c; ++ff) dst[ff] = 0.f;
     }
 }
 
@@ -739,7 +753,21 @@ extern "C" int seevcn_mean_vfe(int num_voxels, int max_points, int num_features,
     if (num_voxels == 0 || num_features == 0) return SEEVCN_OK;
     SEEVCN_REQUIRE(voxels && voxel_num_points && voxel_features, "mean_vfe: null pointer");
     const long long total = (long long)num_voxels * num_features;
-    mean_vfe_kernel<<<(unsigned)div_up(total, 256ll), 256, 0, as_stream(stream)>>>(
+    SEEVCN_PROF("mean_vfe", as_stream(stream));
+    mean_vfe_kernel<float><<<(unsigned)div_up(total, 256ll), 256, 0, as_stream(stream)>>>(
+        num_voxels, max_points, num_features, voxels, voxel_num_points, voxel_features);
+    SEEVCN_LAUNCH_CHECK();
+    return SEEVCN_OK;
+}
+
+extern "C" int seevcn_mean_vfe_int(int num_voxels, int max_points, int num_features, const float* voxels,
+                                   const int* voxel_num_points, float* voxel_features, seevcn_stream_t stream) {
+    SEEVCN_REQUIRE(num_voxels >= 0 && max_points >= 0 && num_features >= 0, "mean_vfe: negative size");
+    if (num_voxels == 0 || num_features == 0) return SEEVCN_OK;
+    SEEVCN_REQUIRE(voxels && voxel_num_points && voxel_features, "mean_vfe: null pointer");
+    const long long total = (long long)num_voxels * num_features;
+    SEEVCN_PROF("mean_vfe", as_stream(stream));
+    mean_vfe_kernel<int><<<(unsigned)div_up(total, 256ll), 256, 0, as_stream(stream)>>>(
         num_voxels, max_points, num_features, voxels, voxel_num_points, voxel_features);
     SEEVCN_LAUNCH_CHECK();
     return SEEVCN_OK;
@@ -934,6 +962,69 @@ extern "C" size_t seevcn_hard_voxelize_workspace_bytes(int num_points, int max_p
     return hard_layout(num_points, max_points, max_voxels).total;
 }
 
+namespace {
+int hardvox_run(const char* what, int frames, int stride, int num_features, const float* points, const int* counts,
+                const float* pc_range, const float* voxel_size, const int* grid_size, int max_points, int max_voxels,
+                int coords4, float* voxels, int* coordinates, int* num_points_per_voxel, int* num_voxels, void* workspace,
+                size_t workspace_bytes, cudaStream_t st) {
+    const long long n = (long long)frames * stride;
+    SEEVCN_REQUIRE(n < (1ll << 31) && (long long)frames * max_voxels * max_points < (1ll << 31), "%s: more than 2^31 rows", what);
+    const HardWs w = hard_layout((int)n, max_points, frames * max_voxels);
+    if (workspace_bytes < w.total) {
+        seevcn_set_error("%s: workspace %zu < %zu", what, workspace_bytes, w.total);
+        return SEEVCN_E_WORKSPACE;
+    }
+    VoxGeom g;
+    for (int i = 0; i < 3; ++i) {
+        g.lo[i] = pc_range[i]; g.vs[i] = voxel_size[i]; g.g[i] = grid_size[i];
+        SEEVCN_REQUIRE(grid_size[i] > 0 && voxel_size[i] > 0.f, "%s: bad grid", what);
+    }
+    SEEVCN_PROF("hard_voxelize", st);
+    char* ws = static_cast<char*>(workspace);
+    auto* keys = reinterpret_cast<unsigned long long*>(ws + w.off_keys);
+    int* first = reinterpret_cast<int*>(ws + w.off_first);
+    int* vid = reinterpret_cast<int*>(ws + w.off_vid);
+    int* slot = reinterpret_cast<int*>(ws + w.off_slot);
+    int* flag = reinterpret_cast<int*>(ws + w.off_flag);
+    int* rank = reinterpret_cast<int*>(ws + w.off_rank);
+    int* sel = reinterpret_cast<int*>(ws + w.off_sel);
+    int* cnt = reinterpret_cast<int*>(ws + w.off_cnt);
+    const size_t mv = (size_t)frames * max_voxels;
+    SEEVCN_CUDA_CHECK(cudaMemsetAsync(keys, 0xff, w.nslots * 8, st));
+    SEEVCN_CUDA_CHECK(cudaMemsetAsync(first, 0x7f, w.nslots * 4, st));
+    SEEVCN_CUDA_CHECK(cudaMemsetAsync(vid, 0xff, w.nslots * 4, st));
+    SEEVCN_CUDA_CHECK(cudaMemsetAsync(sel, 0x7f, mv * max_points * 4, st));
+    SEEVCN_CUDA_CHECK(cudaMemsetAsync(cnt, 0, mv * 4, st));
+    if (frames > 1) SEEVCN_CUDA_CHECK(cudaMemsetAsync(num_points_per_voxel, 0, mv * 4, st));   // padded slots read as empty voxels
+    const int gp = (int)div_up(n, 256ll);
+    hardvox_insert_kernel<<<gp, 256, 0, st>>>(frames, stride, num_features, points, counts, g, w.nslots - 1, keys, first, slot);
+    SEEVCN_LAUNCH_CHECK();
+    hardvox_flag_kernel<<<gp, 256, 0, st>>>((int)n, first, slot, flag);
+    SEEVCN_LAUNCH_CHECK();
+    SEEVCN_CUDA_CHECK(cudaMemsetAsync(ws + w.off_scan, 0, w.scan_bytes, st));
+    seevcn_scan::exclusive_scan_u32_kernel<<<w.scan_tiles, seevcn_scan::kScanThreads, 0, st>>>(
+        (int)n, reinterpret_cast<const unsigned*>(flag), reinterpret_cast<unsigned*>(rank),
+        reinterpret_cast<unsigned long long*>(ws + w.off_scan), reinterpret_cast<int*>(ws + w.off_scan + 8 * (size_t)w.scan_tiles),
+        nullptr);
+    SEEVCN_LAUNCH_CHECK();
+    hardvox_assign_kernel<<<gp, 256, 0, st>>>(frames, stride, max_voxels, g, keys, slot, flag, rank, vid, coords4, coordinates, num_voxels);
+    SEEVCN_LAUNCH_CHECK();
+    hardvox_pick_kernel<<<gp, 256, 0, st>>>((int)n, max_points, slot, vid, sel, cnt);
+    SEEVCN_LAUNCH_CHECK();
+    const long long tot = (long long)mv * max_points;
+    hardvox_gather_kernel<<<(unsigned)div_up(tot, 256ll), 256, 0, st>>>(frames, max_voxels, max_points, num_features, points,
+                                                                        num_voxels, sel, cnt, voxels, num_points_per_voxel);
+    SEEVCN_LAUNCH_CHECK();
+    return SEEVCN_OK;
+}
+}  // namespace
+
+extern "C" size_t seevcn_hard_voxelize_frames_workspace_bytes(int num_frames, int stride, int max_points, int max_voxels) {
+    const long long n = (long long)num_frames * stride;
+    if (n >= (1ll << 31) || (long long)num_frames * max_voxels >= (1ll << 31)) return 0;
+    return hard_layout((int)n, max_points, num_frames * max_voxels).total;
+}
+
 extern "C" int seevcn_hard_voxelize(int num_points, int num_features, const float* points, const float* pc_range,
                                     const float* voxel_size, const int* grid_size, int max_points, int max_voxels,
                                     float* voxels, int* coordinates, int* num_points_per_voxel, int* num_voxels,
@@ -945,48 +1036,23 @@ extern "C" int seevcn_hard_voxelize(int num_points, int num_features, const floa
     SEEVCN_CUDA_CHECK(cudaMemsetAsync(num_voxels, 0, sizeof(int), st));
     if (num_points == 0 || max_voxels == 0) return SEEVCN_OK;
     SEEVCN_REQUIRE(points && voxels && coordinates && num_points_per_voxel && workspace, "hard_voxelize: null pointer");
-    const HardWs w = hard_layout(num_points, max_points, max_voxels);
-    if (workspace_bytes < w.total) {
-        seevcn_set_error("hard_voxelize: workspace %zu < %zu", workspace_bytes, w.total);
-        return SEEVCN_E_WORKSPACE;
-    }
-    VoxGeom g;
-    for (int i = 0; i < 3; ++i) {
-        g.lo[i] = pc_range[i]; g.vs[i] = voxel_size[i]; g.g[i] = grid_size[i];
-        SEEVCN_REQUIRE(grid_size[i] > 0 && voxel_size[i] > 0.f, "hard_voxelize: bad grid");
-    }
-    char* ws = static_cast<char*>(workspace);
-    auto* keys = reinterpret_cast<unsigned long long*>(ws + w.off_keys);
-    int* first = reinterpret_cast<int*>(ws + w.off_first);
-    int* vid = reinterpret_cast<int*>(ws + w.off_vid);
-    int* slot = reinterpret_cast<int*>(ws + w.off_slot);
-    int* flag = reinterpret_cast<int*>(ws + w.off_flag);
-    int* rank = reinterpret_cast<int*>(ws + w.off_rank);
-    int* sel = reinterpret_cast<int*>(ws + w.off_sel);
-    int* cnt = reinterpret_cast<int*>(ws + w.off_cnt);
-    SEEVCN_CUDA_CHECK(cudaMemsetAsync(keys, 0xff, w.nslots * 8, st));
-    SEEVCN_CUDA_CHECK(cudaMemsetAsync(first, 0x7f, w.nslots * 4, st));
-    SEEVCN_CUDA_CHECK(cudaMemsetAsync(vid, 0xff, w.nslots * 4, st));
-    SEEVCN_CUDA_CHECK(cudaMemsetAsync(sel, 0x7f, (size_t)max_voxels * max_points * 4, st));
-    SEEVCN_CUDA_CHECK(cudaMemsetAsync(cnt, 0, (size_t)max_voxels * 4, st));
-    const int gp = div_up(num_points, 256);
-    hardvox_insert_kernel<<<gp, 256, 0, st>>>(num_points, num_features, points, g, w.nslots - 1, keys, first, slot);
-    SEEVCN_LAUNCH_CHECK();
-    hardvox_flag_kernel<<<gp, 256, 0, st>>>(num_points, first, slot, flag);
-    SEEVCN_LAUNCH_CHECK();
-    SEEVCN_CUDA_CHECK(cudaMemsetAsync(ws + w.off_scan, 0, w.scan_bytes, st));
-    seevcn_scan::exclusive_scan_u32_kernel<<<w.scan_tiles, seevcn_scan::kScanThreads, 0, st>>>(
-        num_points, reinterpret_cast<const unsigned*>(flag), reinterpret_cast<unsigned*>(rank),
-        reinterpret_cast<unsigned long long*>(ws + w.off_scan), reinterpret_cast<int*>(ws + w.off_scan + 8 * (size_t)w.scan_tiles),
-        nullptr);
-    SEEVCN_LAUNCH_CHECK();
-    hardvox_assign_kernel<<<gp, 256, 0, st>>>(num_points, max_voxels, g, keys, slot, flag, rank, vid, coordinates, num_voxels);
-    SEEVCN_LAUNCH_CHECK();
-    hardvox_pick_kernel<<<gp, 256, 0, st>>>(num_points, max_points, slot, vid, sel, cnt);
-    SEEVCN_LAUNCH_CHECK();
-    const long long tot = (long long)max_voxels * max_points;
-    hardvox_gather_kernel<<<(unsigned)div_up(tot, 256ll), 256, 0, st>>>(max_voxels, max_points, num_features, points,
-                                                                        num_voxels, sel, cnt, voxels, num_points_per_voxel);
-    SEEVCN_LAUNCH_CHECK();
-    return SEEVCN_OK;
+    return hardvox_run("hard_voxelize", 1, num_points, num_features, points, nullptr, pc_range, voxel_size, grid_size, max_points,
+                       max_voxels, 0, voxels, coordinates, num_points_per_voxel, num_voxels, workspace, workspace_bytes, st);
+}
+
+extern "C" int seevcn_hard_voxelize_frames(int num_frames, int stride, int num_features, const float* points, const int* counts,
+                                           const float* pc_range, const float* voxel_size, const int* grid_size,
+                                           int max_points, int max_voxels, float* voxels, int* coordinates,
+                                           int* num_points_per_voxel, int* num_voxels, void* workspace, size_t workspace_bytes,
+                                           seevcn_stream_t stream) {
+    SEEVCN_REQUIRE(num_frames >= 0 && stride >= 0 && max_points >= 1 && max_voxels >= 0, "hard_voxelize_frames: bad sizes");
+    SEEVCN_REQUIRE(num_features >= 3, "hard_voxelize_frames: num_features must be >= 3");
+    SEEVCN_REQUIRE(pc_range && voxel_size && grid_size && (num_voxels || num_frames == 0), "hard_voxelize_frames: null pointer");
+    cudaStream_t st = as_stream(stream);
+    if (num_frames == 0) return SEEVCN_OK;
+    SEEVCN_CUDA_CHECK(cudaMemsetAsync(num_voxels, 0, sizeof(int) * (size_t)num_frames, st));
+    if (stride == 0 || max_voxels == 0) return SEEVCN_OK;
+    SEEVCN_REQUIRE(points && voxels && coordinates && num_points_per_voxel && workspace, "hard_voxelize_frames: null pointer");
+    return hardvox_run("hard_voxelize_frames", num_frames, stride, num_features, points, counts, pc_range, voxel_size, grid_size,
+                       max_points, max_voxels, 1, voxels, coordinates, num_points_per_voxel, num_voxels, workspace, workspace_bytes, st);
 }

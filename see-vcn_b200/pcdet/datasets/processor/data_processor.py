@@ -52,6 +52,29 @@ class VoxelGeneratorWrapper():
         m = min(int(num.item()), MV)
         return voxels[:m], coords[:m], num_pts[:m]
 
+    def generate_frames_device(self, points, counts=None):
+        """The batched form of the frame pipeline: points (F, stride, C) float32 CUDA, counts (F,) int32 CUDA or None
+        (rows >= counts[f] of frame f are padding) -> voxels (F, MV, T, C), coordinates (F, MV, 4) int32 [frame, z, y, x]
+        (what collate_batch builds, dataset.py:193-198), num_points (F, MV) int32, num_voxels (F,) int32 CUDA.  Slots
+        >= num_voxels[f] are padding (num_points 0).  No host synchronisation."""
+        points = points.contiguous()
+        _abi.require_cuda(points, counts)
+        F, S, C = points.shape
+        dev = points.device
+        L = _abi.lib()
+        T, MV = self.max_num_points_per_voxel, self.max_num_voxels
+        ws = _abi.workspace(dev, L.seevcn_hard_voxelize_frames_workspace_bytes(F, S, T, MV), "hardvox")
+        voxels = torch.empty((F, MV, T, C), dtype=torch.float32, device=dev)
+        coords = torch.empty((F, MV, 4), dtype=torch.int32, device=dev)
+        num_pts = torch.empty((F, MV), dtype=torch.int32, device=dev)
+        num = torch.empty((F,), dtype=torch.int32, device=dev)
+        with _abi.device_guard(dev):
+            _abi.check(L.seevcn_hard_voxelize_frames(F, S, C, _abi.ptr(points), _abi.ptr(counts), _abi.farray(self.coors_range_xyz),
+                                                     _abi.farray(self.vsize_xyz), _abi.iarray(self.grid_size), T, MV,
+                                                     _abi.ptr(voxels), _abi.ptr(coords), _abi.ptr(num_pts), _abi.ptr(num),
+                                                     _abi.ptr(ws), ws.numel(), _abi.stream()))
+        return voxels, coords, num_pts, num
+
     def generate(self, points):
         """numpy (N, C) in -> numpy (voxels, coordinates, num_points) out, like the reference wrapper."""
         if isinstance(points, np.ndarray):

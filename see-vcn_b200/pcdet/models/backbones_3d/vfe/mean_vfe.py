@@ -19,12 +19,15 @@ class MeanVFE(VFETemplate):
         = voxels.sum(1) / clamp_min(num_points, 1)"""
         require_keys(batch_dict, 'voxels', 'voxel_num_points')
         voxels = batch_dict['voxels'].contiguous()
-        num = batch_dict['voxel_num_points'].to(torch.float32).contiguous()
+        num = batch_dict['voxel_num_points'].contiguous()
+        if num.dtype not in (torch.float32, torch.int32):      # int32 counts go to the kernel as they are
+            num = num.to(torch.float32)
         _abi.require_cuda(voxels, num)
         assert voxels.dtype == torch.float32
         M, T, C = voxels.shape
         out = torch.empty((M, C), dtype=torch.float32, device=voxels.device)
+        fn = _abi.lib().seevcn_mean_vfe if num.dtype == torch.float32 else _abi.lib().seevcn_mean_vfe_int
         with _abi.device_guard(voxels.device):
-            _abi.check(_abi.lib().seevcn_mean_vfe(M, T, C, _abi.ptr(voxels), _abi.ptr(num), _abi.ptr(out), _abi.stream()))
+            _abi.check(fn(M, T, C, _abi.ptr(voxels), _abi.ptr(num), _abi.ptr(out), _abi.stream()))
         batch_dict['voxel_features'] = out
         return batch_dict

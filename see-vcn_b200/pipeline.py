@@ -31,7 +31,8 @@ class _Crop:
 
 class CompletionPipeline:
     def __init__(self, model_name="VCN_VC", state_dict=None, device=None, sel_k=10, min_lidar_pts=30, resample_num=1024,
-                 voxel_cfg=WAYMO_VOXEL_CFG, precision="bf16", host_rng=False, cluster_eps=None, splice_thresh=None):
+                 voxel_cfg=WAYMO_VOXEL_CFG, precision="bf16", host_rng=False, cluster_eps=None, splice_thresh=None,
+                 hard_voxels=None):
         self.device = device if device is not None else torch.device("cuda", torch.cuda.current_device())
         self.model = MODELS.build({"NAME": model_name}, precision=precision)
         self.state_dict = state_dict
@@ -47,6 +48,10 @@ class CompletionPipeline:
         self.cluster_eps = cluster_eps        # SURFACE_COMPLETION.VCN.CLUSTER_EPS; None skips the largest-cluster filter
         self._pinned_in_flight = []
         self.splice_thresh = splice_thresh    # replace_with_completed_pts point_dist_thresh (SEE_VCN.py:247); None = no splice
+        # (max points per voxel, max voxels per frame): the detector front end of the SECOND-IoU configs — per-frame hard
+        # voxels + MeanVFE (data_processor.py:115-143, mean_vfe.py:14-31) instead of the dynamic scatter-mean
+        self.hard_voxels = hard_voxels
+        self._hard_gen = None
 
     def _to_host_async(self, t):
         """Small device tensor (4-byte elements) -> pinned host copy, written by a copy kernel on the current stream
@@ -143,6 +148,8 @@ class CompletionPipeline:
         F, P, _ = points.shape
         completed = out.get("clustered", out["surface"])
         keep = count = None
+        if self.hard_voxels is not None:
+            return self._run_hard(out, points, completed, defer)
         if self.splice_thresh is not None and completed.shape[0] > 0:
             # SEE_VCN.py:244,247-265: the frame the detector sees = distinct completed points ++ raw points farther
             # than thresh from all of them.  The mask feeds the voxelizer directly; the merged cloud is not built.
@@ -159,6 +166,43 @@ class CompletionPipeline:
         out["_done"] = torch.cuda.Event()
         out["_done"].record(torch.cuda.current_stream(self.device))
         return out if defer else self.finalize(out)
+
+    def _run_hard(self, out, points, completed, defer):
+        """Merged frame clouds (SEE_VCN.py:247-265) -> hard voxels per frame -> MeanVFE, padded per frame, no host sync:
+        voxel_coords (F*MV, 4) [frame, z, y, x], voxel_features (F*MV, 3), voxel_num_points (F*MV,) (0 = padding slot),
+        hard_num_voxels (F,)."""
+        from .pcdet.datasets.processor.data_processor import VoxelGeneratorWrapper
+        from .pcdet.models.backbones_3d.vfe.mean_vfe import MeanVFE
+        F, P, _ = points.shape
+        thresh = self.splice_thresh if self.splice_thresh is not None else 0.0
+        has_obj = completed.shape[0] > 0
+        count = out.get("clustered_distinct", out.get("surface_count")) if has_obj else None
+        keep, merged, m_cnt, c_cnt = splice_frames(points, completed if has_obj else None, out.get("obj_frame_dev"), count,
+                                                   thresh, merged=True)
+        if self._hard_gen is None:
+            T, MV = self.hard_voxels
+            self._hard_gen = VoxelGeneratorWrapper(self.voxel_cfg[1], self.voxel_cfg[0], 3, T, MV)
+            self._hard_vfe = MeanVFE(model_cfg={}, num_point_features=3)
+        voxels, coords, npts, nvox = self._hard_gen.generate_frames_device(merged, m_cnt)
+        MV, T = voxels.shape[1], voxels.shape[2]
+        feats = self._hard_vfe({"voxels": voxels.view(F * MV, T, 3), "voxel_num_points": npts.view(F * MV)})["voxel_features"]
+        out.update(frame_keep=keep, completed_count=count, merged=merged, merged_count=m_cnt, voxels=voxels,
+                   voxel_coords=coords.view(F * MV, 4), voxel_features=feats, voxel_num_points=npts.view(F * MV),
+                   hard_num_voxels=nvox)
+        out["_frame_points"] = points
+        out["_done"] = torch.cuda.Event()
+        out["_done"].record(torch.cuda.current_stream(self.device))
+        return out
+
+    @staticmethod
+    def hard_points_in(out, voxel_cfg):
+        """Merged points that fall inside the voxel grid (what the hard voxelizer was offered), host int.  Diagnostics."""
+        m, cnt = out["merged"], out["merged_count"]
+        F, S, _ = m.shape
+        lo = torch.tensor(voxel_cfg[0][:3], device=m.device); hi = torch.tensor(voxel_cfg[0][3:], device=m.device)
+        valid = torch.arange(S, device=m.device).view(1, S) < cnt.view(F, 1)
+        inside = ((m >= lo) & (m < hi)).all(dim=2) & valid
+        return int(inside.sum().item())
 
     def finalize(self, out):
         """Waits for M only (not for the stream) and exposes voxel_coords / voxel_features / voxel_num_points."""

@@ -5,7 +5,7 @@ import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
 
-from seevcn_b200.dist import shard_range, all_gather_v, all_gather_padded, rebase_batch_index
+from seevcn_b200.dist import shard_range, all_gather_v, all_gather_padded, rebase_batch_index, FrameGather
 
 
 def test_shard_range_covers_everything():
@@ -29,6 +29,23 @@ def _worker(rank, world, port, ret):
     allc, _ = all_gather_v(rebase_batch_index(coords, lo))
     pg = all_gather_padded(local, 4, async_op=True)            # streaming form: fixed capacity, counts as a tensor
     parts = pg.parts()
+    # the per-batch collection of completed clouds + voxel tensors (gloo runs the all-gather fallback)
+    fg = FrameGather(torch.device("cpu"), world, rank, max_obj=4, rows_per_obj=4, frames=2, max_rows=64)
+    gens = []
+    for k in range(3):
+        m = 3 + rank + k
+        out = {"clustered": local + k, "voxel_coords": torch.arange(m * 4, dtype=torch.int32).view(m, 4) * (rank + 1),
+               "voxel_features": torch.full((m, 3), float(rank + k)), "voxel_num_points": torch.full((m,), rank + 7, dtype=torch.int32)}
+        gens.append(fg.push(out, frame_offset=lo))
+    got = fg.parts(gens[-1])                                   # generation of the last push (k = 2)
+    if rank == 0:
+        ret["fg_kind"] = fg.kind
+        ret["fg_obj"] = [int(p["clustered"].shape[0]) for p in got]
+        ret["fg_clu"] = torch.cat([p["clustered"] for p in got]).clone()
+        ret["fg_m"] = [int(p["voxel_coords"].shape[0]) for p in got]
+        ret["fg_b0"] = [int(p["voxel_coords"][0, 0]) for p in got]
+        ret["fg_num"] = [int(p["voxel_num_points"][0]) for p in got]
+        ret["fg_feat"] = [float(p["voxel_features"][0, 0]) for p in got]
     if rank == 0:
         ret["full"] = full.clone(); ret["counts"] = counts; ret["coords"] = allc.clone()
         ret["padded_counts"] = pg.counts.tolist(); ret["padded"] = torch.cat(parts).clone(); ret["padded_shape"] = tuple(pg.out.shape)
@@ -45,3 +62,6 @@ def test_all_gather_v_gloo_world2():
     assert ret["coords"][:, 0].tolist() == [0, 2, 3, 4]
     assert ret["padded_counts"] == [3, 2] and ret["padded_shape"] == (2, 4, 4, 3)
     assert torch.equal(ret["padded"], ret["full"])
+    assert ret["fg_kind"] == "gloo" and ret["fg_obj"] == [3, 2] and ret["fg_m"] == [5, 6]
+    assert torch.equal(ret["fg_clu"], ret["full"] + 2)
+    assert ret["fg_b0"] == [0, 3] and ret["fg_num"] == [7, 8] and ret["fg_feat"] == [2.0, 3.0]

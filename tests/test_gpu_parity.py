@@ -470,6 +470,35 @@ def test_vcn_forward_dense_decoder_c4_shape(cuda):
     np.testing.assert_array_equal(surf.cpu().numpy(), wsurf)
 
 
+def test_hard_voxelize_frames_vs_oracle_per_frame(cuda):
+    """The batched hard voxelizer (F frames, padded outputs, device-side row counts) against the oracle frame by frame;
+    MeanVFE with the int32 counts on the padded slots."""
+    rng = np.random.default_rng(4)
+    F, S, MV, T = 3, 40000, 20000, 5
+    pts, _ = synth.make_stream(F, n_beams=32, n_az=1250, n_boxes=8, first_seed=40)
+    pts = pts[:, rng.permutation(pts.shape[1])]
+    counts = np.array([40000, 25000, 31111], np.int32)
+    gen = VoxelGeneratorWrapper(WAYMO[1], WAYMO[0], 3, T, MV)
+    v, c, n, nv = gen.generate_frames_device(dev(pts, cuda), dev(counts, cuda))
+    assert tuple(v.shape) == (F, MV, T, 3) and tuple(c.shape) == (F, MV, 4)
+    feats = MeanVFE(model_cfg={}, num_point_features=3)({"voxels": v.view(F * MV, T, 3), "voxel_num_points": n.view(-1)})["voxel_features"]
+    feats = feats.view(F, MV, 3).cpu().numpy()
+    v, c, n, nv = v.cpu().numpy(), c.cpu().numpy(), n.cpu().numpy(), nv.cpu().numpy()
+    capped = 0
+    for f in range(F):
+        wv, wc, wn = oracle.hard_voxelize(pts[f, : counts[f]], WAYMO[0], WAYMO[1], WAYMO[2], T, MV)
+        m = int(nv[f])
+        assert m == len(wc)
+        capped += m == MV
+        np.testing.assert_array_equal(c[f, :m, 1:], wc)
+        assert (c[f, :m, 0] == f).all()
+        np.testing.assert_array_equal(n[f, :m], wn)
+        np.testing.assert_array_equal(v[f, :m], wv)
+        assert (n[f, m:] == 0).all()
+        np.testing.assert_allclose(feats[f, :m], oracle.mean_vfe(wv, wn.astype(np.float32)), rtol=1e-6, atol=1e-6)
+    assert capped >= 1            # the per-frame voxel cap was hit at least once
+
+
 # ------------------------------------------------------------------ stage 6: voxelization --
 WAYMO = ([-75.2, -75.2, -2, 75.2, 75.2, 4], [0.1, 0.1, 0.15], [1504, 1504, 40])
 

@@ -234,3 +234,36 @@ def test_pipeline_voxels_are_bit_reproducible(cuda):
         out = pipe.run(d_pts, d_boxes, seed=0)
         for key in ("voxel_coords", "voxel_num_points", "voxel_features"):
             np.testing.assert_array_equal(out[key].cpu().numpy(), ref[key].cpu().numpy())
+
+
+def test_pipeline_hard_voxels_second_iou_front_end(cuda):
+    """BASELINE.json configs[4] (C5): completion + splice -> merged frame clouds -> per-frame hard voxels (5 points per
+    voxel, per-frame cap) -> MeanVFE, all on the device and padded per frame; checked frame by frame against the oracle
+    run on the merged cloud the reference would have written (SEE_VCN.py:247-265, data_processor.py:78-143,
+    mean_vfe.py:14-31)."""
+    from seevcn_b200.pipeline import CompletionPipeline, WAYMO_VOXEL_CFG
+    T, MV = 5, 30000
+    pipe = CompletionPipeline("VCN_VC", oracle.make_state_dict("VCN_VC", seed=0), cuda, sel_k=10, cluster_eps=0.3,
+                              splice_thresh=0.1, hard_voxels=(T, MV))
+    pts, boxes = synth.make_stream(2, n_beams=32, n_az=1090, n_boxes=10, first_seed=300)
+    out = pipe.run(dev(pts, cuda), dev(boxes, cuda), seed=0)
+    comp, cnt, ofr = out["clustered"].cpu().numpy(), out["completed_count"].cpu().numpy(), out["obj_frame"]
+    want_keep, want_merged = _want(pts, comp, ofr, cnt, 0.1)
+    coords = out["voxel_coords"].view(2, MV, 4).cpu().numpy()
+    feats = out["voxel_features"].view(2, MV, 3).cpu().numpy()
+    nums = out["voxel_num_points"].view(2, MV).cpu().numpy()
+    nv = out["hard_num_voxels"].cpu().numpy()
+    rg = WAYMO_VOXEL_CFG[0]
+    total_in = 0
+    for f in range(2):
+        m = want_merged[f]
+        np.testing.assert_array_equal(out["merged"][f, : int(out["merged_count"][f])].cpu().numpy(), m)
+        masked = m[(m[:, 0] >= rg[0]) & (m[:, 0] <= rg[3]) & (m[:, 1] >= rg[1]) & (m[:, 1] <= rg[4])]   # data_processor.py:78-91
+        wv, wc, wn = oracle.hard_voxelize(masked, *WAYMO_VOXEL_CFG, T, MV)
+        k = int(nv[f])
+        assert k == len(wc) and k > 5000
+        np.testing.assert_array_equal(coords[f, :k, 1:], wc)
+        np.testing.assert_array_equal(nums[f, :k], wn)
+        np.testing.assert_allclose(feats[f, :k], oracle.mean_vfe(wv, wn.astype(np.float32)), rtol=1e-6, atol=1e-6)
+        total_in += int((((m >= np.array(rg[:3], np.float32)) & (m < np.array(rg[3:], np.float32))).all(1)).sum())
+    assert pipe.hard_points_in(out, WAYMO_VOXEL_CFG) == total_in
