@@ -55,7 +55,10 @@ __device__ __forceinline__ Cand warp_argmax(Cand c, unsigned mask) {
     return c;   // valid in every lane
 }
 
-// PPT: points per thread held in registers.  SMEM_XYZ: xyz staged in shared memory.
+// PPT: points per thread (their min-distances live in registers).  SMEM_XYZ: xyz staged in shared memory.
+// The coordinates of the first REG of a thread's points are kept in registers as well: at PPT = 16 a round reads
+// 3 x 16,384 floats from shared memory (196 KB = ~1,500 cycles of shared-memory bandwidth, the bulk of a round);
+// holding half of them in the register file (64 registers per thread at 1024 threads) halves that.
 template <int PPT, bool SMEM_XYZ>
 __global__ void __launch_bounds__(1024)
 fps_kernel(int n, int m, int bs, const float* __restrict__ dataset, float* __restrict__ temp, int* __restrict__ idxs) {
@@ -79,13 +82,14 @@ fps_kernel(int n, int m, int bs, const float* __restrict__ dataset, float* __res
         }
         __syncthreads();
     }
+    constexpr int REG = (!SMEM_XYZ || PPT <= 4) ? PPT : (PPT <= 8 ? 6 : 8);
     float dist[PPT];
-    float px[PPT], py[PPT], pz[PPT];
+    float px[REG], py[REG], pz[REG];
 #pragma unroll
     for (int j = 0; j < PPT; ++j) {
         dist[j] = 1e10f;   // pointnet2_utils.py:26
         const int k = tid + j * bs;
-        if (!SMEM_XYZ || PPT <= 4) {   // few points per thread: keep coordinates in registers too
+        if (j < REG) {
             const bool ok = k < n;
             px[j] = ok ? (SMEM_XYZ ? sx[k] : dataset[k * 3 + 0]) : 0.f;
             py[j] = ok ? (SMEM_XYZ ? sy[k] : dataset[k * 3 + 1]) : 0.f;
@@ -104,7 +108,7 @@ fps_kernel(int n, int m, int bs, const float* __restrict__ dataset, float* __res
             const int k = tid + j * bs;
             if (k < n && tid < bs) {
                 float x2, y2, z2;
-                if (!SMEM_XYZ || PPT <= 4) { x2 = px[j]; y2 = py[j]; z2 = pz[j]; }
+                if (j < REG) { x2 = px[j]; y2 = py[j]; z2 = pz[j]; }
                 else { x2 = sx[k]; y2 = sy[k]; z2 = sz[k]; }
                 const float dx = __fsub_rn(x2, x1), dy = __fsub_rn(y2, y1), dz = __fsub_rn(z2, z1);
                 const float d = __fmaf_rn(dz, dz, __fmaf_rn(dy, dy, __fmul_rn(dx, dx)));
@@ -176,6 +180,7 @@ int launch_fps(int b, int n, int m, int bs, const float* dataset, float* temp, i
     auto kern = fps_kernel<PPT, true>;
     if (smem > 40 * 1024)   // dynamic + 512 B static must stay under the 48 KB default
         SEEVCN_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    SEEVCN_PROF("fps", st);
     kern<<<b, bs < 32 ? 32 : bs, smem, st>>>(n, m, bs, dataset, temp, idxs);
     SEEVCN_LAUNCH_CHECK();
     return SEEVCN_OK;
@@ -201,6 +206,7 @@ extern "C" int seevcn_furthest_point_sampling(int b, int n, int m, const float* 
         return launch_fps<16>(b, n, m, bs, dataset, temp, idxs, st);
     }
     SEEVCN_REQUIRE(temp != nullptr, "fps: n=%d needs the temp (B,N) scratch buffer", n);
+    SEEVCN_PROF("fps", st);
     fps_kernel_global<<<b, bs < 32 ? 32 : bs, 0, st>>>(n, m, bs, dataset, temp, idxs);
     SEEVCN_LAUNCH_CHECK();
     return SEEVCN_OK;

@@ -34,6 +34,7 @@ extern "C" int seevcn_gather_points(int b, int c, int n, int npoints, const floa
     SEEVCN_REQUIRE(points && idx && out, "gather_points: null pointer");
     SEEVCN_REQUIRE(b <= 65535, "gather_points: b > 65535");
     dim3 grid(div_up(npoints, 256), b);
+    SEEVCN_PROF("gather_points", as_stream(stream));
     gather_kernel<<<grid, 256, 0, as_stream(stream)>>>(c, n, npoints, points, idx, out);
     SEEVCN_LAUNCH_CHECK();
     return SEEVCN_OK;
@@ -49,6 +50,7 @@ extern "C" int seevcn_group_points(int b, int c, int n, int npoints, int nsample
     SEEVCN_REQUIRE(points && idx && out, "group_points: null pointer");
     SEEVCN_REQUIRE(b <= 65535, "group_points: b > 65535");
     dim3 grid(div_up((int)m, 256), b);
+    SEEVCN_PROF("group_points", as_stream(stream));
     gather_kernel<<<grid, 256, 0, as_stream(stream)>>>(c, n, (int)m, points, idx, out);
     SEEVCN_LAUNCH_CHECK();
     return SEEVCN_OK;
