@@ -246,6 +246,43 @@ int seevcn_linear_bf16(int rows, int cin, int cout, const float* X, const float*
                        const float* obj_bias, int rows_per_obj, int act, float* Y, float* colmax,
                        void* workspace, size_t workspace_bytes, seevcn_stream_t stream);
 
+/* ------------------------------------------------ mask-based isolation */
+
+/* ref: CustomDatasetObjects.map_pointcloud_to_image
+ *      see/surface_completion/datasets/custom_dataset/custom_dataset_objects.py:141-193 (float64 numpy on the host).
+ * pts (N,3) f32 DEVICE; lidar2cam[12] = rows of extrinsic[:3,:], intrinsic[9] = 3x3 row major, distcoeff[5]: HOST float64
+ * (calibration constants).  equidistant != 0 selects the fisheye model, else pinhole (k1 k2 p1 p2 k3 = distcoeff[0..4]).
+ * -> uv (N,2) int32 = (np.round(u), np.round(v)) for points in the field of view, (-1,-1) otherwise; fov (N) uint8;
+ * depth (N) f32 or NULL (camera-frame z). */
+int seevcn_project_points(int num_points, const float* pts, const double* lidar2cam, const double* intrinsic,
+                          const double* distcoeff, int equidistant, int img_w, int img_h,
+                          int* uv, unsigned char* fov, float* depth, seevcn_stream_t stream);
+
+/* ref: get_pts_in_mask  see/surface_completion/datasets/shared_utils.py:36-106 (mask[v, u] lookup per instance).
+ * masks (I, img_h, img_w) uint8 binary instance masks (the polygon -> mask rasterisation, pycocotools annToMask, stays
+ * with the caller) -> lists (I, N) int32: ascending indices of the in-view points inside mask i; counts (I). */
+int seevcn_points_in_masks(int num_points, int num_inst, int img_w, int img_h, const int* uv, const unsigned char* fov,
+                           const unsigned char* masks, int* lists, int* counts, seevcn_stream_t stream);
+
+/* ref: SEE_VCN.isolate_det_pts  see/surface_completion/SEE_VCN.py:144-181: per instance with more than
+ * min_instance_pts points, eps = clip(eps_scaling * |centre| * tan(vres deg), min_eps, max_eps) (adaptive != 0) or the
+ * fixed eps, open3d cluster_dbscan(eps, min_points), the largest cluster (first on ties), kept when it holds more than
+ * min_instance_pts points.  lists (I, stride) indices into pts (P,3) with counts (I) (the output of
+ * seevcn_points_in_masks) -> out_lists (I, stride): the cluster's point indices, ascending; out_counts (I): their number
+ * (0: dropped); out_eps (I) float64 or NULL.  Instances of up to 9600 points are clustered in shared memory; larger ones
+ * take 24 B per point from `workspace` (may be NULL) and report -1 when it is too small — call again with more.
+ * PARITY UNPINNED (open3d). */
+int seevcn_dbscan_largest(int num_inst, int stride, const float* pts, const int* lists, const int* counts,
+                          int adaptive, double eps, double vres_deg, double eps_scaling, double min_eps, double max_eps,
+                          int min_points, int min_instance_pts, int* out_lists, int* out_counts, double* out_eps,
+                          void* workspace, size_t workspace_bytes, seevcn_stream_t stream);
+
+/* ref: ResamplePoints (data_transforms.py:247-262) applied to isolated instances (models/VCN.py:52-53): object o is
+ * list row obj_inst[o]; out[o, j] = pts[lists[inst][perm(j) % count]], perm = seevcn_resample_perm(j, reps * count, seed,
+ * inst).  out (num_obj, n_points, 3). */
+int seevcn_resample_lists(int num_obj, int n_points, int stride, unsigned seed, const float* pts, const int* lists,
+                          const int* counts, const int* obj_inst, float* out, seevcn_stream_t stream);
+
 /* ---------------------------------------------- splice: completed clouds replace raw points */
 
 /* ref: SEE_VCN.replace_with_completed_pts  see/surface_completion/SEE_VCN.py:247-265 (demo twin

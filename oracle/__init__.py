@@ -169,6 +169,109 @@ def distinct_rows(clustered, counts):
                        for o in range(len(clustered))], np.int32)
 
 
+# ------------------------------------------------------------------- mask-based isolation --
+def map_pointcloud_to_image(points, calib, img_shape, camera_model="pinhole"):
+    """ref: CustomDatasetObjects.map_pointcloud_to_image, datasets/custom_dataset/custom_dataset_objects.py:141-193,
+    restated line by line (float64 numpy).  -> dict pc_lidar (K,3), pts_img (K,2) int, fov_inds (N,) bool"""
+    points = np.asarray(points, dtype=np.float64)
+    IMG_H, IMG_W = int(img_shape[0]), int(img_shape[1])
+    cameramat = np.asarray(calib["intrinsic"], np.float64)
+    lidar2cam = np.asarray(calib["extrinsic"], np.float64)
+    distcoeff = np.zeros(5); dc = np.asarray(calib["distcoeff"], np.float64).reshape(-1); distcoeff[: min(5, dc.size)] = dc[:5]
+    pts_3d_hom = np.hstack((points, np.ones((points.shape[0], 1)))).T
+    pts_imgframe = (lidar2cam[:3, :] @ pts_3d_hom).T
+    with np.errstate(divide="ignore", invalid="ignore"):
+        tmpxC = pts_imgframe[:, 0] / pts_imgframe[:, 2]
+        tmpyC = pts_imgframe[:, 1] / pts_imgframe[:, 2]
+    pre = (pts_imgframe[:, 2] > 0) & (abs(tmpxC) < np.arctan(IMG_W / IMG_H))
+    tmpxC, tmpyC, depth = tmpxC[pre], tmpyC[pre], pts_imgframe[:, 2][pre]
+    r2 = tmpxC ** 2 + tmpyC ** 2
+    if camera_model == "equidistant":
+        r1 = np.sqrt(r2)
+        a0 = np.arctan(r1)
+        a1 = a0 * (1 + distcoeff[0] * (a0 ** 2) + distcoeff[1] * (a0 ** 4) + distcoeff[2] * (a0 ** 6) + distcoeff[3] * (a0 ** 8))
+        u = (a1 / r1) * tmpxC
+        v = (a1 / r1) * tmpyC
+    elif camera_model == "pinhole":
+        tmpdist = 1 + distcoeff[0] * r2 + distcoeff[1] * (r2 ** 2) + distcoeff[4] * (r2 ** 3)
+        u = tmpxC * tmpdist + 2 * distcoeff[2] * tmpxC * tmpyC + distcoeff[3] * (r2 + 2 * tmpxC ** 2)
+        v = tmpyC * tmpdist + distcoeff[2] * (r2 + 2 * tmpyC ** 2) + 2 * distcoeff[3] * tmpxC * tmpyC
+    else:
+        raise NotImplementedError
+    u = cameramat[0, 0] * u + cameramat[0, 2]
+    v = cameramat[1, 1] * v + cameramat[1, 2]
+    fov = (u > 0) & (u < IMG_W - 1) & (v > 0) & (v < IMG_H - 1)
+    combined = np.zeros(pre.shape, dtype=bool)
+    combined[pre] = fov
+    uv = np.stack([u[fov], v[fov]], axis=1)
+    # distance of u, v from the nearest rounding boundary (x.5): where the last float64 bit decides the pixel
+    slack = np.abs((uv - np.floor(uv)) - 0.5).min(axis=1) if len(uv) else np.zeros((0,))
+    return {"pc_lidar": points[combined].astype(np.float32), "pts_img": np.round(uv, 0).astype(int), "fov_inds": combined,
+            "depth": depth[fov], "round_slack": slack}
+
+
+def get_pts_in_mask(masks, imgfov):
+    """ref: get_pts_in_mask, datasets/shared_utils.py:36-106 (binary masks given) -> list of index arrays into the frame."""
+    idx = np.nonzero(imgfov["fov_inds"])[0]
+    px = imgfov["pts_img"]
+    return [idx[np.asarray(m[px[:, 1], px[:, 0]], dtype=bool)] for m in masks]
+
+
+def cluster_dbscan(xyz, eps, min_points):
+    """open3d 0.14 PointCloud::ClusterDBSCAN restated as the sequential expansion it is (PARITY UNPINNED: open3d absent):
+    float64 radius search with strict dist < eps (the point itself included), clusters numbered in discovery order,
+    a border point joins the first cluster that reaches it.  -> labels (N,) int, -1 = noise."""
+    p = np.asarray(xyz, dtype=np.float64)
+    n = len(p)
+    d2 = ((p[:, None, :] - p[None, :, :]) ** 2)
+    d2 = (d2[:, :, 0] + d2[:, :, 1]) + d2[:, :, 2]
+    nbs = [np.nonzero(d2[i] < eps * eps)[0] for i in range(n)]
+    labels = np.full(n, -2, dtype=np.int64)
+    cluster = 0
+    for idx in range(n):
+        if labels[idx] != -2:
+            continue
+        if len(nbs[idx]) < min_points:
+            labels[idx] = -1
+            continue
+        nxt = list(nbs[idx]); seen = set(nxt) | {idx}
+        labels[idx] = cluster
+        while nxt:
+            nb = nxt.pop(0)
+            if labels[nb] == -1:
+                labels[nb] = cluster
+            if labels[nb] != -2:
+                continue
+            labels[nb] = cluster
+            if len(nbs[nb]) >= min_points:
+                for q in nbs[nb]:
+                    if q not in seen:
+                        seen.add(q); nxt.append(q)
+        cluster += 1
+    return labels
+
+
+def isolate_det_pts(points, inst_indices, vres, eps_scaling, min_eps, max_eps, min_cluster=10):
+    """ref: SEE_VCN.isolate_det_pts, see/surface_completion/SEE_VCN.py:144-181 -> list over instances of the kept
+    cluster's frame indices (None when the instance is dropped), and the eps used."""
+    out, eps_used = [], []
+    for ind in inst_indices:
+        xyz = np.asarray(points, np.float64)[ind]
+        sel, eps = None, 0.0
+        if xyz.shape[0] > min_cluster:
+            dist = np.linalg.norm(xyz.mean(axis=0))
+            ring_height = dist * np.tan(vres * np.pi / 180)
+            eps = float(np.clip(eps_scaling * ring_height, a_max=max_eps, a_min=min_eps))
+            labels = cluster_dbscan(xyz, eps, 3)
+            y = np.bincount(labels[labels >= 0])
+            if len(y) > 0:
+                members = np.argwhere(labels == np.argmax(y)).reshape(-1)
+                if len(members) > min_cluster:
+                    sel = ind[members]
+        out.append(sel); eps_used.append(eps)
+    return out, eps_used
+
+
 # --------------------------------------------------------------------------- splice --
 def nearest_dist(points, completed, brute=False):
     """Distance (float64) from every row of points (P,3) to its nearest row of completed (K,3): what

@@ -76,6 +76,12 @@ SIGNATURES = {
     "seevcn_hard_voxelize_frames_workspace_bytes": (c_size_t, [I, I, I, I]),
     "seevcn_hard_voxelize_frames": (I, [I, I, I, P, P, POINTER(ctypes.c_float), POINTER(ctypes.c_float), POINTER(c_int),
                                         I, I, P, P, P, P, P, c_size_t, P]),
+    "seevcn_project_points": (I, [I, P, POINTER(ctypes.c_double), POINTER(ctypes.c_double), POINTER(ctypes.c_double), I, I, I,
+                                  P, P, P, P]),
+    "seevcn_points_in_masks": (I, [I, I, I, I, P, P, P, P, P, P]),
+    "seevcn_dbscan_largest": (I, [I, I, P, P, P, I, ctypes.c_double, ctypes.c_double, ctypes.c_double, ctypes.c_double,
+                                  ctypes.c_double, I, I, P, P, P, P, c_size_t, P]),
+    "seevcn_resample_lists": (I, [I, I, I, ctypes.c_uint, P, P, P, P, P, P]),
     "seevcn_chamfer": (I, [I, I, I, P, P, P, P, P]),
     "seevcn_copy_to_pinned": (I, [P, P, c_size_t, P]),
     "seevcn_copy_from_pinned": (I, [P, P, c_size_t, P]),

@@ -333,30 +333,6 @@ __global__ void resample_gather_kernel(int num_obj, int n_points, int boxes_num,
     d[0] = x; d[1] = y; d[2] = z;
 }
 
-// Pseudo-random permutation of [0, n) evaluated point-wise: a 4-round Feistel network on
-// m = ceil(log2 n) bits (made even) with cycle walking.  perm(j) for j = 0..n_points-1 are the first
-// n_points entries of one permutation — exactly what ResamplePoints draws
-// (np.random.permutation(len)[:n], data_transforms.py:258-260), without a host RNG or a sort.
-__host__ __device__ inline unsigned mix32(unsigned x) {
-    x ^= x >> 16; x *= 0x7feb352du; x ^= x >> 15; x *= 0x846ca68bu; x ^= x >> 16;
-    return x;
-}
-__host__ __device__ inline unsigned feistel_perm(unsigned j, unsigned n, unsigned key) {
-    unsigned bits = 2;
-    while ((1u << bits) < n) bits += 2;            // even number of bits >= log2 n
-    const unsigned half = bits >> 1, hmask = (1u << half) - 1u;
-    unsigned v = j;
-    do {
-        unsigned l = v >> half, r = v & hmask;
-#pragma unroll
-        for (unsigned round = 0; round < 4; ++round) {
-            const unsigned f = mix32(r ^ (key + 0x9e3779b9u * (round + 1))) & hmask;
-            const unsigned nl = r; r = l ^ f; l = nl;
-        }
-        v = (l << half) | r;
-    } while (v >= n);                               // cycle walking keeps it a bijection on [0, n)
-    return v;
-}
 
 __global__ void resample_gather_rng_kernel(int num_obj, int n_points, int boxes_num, int pts_num, unsigned seed,
                                            const float* __restrict__ pts, const int* __restrict__ box_counts,

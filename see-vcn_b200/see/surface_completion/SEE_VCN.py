@@ -69,3 +69,34 @@ def replace_with_completed_pts(original_points, sc_instances, point_dist_thresh=
     frame = torch.zeros((1,), dtype=torch.int32, device=dev)
     _, merged, m_cnt, _ = splice_frames(d_pts, d_sc, frame, None, point_dist_thresh, merged=True)
     return merged[0, : int(m_cnt[0])].cpu().numpy()
+
+
+class DetIsolator:
+    """The DET-mode front end of ``SEE_VCN`` (no ground-truth boxes): ``get_det_instances`` + ``isolate_det_pts``
+    (SEE_VCN.py:117-181) for one frame and one camera, on the device.
+
+        iso = DetIsolator(vres=0.4, eps_scaling=5, min_eps=0.2, max_eps=1.0)          # cfg.PC_ISOLATION.*
+        inst = iso(points_cuda, masks_cuda, calib, img_shape)                          # list of (n_i, 3) CUDA clouds
+        clouds = iso.resampled                                                        # (O, 1024, 3) for VCN.forward
+    """
+
+    def __init__(self, vres, eps_scaling, min_eps, max_eps, min_cluster=10, min_lidar_pts=30, camera_model="pinhole",
+                 resample_num=1024, seed=0):
+        self.vres, self.eps_scaling, self.min_eps, self.max_eps = vres, eps_scaling, min_eps, max_eps
+        self.min_cluster, self.min_lidar_pts, self.camera_model = min_cluster, min_lidar_pts, camera_model
+        self.resample_num, self.seed = resample_num, seed
+        self.resampled = None
+
+    @torch.no_grad()
+    def __call__(self, points, masks, calib, img_shape):
+        from .datasets import shared_utils as su
+        imgfov = su.map_pointcloud_to_image(points, calib, img_shape, self.camera_model)
+        lists, counts = su.get_pts_in_mask(masks, imgfov)
+        clists, ccounts, _ = su.isolate_det_pts(points, lists, counts, self.vres, self.eps_scaling, self.min_eps, self.max_eps,
+                                                self.min_cluster)
+        h = ccounts.cpu().numpy()                                   # the one host sync: how many instances survive
+        keep = np.nonzero(h > self.min_lidar_pts)[0].astype(np.int32)   # SEE_VCN.py:222 (single camera: no merging)
+        self.kept = keep
+        obj_inst = torch.from_numpy(keep).to(points.device)
+        self.resampled = su.resample_instances(points, clists, ccounts, obj_inst, self.resample_num, self.seed)
+        return [points[clists[i, : int(h[i])].long()] for i in keep]
