@@ -382,6 +382,19 @@ int seevcn_hard_voxelize(int num_points, int num_features, const float* points,
                          int* num_voxels, void* workspace, size_t workspace_bytes,
                          seevcn_stream_t stream);
 
+/* ref: DataProcessor.mask_points_and_boxes_outside_range  detector3d/pcdet/datasets/processor/data_processor.py:78-91 with
+ * common_utils.mask_points_by_range (pcdet/utils/common_utils.py:60-63): keeps the rows with limit_range[0] <= x <=
+ * limit_range[3] and limit_range[1] <= y <= limit_range[4], in order.  points (N,C) -> out (N,C) (first *out_count rows),
+ * out_count (1) int32 DEVICE.  limit_range[6] HOST.  workspace: seevcn_mask_points_by_range_workspace_bytes(N). */
+size_t seevcn_mask_points_by_range_workspace_bytes(int num_points);
+int seevcn_mask_points_by_range(int num_points, int num_features, const float* points, const float* limit_range,
+                                float* out, int* out_count, void* workspace, size_t workspace_bytes, seevcn_stream_t stream);
+/* ref: DataProcessor.shuffle_points  data_processor.py:93-103 (points[np.random.permutation(n)]): out[j] =
+ * points[perm(j)], perm a seeded bijection of [0, n) evaluated on the fly; seevcn_shuffle_perm gives it on the host. */
+int seevcn_shuffle_points(int num_points, int num_features, unsigned seed, const float* points, float* out,
+                          seevcn_stream_t stream);
+unsigned seevcn_shuffle_perm(unsigned j, unsigned n, unsigned seed);
+
 /* The batched form the frame pipeline uses (the reference voxelizes frame by frame in DataLoader workers and pads the
  * per-frame coordinates with the batch index when collating, detector3d/pcdet/datasets/dataset.py:193-198):
  * points (F, stride, C) f32, row q of frame f takes part iff q < counts[f] (counts (F) int32 DEVICE, NULL = all rows).

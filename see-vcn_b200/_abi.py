@@ -82,6 +82,10 @@ SIGNATURES = {
     "seevcn_dbscan_largest": (I, [I, I, P, P, P, I, ctypes.c_double, ctypes.c_double, ctypes.c_double, ctypes.c_double,
                                   ctypes.c_double, I, I, P, P, P, P, c_size_t, P]),
     "seevcn_resample_lists": (I, [I, I, I, ctypes.c_uint, P, P, P, P, P, P]),
+    "seevcn_mask_points_by_range_workspace_bytes": (c_size_t, [I]),
+    "seevcn_mask_points_by_range": (I, [I, I, P, POINTER(ctypes.c_float), P, P, P, c_size_t, P]),
+    "seevcn_shuffle_points": (I, [I, I, ctypes.c_uint, P, P, P]),
+    "seevcn_shuffle_perm": (ctypes.c_uint, [ctypes.c_uint] * 3),
     "seevcn_chamfer": (I, [I, I, I, P, P, P, P, P]),
     "seevcn_copy_to_pinned": (I, [P, P, c_size_t, P]),
     "seevcn_copy_from_pinned": (I, [P, P, c_size_t, P]),

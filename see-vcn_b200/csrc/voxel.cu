@@ -1019,6 +1019,85 @@ int hardvox_run(const char* what, int frames, int stride, int num_features, cons
 }
 }  // namespace
 
+// ---- the two point-level steps in front of the voxel generator (data_processor.py:78-103) ----
+namespace {
+// ref: common_utils.mask_points_by_range (pcdet/utils/common_utils.py:60-63): x, y inclusive
+__global__ void __launch_bounds__(256)
+range_flag_kernel(int n, int c, const float* __restrict__ points, float x0, float y0, float x1, float y1, unsigned* __restrict__ flag) {
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= n) return;
+    const float x = points[(size_t)p * c], y = points[(size_t)p * c + 1];
+    flag[p] = (x >= x0 && x <= x1 && y >= y0 && y <= y1) ? 1u : 0u;
+}
+__global__ void __launch_bounds__(256)
+range_scatter_kernel(int n, int c, const float* __restrict__ points, const unsigned* __restrict__ flag_in,
+                     const unsigned* __restrict__ pos, float* __restrict__ out) {
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= n || !flag_in[p]) return;
+    for (int f = 0; f < c; ++f) out[(size_t)pos[p] * c + f] = points[(size_t)p * c + f];
+}
+// ref: DataProcessor.shuffle_points (data_processor.py:93-103): points[np.random.permutation(n)], here a keyed bijection
+__global__ void __launch_bounds__(256)
+shuffle_kernel(int n, int c, unsigned key, const float* __restrict__ points, float* __restrict__ out) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n) return;
+    const unsigned src = feistel_perm((unsigned)j, (unsigned)n, key);
+    for (int f = 0; f < c; ++f) out[(size_t)j * c + f] = points[(size_t)src * c + f];
+}
+}  // namespace
+
+extern "C" size_t seevcn_mask_points_by_range_workspace_bytes(int num_points) {
+    const size_t np = (size_t)(num_points > 0 ? num_points : 1);
+    return align_up(np * 4, 256) * 2 + align_up(8 * div_up(np, (size_t)seevcn_scan::kScanTile) + 64, 256);
+}
+
+extern "C" int seevcn_mask_points_by_range(int num_points, int num_features, const float* points, const float* limit_range,
+                                           float* out, int* out_count, void* workspace, size_t workspace_bytes,
+                                           seevcn_stream_t stream) {
+    SEEVCN_REQUIRE(num_points >= 0 && num_features >= 2, "mask_points_by_range: bad sizes");
+    SEEVCN_REQUIRE(limit_range && out_count, "mask_points_by_range: null pointer");
+    cudaStream_t st = as_stream(stream);
+    SEEVCN_CUDA_CHECK(cudaMemsetAsync(out_count, 0, sizeof(int), st));
+    if (num_points == 0) return SEEVCN_OK;
+    SEEVCN_REQUIRE(points && out && workspace, "mask_points_by_range: null pointer");
+    if (workspace_bytes < seevcn_mask_points_by_range_workspace_bytes(num_points)) {
+        seevcn_set_error("mask_points_by_range: workspace too small");
+        return SEEVCN_E_WORKSPACE;
+    }
+    char* ws = static_cast<char*>(workspace);
+    const size_t np = (size_t)num_points;
+    unsigned* flag = reinterpret_cast<unsigned*>(ws);
+    unsigned* pos = reinterpret_cast<unsigned*>(ws + align_up(np * 4, 256));
+    char* scan = ws + 2 * align_up(np * 4, 256);
+    const int tiles = (int)div_up(np, (size_t)seevcn_scan::kScanTile);
+    SEEVCN_CUDA_CHECK(cudaMemsetAsync(scan, 0, 8 * (size_t)tiles + 64, st));
+    const int gp = div_up(num_points, 256);
+    range_flag_kernel<<<gp, 256, 0, st>>>(num_points, num_features, points, limit_range[0], limit_range[1], limit_range[3],
+                                         limit_range[4], flag);
+    SEEVCN_LAUNCH_CHECK();
+    seevcn_scan::exclusive_scan_u32_kernel<<<tiles, seevcn_scan::kScanThreads, 0, st>>>(
+        num_points, flag, pos, reinterpret_cast<unsigned long long*>(scan), reinterpret_cast<int*>(scan + 8 * (size_t)tiles),
+        reinterpret_cast<unsigned*>(out_count));
+    SEEVCN_LAUNCH_CHECK();
+    range_scatter_kernel<<<gp, 256, 0, st>>>(num_points, num_features, points, flag, pos, out);
+    SEEVCN_LAUNCH_CHECK();
+    return SEEVCN_OK;
+}
+
+extern "C" int seevcn_shuffle_points(int num_points, int num_features, unsigned seed, const float* points, float* out,
+                                     seevcn_stream_t stream) {
+    SEEVCN_REQUIRE(num_points >= 0 && num_features >= 1, "shuffle_points: bad sizes");
+    if (num_points == 0) return SEEVCN_OK;
+    SEEVCN_REQUIRE(points && out && points != out, "shuffle_points: null or aliased pointer");
+    shuffle_kernel<<<div_up(num_points, 256), 256, 0, as_stream(stream)>>>(num_points, num_features, mix32(seed ^ 0x5bd1e995u), points, out);
+    SEEVCN_LAUNCH_CHECK();
+    return SEEVCN_OK;
+}
+
+extern "C" unsigned seevcn_shuffle_perm(unsigned j, unsigned n, unsigned seed) {
+    return feistel_perm(j, n, mix32(seed ^ 0x5bd1e995u));
+}
+
 extern "C" size_t seevcn_hard_voxelize_frames_workspace_bytes(int num_frames, int stride, int max_points, int max_voxels) {
     const long long n = (long long)num_frames * stride;
     if (n >= (1ll << 31) || (long long)num_frames * max_voxels >= (1ll << 31)) return 0;

@@ -470,6 +470,34 @@ def test_vcn_forward_dense_decoder_c4_shape(cuda):
     np.testing.assert_array_equal(surf.cpu().numpy(), wsurf)
 
 
+def test_data_processor_range_mask_shuffle_voxels(cuda):
+    """pcdet DataProcessor on the device (data_processor.py:78-143): x/y range mask (inclusive), seeded shuffle, hard voxels."""
+    from seevcn_b200.pcdet.datasets.processor.data_processor import DataProcessor, mask_points_by_range
+    from seevcn_b200 import _abi
+    pts, _ = synth.make_frame(1003)
+    pts = np.concatenate([pts, np.array([[75.2, -75.2, 0.0], [75.2000046, 0.0, 0.0], [-75.2, 75.2, 1.0], [80.0, 0.0, 0.0]], np.float32)])
+    cfgs = [{"NAME": "mask_points_and_boxes_outside_range", "REMOVE_OUTSIDE_BOXES": True},
+            {"NAME": "shuffle_points", "SHUFFLE_ENABLED": {"train": True, "test": False}},
+            {"NAME": "transform_points_to_voxels", "VOXEL_SIZE": WAYMO[1], "MAX_POINTS_PER_VOXEL": 5,
+             "MAX_NUMBER_OF_VOXELS": {"train": 80000, "test": 90000}}]
+    mask = mask_points_by_range(pts, WAYMO[0])
+    assert 0 < (~mask).sum() < len(pts) // 4 and mask[-4] and not mask[-3] and mask[-2]
+    for training in (False, True):
+        dp = DataProcessor(cfgs, WAYMO[0], training=training, num_point_features=3, seed=9)
+        assert dp.grid_size.tolist() == WAYMO[2]
+        out = dp.forward({"points": dev(pts, cuda), "use_lead_xyz": True})
+        want = pts[mask]
+        if training:
+            perm = np.array([_abi.lib().seevcn_shuffle_perm(j, len(want), 9) for j in range(len(want))])
+            assert sorted(perm.tolist()) == list(range(len(want)))
+            want = want[perm]
+        np.testing.assert_array_equal(out["points"].cpu().numpy(), want)
+        wv, wc, wn = oracle.hard_voxelize(want, WAYMO[0], WAYMO[1], WAYMO[2], 5, 80000 if training else 90000)
+        np.testing.assert_array_equal(out["voxel_coords"].cpu().numpy(), wc)
+        np.testing.assert_array_equal(out["voxel_num_points"].cpu().numpy(), wn)
+        np.testing.assert_array_equal(out["voxels"].cpu().numpy(), wv)
+
+
 def test_hard_voxelize_frames_vs_oracle_per_frame(cuda):
     """The batched hard voxelizer (F frames, padded outputs, device-side row counts) against the oracle frame by frame;
     MeanVFE with the int32 counts on the padded slots."""

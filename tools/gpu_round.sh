@@ -11,4 +11,4 @@ timeout 500 python bench.py > gpurun_out/${tag}_bench.json 2> gpurun_out/${tag}_
 timeout 200 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/${tag}_bench_ref.json 2>> gpurun_out/${tag}_bench.err; echo "ref rc=$?"
 timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 2500 --csv --log-file gpurun_out/${tag}_launches.csv \
     python tools/prof_step.py --steps 2 > gpurun_out/${tag}_launches.log 2>&1; echo "launches rc=$?"
-timeout 400 bash tools/ncu_capture.sh ${tag}_full "vcn_chain_kernel|points_in_boxes_kernel|dynvox_insert|dynvox_finalize|knn_scan_kernel|knn_prepare_kernel|largest_cluster_kernel|splice_mask_kernel|vcn_linear_tc" 30 20
+timeout 400 bash tools/ncu_capture.sh ${tag}_full "vcn_chain_kernel|points_in_boxes_kernel|dynvox_|knn_scan_kernel|knn_prepare_kernel|largest_cluster_kernel|splice_mask_kernel|vcn_linear_tc|crop_" 60 40

@@ -30,6 +30,7 @@ def main():
     torch.cuda.synchronize()           # counts are on the host: complete_from never blocks below
     outs = []
     for h in hs:
+        torch.cuda.synchronize()       # empty launch queue: what is timed is the issue cost, never a full queue
         t0 = time.perf_counter()
         outs.append(pipe.run_from(h, 0, defer=True))
         t_b += time.perf_counter() - t0
@@ -43,9 +44,12 @@ def main():
     pr = cProfile.Profile()
     hs = [pipe.crop_async(pts_d, boxes_d) for _ in range(n)]
     torch.cuda.synchronize()
-    pr.enable()
-    outs = [pipe.run_from(h, 0, defer=True) for h in hs]
-    pr.disable()
+    outs = []
+    for h in hs:
+        torch.cuda.synchronize()
+        pr.enable()
+        outs.append(pipe.run_from(h, 0, defer=True))
+        pr.disable()
     torch.cuda.synchronize()
     pstats.Stats(pr).sort_stats("cumulative").print_stats(28)
 
