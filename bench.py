@@ -362,7 +362,7 @@ def run_frames(args):
     hard = args.config == "C5"
     pipe = CompletionPipeline("VCN_VC", seeded_state_dict(), dev, sel_k=SEL_K, precision=args.precision, cluster_eps=CLUSTER_EPS,
                               splice_thresh=SPLICE_THRESH, min_lidar_pts=MIN_LIDAR_PTS,
-                              hard_voxels=(HARD_MAX_PTS, HARD_MAX_VOX) if hard else None)
+                              hard_voxels=(HARD_MAX_PTS, HARD_MAX_VOX) if hard else None, streams=args.streams)
     F, nb = frames_per_step(args, cfg, world)             # frames per pipeline batch, batches per step
     frames_rank = F * nb
     pts_h, boxes_h = make_inputs(frames_rank, 1000 + rank * frames_rank, **cfg["gen"])   # rank r owns frames [r*n, (r+1)*n)
@@ -493,7 +493,7 @@ def run_frames(args):
                        "objects_per_step": int(round(n_obj_res / steps)), "sel_k": SEL_K,
                        "cluster_eps": CLUSTER_EPS, "splice_thresh": SPLICE_THRESH,
                        "l2": "flushed (256 MB write) before every pipeline batch, inside the timed region",
-                       "parallelism": f"frame-sharded x{world}",
+                       "parallelism": f"frame-sharded x{world}", "compute_streams": args.streams,
                        "gather": (gather.describe() if gather is not None else None)},
             "objects_per_sec": obj_s, "voxelized_mpts_per_sec": mpts_s, "voxels_per_step_rank0": int(vox_step_rank0),
             "voxelized_points_per_step_rank0": int(pts_step_rank0),
@@ -632,6 +632,7 @@ def main():
     ap.add_argument("--precision", default=os.environ.get("SEEVCN_PRECISION", "bf16"), choices=["bf16", "fp32"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-gather", action="store_true", help="N > 1: skip the end-of-path collect (attribution runs)")
+    ap.add_argument("--streams", type=int, default=2, help="CUDA streams consecutive pipeline batches alternate on")
     ap.add_argument("--gather", default="auto", choices=["auto", "peer", "nccl"], help="N > 1: how the results are collected")
     args = ap.parse_args()
     if args.steps is None:

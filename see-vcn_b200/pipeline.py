@@ -32,7 +32,7 @@ class _Crop:
 class CompletionPipeline:
     def __init__(self, model_name="VCN_VC", state_dict=None, device=None, sel_k=10, min_lidar_pts=30, resample_num=1024,
                  voxel_cfg=WAYMO_VOXEL_CFG, precision="bf16", host_rng=False, cluster_eps=None, splice_thresh=None,
-                 hard_voxels=None):
+                 hard_voxels=None, streams=1):
         self.device = device if device is not None else torch.device("cuda", torch.cuda.current_device())
         self.model = MODELS.build({"NAME": model_name}, precision=precision)
         self.state_dict = state_dict
@@ -52,6 +52,11 @@ class CompletionPipeline:
         # voxels + MeanVFE (data_processor.py:115-143, mean_vfe.py:14-31) instead of the dynamic scatter-mean
         self.hard_voxels = hard_voxels
         self._hard_gen = None
+        # run_stream / HostStream issue consecutive batches on `streams` CUDA streams in turn: the latency-bound kernels of
+        # one batch (per-object FC layers, cluster filter, scans) then share the SMs with the other batch's work instead of
+        # leaving them idle.  Every batch keeps its own stream from the crop to the voxels; nothing is shared but the weights.
+        self.streams = max(1, int(streams))
+        self._side_streams = None
 
     def _to_host_async(self, t):
         """Small device tensor (4-byte elements) -> pinned host copy, written by a copy kernel on the current stream
@@ -211,6 +216,11 @@ class CompletionPipeline:
             out["_num_done"].synchronize()
             m = min(int(out["_h_num"][0]), coords.shape[0])
             out.update(voxel_coords=coords[:m], voxel_features=feats[:m], voxel_num_points=nums[:m])
+        elif self.hard_voxels is not None and "_done" in out and not out.get("_finalized"):
+            # padded per-frame voxels: no count to wait for, but callers (HostStream) recycle the batch's input slot once
+            # it is finalized, so make sure the batch has really finished
+            out["_done"].synchronize()
+            out["_finalized"] = True
         return out
 
     @torch.no_grad()
@@ -218,24 +228,68 @@ class CompletionPipeline:
         """complete() + dynamic voxelization of [frame points ++ completed surfaces] -> detector input."""
         return self.run_from(self.crop_async(points, boxes), seed)
 
+    def batch_stream(self, i):
+        """The CUDA stream batch i runs on (streams > 1: side streams in turn; else the caller's current stream)."""
+        if self.streams == 1:
+            return torch.cuda.current_stream(self.device)
+        if self._side_streams is None:
+            self._side_streams = [torch.cuda.Stream(self.device) for _ in range(self.streams)]
+        return self._side_streams[i % self.streams]
+
     @torch.no_grad()
     def run_stream(self, batches, seed=0):
         """Streams batches of frames: yields run()'s dict for every (points (F,P,3), boxes (F,T,7)) CUDA pair, in order.
         Batch i+1's crop is queued ahead of batch i's stage B and M is collected one batch late, so the host never
-        waits on the kernels it has just launched and the stream never drains between batches."""
+        waits on the kernels it has just launched and the stream never drains between batches.  With ``streams`` > 1
+        consecutive batches run on different CUDA streams (ordered after the caller's stream at entry; the caller's
+        stream is ordered after all of them before the generator ends)."""
         it = iter(batches)
+        main = torch.cuda.current_stream(self.device)
+        multi = self.streams > 1
+        entry = None
+        if multi:
+            entry = torch.cuda.Event()
+            entry.record(main)
+
+        def crop(i, batch):
+            if not multi:
+                return self.crop_async(*batch)
+            s = self.batch_stream(i)
+            s.wait_event(entry)
+            # the producer of the batch (e.g. an L2 flush or an upload the caller queued on its stream) comes first
+            ev = torch.cuda.Event(); ev.record(main); s.wait_event(ev)
+            with torch.cuda.stream(s):
+                return self.crop_async(*batch)
+
+        def stage_b(i, h):
+            if not multi:
+                return self.run_from(h, seed, defer=True)
+            with torch.cuda.stream(self.batch_stream(i)):
+                return self.run_from(h, seed, defer=True)
+
+        def hand_over(out):
+            """The batch ran on a side stream; the consumer works on the caller's stream."""
+            out = self.finalize(out)
+            if multi:
+                main.wait_event(out["_done"])
+                for v in out.values():
+                    if torch.is_tensor(v) and v.is_cuda:
+                        v.record_stream(main)
+            return out
+
         cur = next(it, None)
         if cur is None:
             return
-        h, prev = self.crop_async(*cur), None
+        i = 0
+        h, prev = crop(0, cur), None
         while h is not None:
             nxt = next(it, None)
-            h_next = self.crop_async(*nxt) if nxt is not None else None
-            out = self.run_from(h, seed, defer=True)
+            h_next = crop(i + 1, nxt) if nxt is not None else None
+            out = stage_b(i, h)
             if prev is not None:
-                yield self.finalize(prev)
-            prev, h = out, h_next
-        yield self.finalize(prev)
+                yield hand_over(prev)
+            prev, h, i = out, h_next, i + 1
+        yield hand_over(prev)
 
     @staticmethod
     def voxel_points(out):
@@ -339,9 +393,22 @@ class HostStream:
                     self._upload(state["up"] % D, *nxt)
                     state["up"] += 1
 
+        multi = self.pipe.streams > 1
+
         def crop(i):
-            compute.wait_event(self.ev_in[i % D])
-            return self.pipe.crop_async(self.d_pts[i % D], self.d_boxes[i % D])
+            cs = self.pipe.batch_stream(i) if multi else compute     # batch i's own compute stream
+            cs.wait_event(self.ev_in[i % D])
+            if not multi:
+                return self.pipe.crop_async(self.d_pts[i % D], self.d_boxes[i % D])
+            ev = torch.cuda.Event(); ev.record(compute); cs.wait_event(ev)   # whatever the caller queued for this batch (L2 flush)
+            with torch.cuda.stream(cs):
+                return self.pipe.crop_async(self.d_pts[i % D], self.d_boxes[i % D])
+
+        def stage_b(i, h):
+            if not multi:
+                return self.pipe.run_from(h, seed, defer=True)
+            with torch.cuda.stream(self.pipe.batch_stream(i)):
+                return self.pipe.run_from(h, seed, defer=True)
 
         upload_next(); upload_next(); upload_next()
         if state["up"] == 0:
@@ -356,7 +423,7 @@ class HostStream:
         while h is not None:
             upload_next()                                            # batch i+3: overlaps the kernels below
             h_next = crop(i + 1) if i + 1 < state["up"] else None    # ahead of batch i's stage B
-            out = self.pipe.run_from(h, seed, defer=True)
+            out = stage_b(i, h)
             if fin is not None:
                 pending.append((fin[0] % D, self._download(fin[0] % D, fin[1])))   # overlaps this batch's kernels
                 fin = None

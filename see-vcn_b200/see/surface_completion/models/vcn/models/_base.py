@@ -128,8 +128,7 @@ class VCNBase(nn.Module):
             handle = self._pack()
             L = _abi.lib()
             ws_bytes = L.seevcn_vcn_workspace_bytes(handle, B, N)
-            if self._ws is None or self._ws.numel() < ws_bytes or self._ws.device != dev:
-                self._ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+            ws = _abi.workspace(dev, ws_bytes, "vcn")     # per (device, stream): two batches may be in flight on two streams
             coarse = torch.empty((B, self.number_coarse, 3), dtype=torch.float32, device=dev)
             reg_rot = torch.empty((B, 3, 3), dtype=torch.float32, device=dev) if self.viewer_centred else None
             reg_centre = torch.empty((B, 3), dtype=torch.float32, device=dev) if self.viewer_centred else None
@@ -138,6 +137,6 @@ class VCNBase(nn.Module):
                 gt = gt_boxes[:, :7].contiguous().float()
                 _abi.require_cuda(gt)
             _abi.check(L.seevcn_vcn_forward(handle, B, N, _abi.ptr(pts), _abi.ptr(gt), _abi.ptr(coarse),
-                                            _abi.ptr(reg_rot), _abi.ptr(reg_centre), _abi.ptr(self._ws),
-                                            self._ws.numel(), PRECISIONS[self.precision], _abi.stream()))
+                                            _abi.ptr(reg_rot), _abi.ptr(reg_centre), _abi.ptr(ws),
+                                            ws.numel(), PRECISIONS[self.precision], _abi.stream()))
         return coarse, reg_rot, reg_centre

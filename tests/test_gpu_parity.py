@@ -650,6 +650,12 @@ def test_pipeline_stream_equals_single_runs(cuda):
     dbat = [(dev(p, cuda), dev(b, cuda)) for p, b in batches]
     singles = [pipe.run(p, b, seed=0) for p, b in dbat]
     streamed = list(pipe.run_stream(iter(dbat), seed=0))
+    pipe2 = CompletionPipeline("VCN_VC", oracle.make_state_dict("VCN_VC", seed=0), cuda, sel_k=10, cluster_eps=0.3, streams=2)
+    two = list(pipe2.run_stream(iter(dbat), seed=0))             # consecutive batches on two CUDA streams
+    torch.cuda.synchronize()
+    for a, b in zip(singles, two):
+        for key in ("clustered", "voxel_coords", "voxel_num_points", "voxel_features"):
+            np.testing.assert_array_equal(a[key].cpu().numpy(), b[key].cpu().numpy())
     hs = HostStream(pipe, 2, batches[0][0].shape[1], batches[0][1].shape[1])
     pinned = [(torch.from_numpy(p).pin_memory(), torch.from_numpy(b).pin_memory()) for p, b in batches]
     hosted = [{k: v.clone() for k, v in res.items()} for res in hs.run(iter(pinned), seed=0)]
