@@ -367,18 +367,31 @@ def run_frames(args):
     frames_rank = F * nb
     pts_h, boxes_h = make_inputs(frames_rank, 1000 + rank * frames_rank, **cfg["gen"])   # rank r owns frames [r*n, (r+1)*n)
     P_pts, T_box = pts_h.shape[1], boxes_h.shape[1]
-    pts_pin = [torch.from_numpy(pts_h[b * F:(b + 1) * F]).pin_memory() for b in range(nb)]
-    boxes_pin = [torch.from_numpy(boxes_h[b * F:(b + 1) * F]).pin_memory() for b in range(nb)]
+    # L2 policy (timing rule: flush L2 between timed iterations, or use inputs larger than L2).
+    #   rotate (default): the step's frames exist in V variants (the same frames under V sensor yaw offsets, a rigid
+    #     rotation) resident in HBM, V x (input bytes per step) > 2 x the 126 MB L2; consecutive steps take consecutive
+    #     variants, so no step finds its inputs in L2.
+    #   flush: one set of frames, a 256 MB write before every pipeline batch inside the timed region.
+    from seevcn_b200 import synth
+    step_bytes = pts_h.nbytes + boxes_h.nbytes
+    V = 1 if args.l2 == "flush" else int(np.ceil(2 * 126e6 / step_bytes)) + 1
+    variants = [(pts_h, boxes_h)] + [synth.rotate_stream(pts_h, boxes_h, 2 * np.pi * v / V) for v in range(1, V)]
+    pts_pin = [torch.from_numpy(np.ascontiguousarray(p[b * F:(b + 1) * F])).pin_memory() for p, _ in variants for b in range(nb)]
+    boxes_pin = [torch.from_numpy(np.ascontiguousarray(x[b * F:(b + 1) * F])).pin_memory() for _, x in variants for b in range(nb)]
     pts_d = [p.to(dev) for p in pts_pin]
     boxes_d = [b.to(dev) for b in boxes_pin]
-    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)   # > 126 MB L2
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev) if args.l2 == "flush" else None   # > 126 MB L2
     hs = HostStream(pipe, F, P_pts, T_box)
+    step_no = [0]
 
     def batches(n_steps, srcs_p, srcs_b):
         for _ in range(n_steps):
+            v = step_no[0] % V
+            step_no[0] += 1
             for b in range(nb):
-                flush.fill_(1)                               # L2 flush before every batch (on the compute stream, timed)
-                yield srcs_p[b], srcs_b[b]
+                if flush is not None:
+                    flush.fill_(1)                           # L2 flush before every batch (on the compute stream, timed)
+                yield srcs_p[v * nb + b], srcs_b[v * nb + b]
 
     # "collect for the detector" (N > 1): completed clouds + voxel tensors of every rank on every rank
     gather = None
@@ -416,11 +429,13 @@ def run_frames(args):
         prof = _abi.prof_report()
         launches = _abi.lib().seevcn_launch_count() - l0
         # rows actually voxelized (spliced-out points, cyclic repeats and out-of-range points are not): the voxel counts sum
-        # to it.  Counted on one untimed pass over the rank's batches (every step runs the same frames).
+        # to it.  Counted on one untimed pass over every variant of the rank's frames, averaged per step.
         n_pts = n_vox = 0
-        for out in pipe.run_stream(batches(1, pts_d, boxes_d)):
+        step_no[0] = 0
+        for out in pipe.run_stream(batches(V, pts_d, boxes_d)):
             n_pts += int(out["voxel_num_points"].sum().item()) if not hard else pipe.hard_points_in(out, pipe.voxel_cfg)
             n_vox += int(out["voxel_coords"].shape[0]) if not hard else int(out["hard_num_voxels"].sum().item())
+        n_pts, n_vox = n_pts / V, n_vox / V
         D.sync_all()
         my_ms = e0.elapsed_time(e1)
         ms, objs = D.max_sum(my_ms, n_obj)
@@ -492,7 +507,9 @@ def run_frames(args):
             "config": {"workload": cfg["workload"], "frames_per_step_per_gpu": fr, "frames_per_pipeline_batch": F,
                        "objects_per_step": int(round(n_obj_res / steps)), "sel_k": SEL_K,
                        "cluster_eps": CLUSTER_EPS, "splice_thresh": SPLICE_THRESH,
-                       "l2": "flushed (256 MB write) before every pipeline batch, inside the timed region",
+                       "l2": ("flushed (256 MB write) before every pipeline batch, inside the timed region" if args.l2 == "flush" else
+                              f"inputs larger than L2: {V} variants of the step's frames (rigid yaw rotations) resident in HBM = "
+                              f"{V * step_bytes / 1e6:.0f} MB, consecutive steps take consecutive variants; no flush"),
                        "parallelism": f"frame-sharded x{world}", "compute_streams": args.streams,
                        "gather": (gather.describe() if gather is not None else None)},
             "objects_per_sec": obj_s, "voxelized_mpts_per_sec": mpts_s, "voxels_per_step_rank0": int(vox_step_rank0),
@@ -633,6 +650,7 @@ def main():
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-gather", action="store_true", help="N > 1: skip the end-of-path collect (attribution runs)")
     ap.add_argument("--streams", type=int, default=2, help="CUDA streams consecutive pipeline batches alternate on")
+    ap.add_argument("--l2", default="rotate", choices=["rotate", "flush"], help="how a step is kept from finding its inputs in L2")
     ap.add_argument("--gather", default="auto", choices=["auto", "peer", "nccl"], help="N > 1: how the results are collected")
     args = ap.parse_args()
     if args.steps is None:

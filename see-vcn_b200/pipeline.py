@@ -281,15 +281,17 @@ class CompletionPipeline:
         if cur is None:
             return
         i = 0
-        h, prev = crop(0, cur), None
-        while h is not None:
+        h = crop(0, cur)
+        inflight = []                 # issued, not finalized: as many batches as there are streams, so that the host is
+        while h is not None:          # always a full batch ahead of every stream
             nxt = next(it, None)
             h_next = crop(i + 1, nxt) if nxt is not None else None
-            out = stage_b(i, h)
-            if prev is not None:
-                yield hand_over(prev)
-            prev, h, i = out, h_next, i + 1
-        yield hand_over(prev)
+            inflight.append(stage_b(i, h))
+            if len(inflight) > self.streams:
+                yield hand_over(inflight.pop(0))
+            h, i = h_next, i + 1
+        for out in inflight:
+            yield hand_over(out)
 
     @staticmethod
     def voxel_points(out):

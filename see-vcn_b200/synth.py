@@ -61,6 +61,18 @@ def make_stream(n_frames, first_seed=1000, **kw):
     return np.stack([f[0] for f in frames]), np.stack([f[1] for f in frames])
 
 
+def rotate_stream(points, boxes, angle):
+    """The same frames seen by a sensor mounted with a yaw offset: points (F,P,3) and boxes (F,T,7) rotated about z by
+    ``angle`` (rigid, so every point keeps its box).  A cheap way to get many distinct frames with identical statistics."""
+    c, s = np.cos(angle), np.sin(angle)
+    p = points.astype(np.float64)
+    out_p = np.stack([p[..., 0] * c - p[..., 1] * s, p[..., 0] * s + p[..., 1] * c, p[..., 2]], axis=-1).astype(np.float32)
+    b = boxes.astype(np.float64).copy()
+    b[..., 0], b[..., 1] = boxes[..., 0] * c - boxes[..., 1] * s, boxes[..., 0] * s + boxes[..., 1] * c
+    b[..., 6] = (boxes[..., 6] + angle + np.pi) % (2 * np.pi) - np.pi
+    return out_p, b.astype(np.float32)
+
+
 def make_object_clouds(seed, n_obj, n_in=1024, n_dense=0):
     """Per-object clouds for the MLP / FPS / kNN stages: ``n_in`` points on the two sensor-facing
     faces of a car box (+1 cm noise) and optionally an ``n_dense``-point full surface (C4)."""
