@@ -282,6 +282,43 @@ def seeded_state_dict(num_coarse=1024):
     return m.state_dict()
 
 
+def bind_to_gpu_numa_node(local_rank, world):
+    """N > 1: run this rank's host threads (and, by first touch, its pinned buffers) on the CPUs of the NUMA node its GPU
+    hangs off, split between the ranks that share the node.  The e2e leg moves ~36 MB per step and rank over PCIe; with
+    every rank on one node they all go through one memory controller and one root complex.  Returns a description."""
+    if world <= 1:
+        return None
+    try:
+        import torch
+        pr = torch.cuda.get_device_properties(local_rank)
+        bdf = "%04x:%02x:%02x.0" % (getattr(pr, "pci_domain_id", 0), pr.pci_bus_id, pr.pci_device_id)
+        base = f"/sys/bus/pci/devices/{bdf}"
+        node = int(open(base + "/numa_node").read().strip())
+        cpus = []
+        for part in open(base + "/local_cpulist").read().strip().split(","):
+            a, _, b = part.partition("-")
+            cpus += list(range(int(a), int(b or a) + 1))
+        allowed = sorted(set(cpus) & os.sched_getaffinity(0))
+        if not allowed:
+            return {"numa_node": node, "bound": False, "why": "no local cpu in the affinity mask"}
+        # ranks on the same node share its CPUs evenly (local ranks are dealt to nodes in order)
+        peers = []
+        for r in range(world):
+            q = torch.cuda.get_device_properties(r)
+            b2 = "%04x:%02x:%02x.0" % (getattr(q, "pci_domain_id", 0), q.pci_bus_id, q.pci_device_id)
+            try:
+                if int(open(f"/sys/bus/pci/devices/{b2}/numa_node").read().strip()) == node:
+                    peers.append(r)
+            except OSError:
+                pass
+        k, n = (peers.index(local_rank), len(peers)) if local_rank in peers else (0, 1)
+        share = allowed[k * len(allowed) // n:(k + 1) * len(allowed) // n] or allowed
+        os.sched_setaffinity(0, share)
+        return {"numa_node": node, "bound": True, "cpus": len(share), "ranks_on_node": n}
+    except Exception as e:   # noqa: BLE001
+        return {"bound": False, "why": repr(e)[:120]}
+
+
 class Dist:
     """Rank bookkeeping + the timing helpers of the contract (barrier + synchronize on both sides, max over ranks)."""
 
@@ -292,6 +329,7 @@ class Dist:
         self.world = int(os.environ.get("WORLD_SIZE", "1"))
         self.rank = int(os.environ.get("RANK", "0"))
         self.local = int(os.environ.get("LOCAL_RANK", "0"))
+        self.numa = bind_to_gpu_numa_node(self.local, self.world) if os.environ.get("SEEVCN_NUMA_BIND", "1") != "0" else None
         torch.cuda.set_device(self.local)
         self.dev = torch.device("cuda", self.local)
         if self.world > 1:
@@ -510,7 +548,7 @@ def run_frames(args):
                        "l2": ("flushed (256 MB write) before every pipeline batch, inside the timed region" if args.l2 == "flush" else
                               f"inputs larger than L2: {V} variants of the step's frames (rigid yaw rotations) resident in HBM = "
                               f"{V * step_bytes / 1e6:.0f} MB, consecutive steps take consecutive variants; no flush"),
-                       "parallelism": f"frame-sharded x{world}", "compute_streams": args.streams,
+                       "parallelism": f"frame-sharded x{world}", "compute_streams": args.streams, "host_binding": D.numa,
                        "gather": (gather.describe() if gather is not None else None)},
             "objects_per_sec": obj_s, "voxelized_mpts_per_sec": mpts_s, "voxels_per_step_rank0": int(vox_step_rank0),
             "voxelized_points_per_step_rank0": int(pts_step_rank0),
