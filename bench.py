@@ -677,6 +677,8 @@ def run_c4(args):
 
 
 def main():
+    import gc
+    gc.disable()            # no collector pauses inside the timed regions (the step loop allocates only short-lived tensors)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=None)   # C2: 200 steps = ~0.3 s per timed leg: box-level jitter averages out
