@@ -211,8 +211,7 @@ typedef struct seevcn_vcn_params {
 typedef struct seevcn_vcn_model seevcn_vcn_model;   /* opaque: packed bf16 weights on device */
 
 /* Packs the parameters into the kernels' bf16 operand layouts (allocates device memory —
- * model-load time, not the hot path).  precision: 0 = bf16 tensor-core path (tcgen05),
- * 1 = fp32 SIMT validation path. */
+ * model-load time, not the hot path). */
 int  seevcn_vcn_create(const seevcn_vcn_params* params, seevcn_vcn_model** out_model,
                        seevcn_stream_t stream);
 void seevcn_vcn_destroy(seevcn_vcn_model* model);
@@ -223,17 +222,14 @@ size_t seevcn_vcn_workspace_bytes(const seevcn_vcn_model* model, int num_obj, in
  *      VCN_CN.forward  see/surface_completion/models/vcn/models/VCN_CN.py:142-157
  * input (B,N,3) f32; gt_boxes (B,7) f32 (VCN_CN only, else NULL)
  * -> coarse (B,num_coarse,3) f32, reg_rot (B,3,3) f32, reg_centre (B,3) f32 (VC only; may be NULL).
- * precision: 0 = bf16 operands / fp32 accumulate on tcgen05, 1 = fp32 SIMT. */
+ * precision: 0 = bf16 operands / fp32 accumulate on tcgen05 with the per-point layers fused into chains whose
+ * activations stay in tensor memory (vcn_chain.cu); 1 = fp32 SIMT (validation); 2 = the bf16 tcgen05 path with one GEMM
+ * launch per layer (vcn_tc.cu; same layers and roundings as 0 up to accumulation order, kept for cross-checking). */
 int seevcn_vcn_forward(const seevcn_vcn_model* model, int num_obj, int n_pts,
                        const float* input, const float* gt_boxes,
                        float* coarse, float* reg_rot, float* reg_centre,
                        void* workspace, size_t workspace_bytes, int precision,
                        seevcn_stream_t stream);
-
-/* Selects how the bf16 path (precision 0) runs the per-point shared-MLP chains: 1 (default) = fused tcgen05
- * chains with the activations kept in tensor memory (vcn_chain.cu); 0 = one tcgen05 GEMM launch per layer
- * (vcn_tc.cu).  Both compute the same layers; returns the previous setting.  Process-wide, not thread-safe. */
-int seevcn_set_fused_chains(int on);
 
 /* One shared-MLP layer on the tcgen05 path, standalone (the building block of seevcn_vcn_forward;
  * ref: nn.Conv1d(k=1) / nn.Linear as used in VCN_VC.py:116-131):

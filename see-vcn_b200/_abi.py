@@ -56,7 +56,6 @@ SIGNATURES = {
     "seevcn_vcn_destroy": (None, [P]),
     "seevcn_vcn_workspace_bytes": (c_size_t, [P, I, I]),
     "seevcn_vcn_forward": (I, [P, I, I, P, P, P, P, P, P, c_size_t, I, P]),
-    "seevcn_set_fused_chains": (I, [I]),
     "seevcn_linear_bf16_workspace_bytes": (c_size_t, [I, I, I]),
     "seevcn_linear_bf16": (I, [I, I, I, P, P, P, P, I, I, P, P, P, c_size_t, P]),
     "seevcn_mean_vfe": (I, [I, I, I, P, P, P, P]),

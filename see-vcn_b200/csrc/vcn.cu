@@ -443,18 +443,6 @@ extern "C" size_t seevcn_vcn_workspace_bytes(const seevcn_vcn_model* model, int 
     return a > b ? a : b;
 }
 
-// SEEVCN_FUSED_CHAINS=0 selects the layer-by-layer tcgen05 kernels (vcn_tc.cu) instead of the fused chains
-static int g_fused_chains = -1;
-static bool fused_chains_enabled() {
-    if (g_fused_chains < 0) { const char* e = getenv("SEEVCN_FUSED_CHAINS"); g_fused_chains = (e && e[0] == '0') ? 0 : 1; }
-    return g_fused_chains == 1;
-}
-extern "C" int seevcn_set_fused_chains(int on) {
-    const int prev = fused_chains_enabled() ? 1 : 0;
-    g_fused_chains = on ? 1 : 0;
-    return prev;
-}
-
 #define TRY(expr) do { int _rc = (expr); if (_rc != SEEVCN_OK) return _rc; } while (0)
 
 extern "C" int seevcn_vcn_forward(const seevcn_vcn_model* M, int num_obj, int n, const float* input,
@@ -462,12 +450,12 @@ extern "C" int seevcn_vcn_forward(const seevcn_vcn_model* M, int num_obj, int n,
                                   void* workspace, size_t workspace_bytes, int precision, seevcn_stream_t stream) {
     SEEVCN_REQUIRE(M, "vcn_forward: null model");
     SEEVCN_REQUIRE(num_obj >= 0 && n >= 1, "vcn_forward: bad sizes");
-    SEEVCN_REQUIRE(precision == 0 || precision == 1, "vcn_forward: precision must be 0 (bf16 tcgen05) or 1 (fp32)");
+    SEEVCN_REQUIRE(precision >= 0 && precision <= 2, "vcn_forward: precision must be 0 (bf16 fused tcgen05 chains), 1 (fp32) or 2 (bf16, one tcgen05 GEMM per layer)");
     if (num_obj == 0) return SEEVCN_OK;
     SEEVCN_REQUIRE(input && coarse && workspace, "vcn_forward: null pointer");
     SEEVCN_REQUIRE(M->viewer_centred || gt_boxes, "vcn_forward: VCN_CN needs gt_boxes");
     SEEVCN_REQUIRE(num_obj <= 65535, "vcn_forward: num_obj > 65535 per call");
-    const VcnWs w = vcn_ws(num_obj, n, M->num_coarse, precision);
+    const VcnWs w = vcn_ws(num_obj, n, M->num_coarse, precision == 1 ? 1 : 0);
     if (workspace_bytes < w.total) {
         seevcn_set_error("vcn_forward: workspace %zu < %zu", workspace_bytes, w.total);
         return SEEVCN_E_WORKSPACE;
@@ -487,7 +475,7 @@ extern "C" int seevcn_vcn_forward(const seevcn_vcn_model* M, int num_obj, int n,
     float* fc_a = reinterpret_cast<float*>(ws + w.fc_a);
     float* fc_b = reinterpret_cast<float*>(ws + w.fc_b);
     float* coarse_cn = reinterpret_cast<float*>(ws + w.coarse_cn);
-    const bool tc = precision == 0;
+    const bool tc = precision != 1;
     float* actA = reinterpret_cast<float*>(ws + w.act_a);
     float* actB = reinterpret_cast<float*>(ws + w.act_b);
     auto* actA16 = reinterpret_cast<__nv_bfloat16*>(ws + w.act_a);
@@ -535,7 +523,7 @@ extern "C" int seevcn_vcn_forward(const seevcn_vcn_model* M, int num_obj, int n,
     void* A = tc ? static_cast<void*>(actA16) : static_cast<void*>(actA);
     void* Bf = tc ? static_cast<void*>(actB16) : static_cast<void*>(actB);
 
-    if (tc && fused_chains_enabled()) {
+    if (precision == 0) {
         // ---- fused tcgen05 chains (vcn_chain.cu): one launch per chain, activations stay in TMEM ----
         if (M->viewer_centred) {
             vcn_frame_kernel<<<num_obj, 256, 0, st>>>(n, 1, input, nullptr, frames, nullptr);

@@ -511,26 +511,13 @@ int launch_chain(const CUtensorMap& tw1, const CUtensorMap& tw2, const CUtensorM
     SEEVCN_CUDA_CHECK(cudaFuncSetAttribute(vcn_chain_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     const int grid = a.num_tiles < seevcn_num_sms() ? a.num_tiles : seevcn_num_sms();
     ChainArgs b = a;
-    static int dbg = -1;
-    if (dbg < 0) { const char* e = getenv("SEEVCN_CHAIN_DBG"); dbg = e ? atoi(e) : 0; }
-    b.dbg = dbg;
+    b.dbg = 0;              // timing experiments (see the kernel's dbg bits) are compiled in but never enabled from here
     b.prof = nullptr;
-    if (dbg & 4) SEEVCN_CUDA_CHECK(cudaMalloc(&b.prof, (size_t)grid * 8 * sizeof(long long)));
     {
         SEEVCN_PROF(MODE == CHAIN_POSE ? "vcn_chain_pose" : MODE == CHAIN_ENC1 ? "vcn_chain_enc1" : "vcn_chain_enc2", st);
         vcn_chain_kernel<MODE><<<grid, NUM_THREADS, smem, st>>>(tw1, tw2, tx, b);
     }
     SEEVCN_LAUNCH_CHECK();
-    if (dbg & 4) {   // timing experiment: issuer-0 wait breakdown, averaged over CTAs
-        std::vector<long long> h((size_t)grid * 8);
-        SEEVCN_CUDA_CHECK(cudaStreamSynchronize(st));
-        SEEVCN_CUDA_CHECK(cudaMemcpy(h.data(), b.prof, h.size() * sizeof(long long), cudaMemcpyDeviceToHost));
-        cudaFree(b.prof);
-        double s[6] = {0, 0, 0, 0, 0, 0};
-        for (int i = 0; i < grid; ++i) for (int j = 0; j < 6; ++j) s[j] += (double)h[(size_t)i * 8 + j] / grid;
-        fprintf(stderr, "chain<%d> tiles/CTA %.1f: issuer0 cycles total %.0f | wait A %.0f | acc_empty %.0f | w_full %.0f | h_full %.0f  (per tile: %.0f)\n",
-                MODE, s[5], s[0], s[1], s[2], s[3], s[4], s[0] / (s[5] > 0 ? s[5] : 1));
-    }
     return SEEVCN_OK;
 }
 

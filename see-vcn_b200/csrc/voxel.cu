@@ -783,14 +783,7 @@ struct DynWs {
 
 // Bucket width: W = 2^logw consecutive keys per bucket.  1024 keys = 25 y-columns of the Waymo grid at one x: a LiDAR frame
 // puts ~20 points into a non-empty bucket, and a bucket's occupancy bitmap is one word per lane of a warp.
-int dyn_logw(double span) {
-    int logw = 10;
-    if (const char* e = getenv("SEEVCN_VOX_LOGW")) {   // tuning knob (10..11)
-        const int v = atoi(e);
-        if (v >= 10 && v <= 11) logw = v;
-    }
-    return logw;
-}
+int dyn_logw(double) { return 10; }
 
 bool dyn_layout(long long n, int c, int batch, const int* grid, DynWs* out) {
     DynWs w{};

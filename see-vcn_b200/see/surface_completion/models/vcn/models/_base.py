@@ -7,7 +7,7 @@ import torch.nn as nn
 
 from ...... import _abi
 
-PRECISIONS = {"bf16": 0, "fp32": 1}
+PRECISIONS = {"bf16": 0, "fp32": 1, "bf16_layerwise": 2}
 
 
 def conv_stack(spec):

@@ -11,7 +11,7 @@ BASE_KEYS = {"metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_ste
 
 
 def test_committed_bench_line_has_the_contract_keys():
-    line = json.loads(open(os.path.join(ROOT, "profiles", "r01_bench_final.json")).read().strip().splitlines()[-1])
+    line = json.loads(open(os.path.join(ROOT, "profiles", "r02_bench_final.json")).read().strip().splitlines()[-1])
     assert BASE_KEYS | {"gpu_launches", "roofline", "clocks"} <= set(line)
     base = json.load(open(os.path.join(ROOT, "BASELINE.json")))
     assert line["metric"] in base["metric"] and line["unit"] == "objects/s" and line["higher_is_better"] is True

@@ -411,14 +411,10 @@ def test_vcn_fused_chains_vs_layerwise_and_oracle(cuda, name, nobj, n):
     in_dict = {"input": dev(part, cuda)}
     if name == "VCN_CN":
         in_dict["gt_boxes"] = dev(boxes[:, :7].astype(np.float32), cuda)
-    L = _abi.lib()
-    prev = L.seevcn_set_fused_chains(1)
-    try:
-        fused = model(in_dict)["coarse"].cpu().numpy()
-        L.seevcn_set_fused_chains(0)
-        layer = model(in_dict)["coarse"].cpu().numpy()
-    finally:
-        L.seevcn_set_fused_chains(prev)
+    fused = model(in_dict)["coarse"].cpu().numpy()
+    model.precision = "bf16_layerwise"                       # same weights, one tcgen05 GEMM launch per layer
+    layer = model(in_dict)["coarse"].cpu().numpy()
+    model.precision = "bf16"
     want = oracle.vcn_forward_ref(sd, part, boxes[:, :7].astype(np.float32) if name == "VCN_CN" else None, name)["coarse"].numpy()
     assert np.isfinite(fused).all()
     assert (rel_chamfer(fused, want, part) < 1e-3).all(), rel_chamfer(fused, want, part).max()
@@ -572,19 +568,6 @@ def test_dynamic_voxelize_vs_reference_module_golden(cuda):
         out = vfe({"points": dev(g[f"{tag}_points"], cuda), "batch_size": 2})
         np.testing.assert_array_equal(out["voxel_coords"].cpu().numpy(), g[f"{tag}_voxel_coords"])
         np.testing.assert_allclose(out["voxel_features"].cpu().numpy(), g[f"{tag}_voxel_features"], rtol=1e-5, atol=1e-6)
-
-
-@pytest.mark.parametrize("logw", [10, 11])
-def test_dynamic_voxelize_bucket_widths(cuda, logw, monkeypatch):
-    """Every bucket width the kernels support gives the same rows (SEEVCN_VOX_LOGW is the tuning knob)."""
-    monkeypatch.setenv("SEEVCN_VOX_LOGW", str(logw))
-    pts, _ = synth.make_stream(2, n_beams=32, n_az=1090, n_boxes=10)
-    points = np.concatenate([np.concatenate([np.full((pts.shape[1], 1), b, np.float32), pts[b]], axis=1) for b in range(2)])
-    want_c, want_f, want_n = oracle.dynamic_voxelize(points, *WAYMO)
-    c, f, n = dynamic_voxelize(dev(points, cuda), *WAYMO, batch_size=2)
-    np.testing.assert_array_equal(c.cpu().numpy(), want_c)
-    np.testing.assert_array_equal(n.cpu().numpy(), want_n)
-    np.testing.assert_allclose(f.cpu().numpy(), want_f, rtol=1e-6, atol=1e-6)
 
 
 def test_dynamic_voxelize_dense_voxels_vs_float64_mean(cuda):

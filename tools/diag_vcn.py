@@ -21,8 +21,7 @@ for seed in (3, 5, 7):
             model = MODELS.build({"NAME": name}, precision=prec); model.load_state_dict(sd); model.to(cuda).eval()
             d = {"input": torch.from_numpy(part).to(cuda)}
             if gt is not None: d["gt_boxes"] = torch.from_numpy(gt).to(cuda)
-            L.seevcn_set_fused_chains(fused)
+            model.precision = prec if (fused or prec == "fp32") else "bf16_layerwise"
             res[(prec, fused)] = model(d)["coarse"].cpu().numpy()
-        L.seevcn_set_fused_chains(1)
         print(seed, name, nobj, n, "fused", rel_chamfer(res[("bf16", 1)], want).round(6), "layer", rel_chamfer(res[("bf16", 0)], want).round(6),
               "fp32", rel_chamfer(res[("fp32", 0)], want).max(), "maxabs f-l", np.abs(res[("bf16", 1)] - res[("bf16", 0)]).max())

@@ -28,8 +28,7 @@ def main():
         if obj is not None:
             od = torch.from_numpy(obj.astype(np.float32)).to(dev)
             of = torch.from_numpy(np.sort(rng.integers(0, args.frames, O)).astype(np.int32)).to(dev)
-        for logw in (10, 12, 14, 16):
-            os.environ["SEEVCN_VOX_LOGW"] = str(logw)
+        for logw in (10,):
             for _ in range(3):
                 c, f, n, m = dynamic_voxelize_frames(d, od, of, *WAYMO_VOXEL_CFG)
             torch.cuda.synchronize()
