@@ -290,16 +290,30 @@ int seevcn_resample_lists(int num_obj, int n_points, int stride, unsigned seed, 
  *   keep (F,P) uint8: 1 = the point survives.
  *   merged (F,out_stride,3) f32 or NULL: per frame [rows of its objects in object order ++ surviving points in point
  *   order]; merged_count (F) int32 rows written per frame (out_stride >= P + the frame's object rows);
- *   completed_count (F) int32 or NULL = how many of them are object rows.  The reference stacks
- *   np.unique(all object rows) (SEE_VCN.py:244, lexicographic order, cross-object duplicates removed) — same rows up to
- *   order whenever two objects share no point.
+ *   completed_count (F) int32 or NULL = how many of them are object rows.
+ *   frame_rows (F, frame_rows_stride, 3) + frame_row_count (F) int32, or NULL: the completed rows of every frame as one
+ *   pre-merged block that replaces the per-object rows at the head of the merged cloud — pass the output of
+ *   seevcn_unique_rows_frames to get the reference's `vstack(np.unique(all object rows), pcd_without_object)`
+ *   (SEE_VCN.py:244,262: lexicographic order, cross-object duplicates removed) bit for bit.  The keep mask does not
+ *   depend on it.
  * workspace: seevcn_splice_workspace_bytes(F, P, O) bytes, 16-byte aligned. */
 size_t seevcn_splice_workspace_bytes(int num_frames, int pts_per_frame, int num_obj);
 int seevcn_splice(int num_frames, int pts_per_frame, const float* frame_pts,
                   int num_obj, int pts_per_obj, const float* obj_pts, const int* obj_count, const int* obj_frame,
                   double thresh, unsigned char* keep,
                   int out_stride, float* merged, int* merged_count, int* completed_count,
+                  const float* frame_rows, int frame_rows_stride, const int* frame_row_count,
                   void* workspace, size_t workspace_bytes, seevcn_stream_t stream);
+
+/* ref: sc_model_ret['all_instances'] = np.unique(np.vstack(sc_model_ret['clustered']), axis=0)
+ *      see/surface_completion/SEE_VCN.py:113,244.  Per frame: the first obj_count[o] rows (NULL = all) of the frame's objects
+ * (obj_frame non-decreasing), sorted lexicographically by (x, y, z) with duplicates removed.
+ * -> uniq (F, out_stride, 3) f32, ucount (F) int32; out_stride >= the rows any frame's objects hold together;
+ * pts_per_obj <= 4096.  workspace: seevcn_unique_rows_frames_workspace_bytes(F, O, S, out_stride). */
+size_t seevcn_unique_rows_frames_workspace_bytes(int num_frames, int num_obj, int pts_per_obj, int out_stride);
+int seevcn_unique_rows_frames(int num_frames, int num_obj, int pts_per_obj, const float* obj_pts, const int* obj_count,
+                              const int* obj_frame, int out_stride, float* uniq, int* ucount,
+                              void* workspace, size_t workspace_bytes, seevcn_stream_t stream);
 
 /* ------------------------------------------------------------ stage 6: voxelization -- */
 

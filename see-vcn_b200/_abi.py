@@ -68,7 +68,9 @@ SIGNATURES = {
     "seevcn_dynamic_voxelize_spliced": (I, [I, I, P, P, I, I, P, P, P, POINTER(ctypes.c_float), POINTER(ctypes.c_float),
                                             POINTER(c_int), I, I, P, P, P, P, P, c_size_t, P]),
     "seevcn_splice_workspace_bytes": (c_size_t, [I, I, I]),
-    "seevcn_splice": (I, [I, I, P, I, I, P, P, P, ctypes.c_double, P, I, P, P, P, P, c_size_t, P]),
+    "seevcn_splice": (I, [I, I, P, I, I, P, P, P, ctypes.c_double, P, I, P, P, P, P, I, P, P, c_size_t, P]),
+    "seevcn_unique_rows_frames_workspace_bytes": (c_size_t, [I, I, I, I]),
+    "seevcn_unique_rows_frames": (I, [I, I, I, P, P, P, I, P, P, P, c_size_t, P]),
     "seevcn_hard_voxelize_workspace_bytes": (c_size_t, [I, I, I]),
     "seevcn_hard_voxelize": (I, [I, I, P, POINTER(ctypes.c_float), POINTER(ctypes.c_float), POINTER(c_int),
                                  I, I, P, P, P, P, P, c_size_t, P]),

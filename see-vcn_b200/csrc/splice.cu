@@ -247,7 +247,7 @@ __device__ __forceinline__ int block_exscan(int v, int* s_warp, int* total) {
 __global__ void __launch_bounds__(kThreads)
 splice_offsets_kernel(int num_obj, int ntiles, const ObjBound* __restrict__ bounds, const int* __restrict__ tile_kept,
                       int* __restrict__ obj_off, int* __restrict__ tile_off, int* __restrict__ merged_count,
-                      int* __restrict__ completed_count) {
+                      int* __restrict__ completed_count, const int* __restrict__ frame_row_count) {
     __shared__ int s_warp[kThreads / 32 + 1];
     __shared__ int s_range[2];
     const int f = blockIdx.x;
@@ -255,13 +255,17 @@ splice_offsets_kernel(int num_obj, int ntiles, const ObjBound* __restrict__ boun
     if (threadIdx.x == 32) s_range[1] = lower_bound_frame(bounds, num_obj, f + 1);
     __syncthreads();
     int base = 0;
-    for (int o0 = s_range[0]; o0 < s_range[1]; o0 += kThreads) {
-        const int o = o0 + threadIdx.x;
-        const int c = o < s_range[1] ? bounds[o].count : 0;
-        int tot;
-        const int ex = block_exscan(c, s_warp, &tot);
-        if (o < s_range[1]) obj_off[o] = base + ex;
-        base += tot;
+    if (frame_row_count) {               // the frame's completed rows come as one pre-merged block (np.unique order)
+        base = frame_row_count[f];
+    } else {
+        for (int o0 = s_range[0]; o0 < s_range[1]; o0 += kThreads) {
+            const int o = o0 + threadIdx.x;
+            const int c = o < s_range[1] ? bounds[o].count : 0;
+            int tot;
+            const int ex = block_exscan(c, s_warp, &tot);
+            if (o < s_range[1]) obj_off[o] = base + ex;
+            base += tot;
+        }
     }
     if (threadIdx.x == 0 && completed_count) completed_count[f] = base;
     for (int t0 = 0; t0 < ntiles; t0 += kThreads) {
@@ -320,6 +324,16 @@ splice_scatter_objects_kernel(int pts_per_obj, const float* __restrict__ obj_pts
     merged[((size_t)b.frame * out_stride + obj_off[o]) * 3 + j] = obj_pts[(size_t)o * pts_per_obj * 3 + j];
 }
 
+// grid (ceil(rows_stride*3 / 256), F): the frame's pre-merged completed rows go to the head of its merged cloud
+__global__ void __launch_bounds__(kThreads)
+splice_copy_rows_kernel(int rows_stride, const float* __restrict__ frame_rows, const int* __restrict__ frame_row_count,
+                        int out_stride, float* __restrict__ merged) {
+    const int f = blockIdx.y;
+    const int j = blockIdx.x * kThreads + threadIdx.x;
+    if (j >= frame_row_count[f] * 3) return;
+    merged[(size_t)f * out_stride * 3 + j] = frame_rows[(size_t)f * rows_stride * 3 + j];
+}
+
 struct SpliceWs {
     size_t off_bounds, off_tile_kept, off_tile_off, off_obj_off, total;
 };
@@ -344,6 +358,7 @@ extern "C" size_t seevcn_splice_workspace_bytes(int num_frames, int pts_per_fram
 extern "C" int seevcn_splice(int num_frames, int pts_per_frame, const float* frame_pts, int num_obj, int pts_per_obj,
                              const float* obj_pts, const int* obj_count, const int* obj_frame, double thresh,
                              unsigned char* keep, int out_stride, float* merged, int* merged_count, int* completed_count,
+                             const float* frame_rows, int frame_rows_stride, const int* frame_row_count,
                              void* workspace, size_t workspace_bytes, seevcn_stream_t stream) {
     SEEVCN_REQUIRE(num_frames >= 0 && pts_per_frame >= 0 && num_obj >= 0 && pts_per_obj >= 0, "splice: negative size");
     SEEVCN_REQUIRE(thresh >= 0.0 && thresh < 1e18, "splice: thresh=%g", thresh);
@@ -383,19 +398,202 @@ extern "C" int seevcn_splice(int num_frames, int pts_per_frame, const float* fra
     }
     if (merged) {
         if (pts_per_frame == 0) SEEVCN_CUDA_CHECK(cudaMemsetAsync(tile_kept, 0, 4 * (size_t)ntiles * num_frames, st));
+        SEEVCN_REQUIRE(!frame_rows == !frame_row_count, "splice: frame_rows and frame_row_count come together");
         splice_offsets_kernel<<<num_frames, kThreads, 0, st>>>(n_obj, ntiles, bounds, tile_kept, obj_off, tile_off, merged_count,
-                                                               completed_count);
+                                                               completed_count, frame_row_count);
         SEEVCN_LAUNCH_CHECK();
         if (pts_per_frame > 0) {
             splice_scatter_points_kernel<<<dim3(ntiles, num_frames), kThreads, 0, st>>>(pts_per_frame, frame_pts, keep, tile_off,
                                                                                         out_stride, merged);
             SEEVCN_LAUNCH_CHECK();
         }
-        if (n_obj > 0) {
+        if (frame_rows) {
+            if (frame_rows_stride > 0) {
+                splice_copy_rows_kernel<<<dim3(div_up(frame_rows_stride * 3, kThreads), num_frames), kThreads, 0, st>>>(
+                    frame_rows_stride, frame_rows, frame_row_count, out_stride, merged);
+                SEEVCN_LAUNCH_CHECK();
+            }
+        } else if (n_obj > 0) {
             splice_scatter_objects_kernel<<<dim3(div_up(pts_per_obj * 3, kThreads), n_obj), kThreads, 0, st>>>(
                 pts_per_obj, obj_pts, bounds, obj_off, out_stride, merged);
             SEEVCN_LAUNCH_CHECK();
         }
     }
+    return SEEVCN_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// all_instances = np.unique(np.vstack(clustered), axis=0)  (SEE_VCN.py:113,244): the distinct completed rows of a frame
+// in lexicographic (x, y, z) order, duplicates across objects removed.  Three kernels, no device-wide sort:
+//   1. unique_sort_objects   a CTA per object: bitonic sort of its (distinct) rows in shared memory
+//   2. unique_rank_rows      a thread per row: its position in the frame = its position in its own object + binary searches
+//                            in the sorted runs of the frame's other objects (equal rows: lower object first)
+//   3. unique_compact        a CTA per frame: drop rows equal to their predecessor, scan, write
+namespace {
+
+constexpr int kUqThreads = 512;
+constexpr int kUqMaxRows = 4096;     // rows per object held in shared memory (16 B per row)
+
+__device__ __forceinline__ bool row_less(float ax, float ay, float az, float bx, float by, float bz) {
+    if (ax != bx) return ax < bx;
+    if (ay != by) return ay < by;
+    return az < bz;
+}
+__device__ __forceinline__ bool row_eq(float ax, float ay, float az, float bx, float by, float bz) {
+    return ax == bx && ay == by && az == bz;
+}
+
+__global__ void __launch_bounds__(kUqThreads)
+unique_sort_objects_kernel(int pts_per_obj, const float* __restrict__ obj_pts, const int* __restrict__ obj_count,
+                           float* __restrict__ sorted_pts) {
+    extern __shared__ __align__(16) unsigned char s_raw[];
+    const int o = blockIdx.x;
+    const int n = obj_count ? min(max(obj_count[o], 0), pts_per_obj) : pts_per_obj;
+    int p2 = 1;
+    while (p2 < n) p2 <<= 1;
+    float* sx = reinterpret_cast<float*>(s_raw);
+    float* sy = sx + p2; float* sz = sy + p2;
+    int* idx = reinterpret_cast<int*>(sz + p2);
+    const float* src = obj_pts + (size_t)o * pts_per_obj * 3;
+    const float inf = __int_as_float(0x7f800000);
+    for (int i = threadIdx.x; i < p2; i += kUqThreads) {
+        const bool ok = i < n;
+        sx[i] = ok ? src[i * 3] : inf; sy[i] = ok ? src[i * 3 + 1] : inf; sz[i] = ok ? src[i * 3 + 2] : inf;
+        idx[i] = i;
+    }
+    __syncthreads();
+    for (int k = 2; k <= p2; k <<= 1)
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            for (int t = threadIdx.x; t < (p2 >> 1); t += kUqThreads) {
+                const int i = ((t & ~(j - 1)) << 1) | (t & (j - 1));
+                const int p = i | j;
+                const int a = idx[i], b = idx[p];
+                // order by (x, y, z), then by original position (stable: equal rows keep their order)
+                const bool a_gt_b = row_less(sx[b], sy[b], sz[b], sx[a], sy[a], sz[a]) ||
+                                    (row_eq(sx[a], sy[a], sz[a], sx[b], sy[b], sz[b]) && a > b);
+                if (a_gt_b == ((i & k) == 0)) { idx[i] = b; idx[p] = a; }
+            }
+            __syncthreads();
+        }
+    float* dst = sorted_pts + (size_t)o * pts_per_obj * 3;
+    for (int i = threadIdx.x; i < n; i += kUqThreads) {
+        const int s = idx[i];
+        dst[i * 3] = sx[s]; dst[i * 3 + 1] = sy[s]; dst[i * 3 + 2] = sz[s];
+    }
+}
+
+// number of rows of the sorted run `run` (n rows) that are < (x,y,z) [or <= when `inclusive`]
+__device__ __forceinline__ int run_bound(const float* __restrict__ run, int n, float x, float y, float z, bool inclusive) {
+    int lo = 0, hi = n;
+    while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        const float mx = run[mid * 3], my = run[mid * 3 + 1], mz = run[mid * 3 + 2];
+        const bool before = inclusive ? !row_less(x, y, z, mx, my, mz) : row_less(mx, my, mz, x, y, z);
+        if (before) lo = mid + 1; else hi = mid;
+    }
+    return lo;
+}
+
+// grid (ceil(S / 256), O)
+__global__ void __launch_bounds__(256)
+unique_rank_rows_kernel(int num_obj, int pts_per_obj, const float* __restrict__ sorted_pts, const int* __restrict__ obj_count,
+                        const int* __restrict__ obj_frame, int out_stride, float* __restrict__ frame_sorted) {
+    const int o = blockIdx.y, i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int n = obj_count ? min(max(obj_count[o], 0), pts_per_obj) : pts_per_obj;
+    if (i >= n) return;
+    const int f = obj_frame[o];
+    const float* mine = sorted_pts + ((size_t)o * pts_per_obj + i) * 3;
+    const float x = mine[0], y = mine[1], z = mine[2];
+    int rank = i;
+    for (int b = o - 1; b >= 0 && obj_frame[b] == f; --b) {      // earlier objects of the frame: their equal rows come first
+        const int nb = obj_count ? min(max(obj_count[b], 0), pts_per_obj) : pts_per_obj;
+        rank += run_bound(sorted_pts + (size_t)b * pts_per_obj * 3, nb, x, y, z, true);
+    }
+    for (int b = o + 1; b < num_obj && obj_frame[b] == f; ++b) {
+        const int nb = obj_count ? min(max(obj_count[b], 0), pts_per_obj) : pts_per_obj;
+        rank += run_bound(sorted_pts + (size_t)b * pts_per_obj * 3, nb, x, y, z, false);
+    }
+    float* dst = frame_sorted + ((size_t)f * out_stride + rank) * 3;
+    dst[0] = x; dst[1] = y; dst[2] = z;
+}
+
+// grid F: total rows of the frame = sum of its objects' counts; keeps row i iff it differs from row i - 1
+__global__ void __launch_bounds__(1024)
+unique_compact_kernel(int num_obj, int pts_per_obj, const int* __restrict__ obj_count, const int* __restrict__ obj_frame,
+                      int out_stride, const float* __restrict__ frame_sorted, float* __restrict__ uniq, int* __restrict__ ucount) {
+    __shared__ int s_w[32];
+    __shared__ int s_total, s_base;
+    const int f = blockIdx.x;
+    if (threadIdx.x == 0) { s_total = 0; s_base = 0; }
+    __syncthreads();
+    int part = 0;
+    for (int o = threadIdx.x; o < num_obj; o += blockDim.x)
+        if (obj_frame[o] == f) part += obj_count ? min(max(obj_count[o], 0), pts_per_obj) : pts_per_obj;
+    if (part) atomicAdd(&s_total, part);
+    __syncthreads();
+    const int total = s_total;
+    const float* src = frame_sorted + (size_t)f * out_stride * 3;
+    float* dst = uniq + (size_t)f * out_stride * 3;
+    for (int i0 = 0; i0 < total; i0 += blockDim.x) {
+        const int i = i0 + threadIdx.x;
+        bool keep = false;
+        float x = 0.f, y = 0.f, z = 0.f;
+        if (i < total) {
+            x = src[i * 3]; y = src[i * 3 + 1]; z = src[i * 3 + 2];
+            keep = i == 0 || !row_eq(x, y, z, src[(i - 1) * 3], src[(i - 1) * 3 + 1], src[(i - 1) * 3 + 2]);
+        }
+        const unsigned b = __ballot_sync(0xffffffffu, keep);
+        if (lane_id() == 0) s_w[warp_id()] = __popc(b);
+        __syncthreads();
+        int before = 0, tot = 0;
+        for (int w = 0; w < (int)(blockDim.x >> 5); ++w) { const int c = s_w[w]; if (w < warp_id()) before += c; tot += c; }
+        if (keep) {
+            float* d = dst + (size_t)(s_base + before + __popc(b & ((1u << lane_id()) - 1))) * 3;
+            d[0] = x; d[1] = y; d[2] = z;
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) s_base += tot;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) ucount[f] = s_base;
+}
+
+}  // namespace
+
+extern "C" size_t seevcn_unique_rows_frames_workspace_bytes(int num_frames, int num_obj, int pts_per_obj, int out_stride) {
+    return align_up((size_t)(num_obj > 0 ? num_obj : 1) * (pts_per_obj > 0 ? pts_per_obj : 1) * 12, 256) +
+           align_up((size_t)(num_frames > 0 ? num_frames : 1) * (out_stride > 0 ? out_stride : 1) * 12, 256);
+}
+
+extern "C" int seevcn_unique_rows_frames(int num_frames, int num_obj, int pts_per_obj, const float* obj_pts, const int* obj_count,
+                                         const int* obj_frame, int out_stride, float* uniq, int* ucount, void* workspace,
+                                         size_t workspace_bytes, seevcn_stream_t stream) {
+    SEEVCN_REQUIRE(num_frames >= 0 && num_obj >= 0 && pts_per_obj >= 0 && out_stride >= 0, "unique_rows_frames: negative size");
+    SEEVCN_REQUIRE(pts_per_obj <= kUqMaxRows, "unique_rows_frames: more than %d rows per object", kUqMaxRows);
+    SEEVCN_REQUIRE(num_obj <= 65535, "unique_rows_frames: more than 65535 objects per call");
+    cudaStream_t st = as_stream(stream);
+    if (num_frames == 0) return SEEVCN_OK;
+    SEEVCN_REQUIRE(ucount, "unique_rows_frames: null pointer");
+    SEEVCN_CUDA_CHECK(cudaMemsetAsync(ucount, 0, sizeof(int) * (size_t)num_frames, st));
+    if (num_obj == 0 || pts_per_obj == 0) return SEEVCN_OK;
+    SEEVCN_REQUIRE(obj_pts && obj_frame && uniq && workspace, "unique_rows_frames: null pointer");
+    if (workspace_bytes < seevcn_unique_rows_frames_workspace_bytes(num_frames, num_obj, pts_per_obj, out_stride)) {
+        seevcn_set_error("unique_rows_frames: workspace too small");
+        return SEEVCN_E_WORKSPACE;
+    }
+    SEEVCN_PROF("unique_rows", st);
+    float* sorted_pts = static_cast<float*>(workspace);
+    float* frame_sorted = reinterpret_cast<float*>(static_cast<char*>(workspace) + align_up((size_t)num_obj * pts_per_obj * 12, 256));
+    int p2 = 1;
+    while (p2 < pts_per_obj) p2 <<= 1;
+    const size_t smem = (size_t)p2 * 16;
+    SEEVCN_CUDA_CHECK(cudaFuncSetAttribute(unique_sort_objects_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((size_t)kUqMaxRows * 16)));
+    unique_sort_objects_kernel<<<num_obj, kUqThreads, smem, st>>>(pts_per_obj, obj_pts, obj_count, sorted_pts);
+    SEEVCN_LAUNCH_CHECK();
+    unique_rank_rows_kernel<<<dim3(div_up(pts_per_obj, 256), num_obj), 256, 0, st>>>(num_obj, pts_per_obj, sorted_pts, obj_count,
+                                                                                    obj_frame, out_stride, frame_sorted);
+    SEEVCN_LAUNCH_CHECK();
+    unique_compact_kernel<<<num_frames, 1024, 0, st>>>(num_obj, pts_per_obj, obj_count, obj_frame, out_stride, frame_sorted, uniq, ucount);
+    SEEVCN_LAUNCH_CHECK();
     return SEEVCN_OK;
 }

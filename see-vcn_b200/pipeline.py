@@ -182,8 +182,9 @@ class CompletionPipeline:
         thresh = self.splice_thresh if self.splice_thresh is not None else 0.0
         has_obj = completed.shape[0] > 0
         count = out.get("clustered_distinct", out.get("surface_count")) if has_obj else None
+        # merged frame cloud exactly as the reference writes it: np.unique of the frame's completed rows, then the survivors
         keep, merged, m_cnt, c_cnt = splice_frames(points, completed if has_obj else None, out.get("obj_frame_dev"), count,
-                                                   thresh, merged=True)
+                                                   thresh, merged=True, unique=True)
         if self._hard_gen is None:
             T, MV = self.hard_voxels
             self._hard_gen = VoxelGeneratorWrapper(self.voxel_cfg[1], self.voxel_cfg[0], 3, T, MV)

@@ -12,13 +12,32 @@ import torch
 from ... import _abi
 
 
-def splice_frames(frame_pts, obj_pts, obj_frame, obj_count=None, point_dist_thresh=0.1, merged=False):
+def all_instances_frames(obj_pts, obj_frame, obj_count, num_frames, out_stride):
+    """ref: SEE_VCN.py:113,244 — ``np.unique(np.vstack(clustered), axis=0)`` per frame, on the device.
+    obj_pts (O,S,3), obj_frame (O,) int32 non-decreasing, obj_count (O,) int32 or None ->
+    (uniq (F, out_stride, 3) f32, ucount (F,) int32): rows in lexicographic (x, y, z) order, duplicates removed."""
+    _abi.require_cuda(obj_pts, obj_frame, obj_count)
+    O, S, _ = obj_pts.shape
+    dev = obj_pts.device
+    L = _abi.lib()
+    uniq = torch.empty((num_frames, out_stride, 3), dtype=torch.float32, device=dev)
+    ucount = torch.empty((num_frames,), dtype=torch.int32, device=dev)
+    ws = _abi.workspace(dev, L.seevcn_unique_rows_frames_workspace_bytes(num_frames, O, S, out_stride), "uniq")
+    with _abi.device_guard(dev):
+        _abi.check(L.seevcn_unique_rows_frames(num_frames, O, S, _abi.ptr(obj_pts), _abi.ptr(obj_count), _abi.ptr(obj_frame), out_stride,
+                                               _abi.ptr(uniq), _abi.ptr(ucount), _abi.ptr(ws), ws.numel(), _abi.stream()))
+    return uniq, ucount
+
+
+def splice_frames(frame_pts, obj_pts, obj_frame, obj_count=None, point_dist_thresh=0.1, merged=False, unique=False):
     """frame_pts (F,P,3) f32 CUDA; obj_pts (O,S,3) f32 CUDA completed clouds, obj_frame (O,) int32 non-decreasing,
     obj_count (O,) int32 or None = the distinct rows of every (cyclically tiled) object cloud.
 
     -> keep (F,P) uint8 CUDA (1 = the raw point survives); with ``merged=True`` also
        (merged (F,P+max rows,3) f32, merged_count (F,) int32, completed_count (F,) int32): per frame
-       [completed rows ++ surviving raw points], the reference's return value, rows >= merged_count[f] undefined."""
+       [completed rows ++ surviving raw points], the reference's return value, rows >= merged_count[f] undefined.
+       ``unique=True``: the completed rows are ``np.unique`` of the frame's object rows (lexicographic order, cross-object
+       duplicates removed) exactly as SEE_VCN.py:244 builds ``all_instances``; default: distinct rows per object, object order."""
     frame_pts = frame_pts.contiguous()
     _abi.require_cuda(frame_pts)
     assert frame_pts.dtype == torch.float32 and frame_pts.dim() == 3 and frame_pts.shape[2] == 3
@@ -47,10 +66,16 @@ def splice_frames(frame_pts, obj_pts, obj_frame, obj_count=None, point_dist_thre
         out = torch.empty((F, stride, 3), dtype=torch.float32, device=dev)
         m_cnt = torch.empty((F,), dtype=torch.int32, device=dev)
         c_cnt = torch.empty((F,), dtype=torch.int32, device=dev)
+    rows = rows_cnt = None
+    rows_stride = 0
+    if merged and unique and O > 0:
+        rows_stride = O * S
+        rows, rows_cnt = all_instances_frames(obj_pts, obj_frame, obj_count, F, rows_stride)
     with _abi.device_guard(dev):
         _abi.check(L.seevcn_splice(F, P, _abi.ptr(frame_pts), O, S, _abi.ptr(obj_pts), _abi.ptr(obj_count), _abi.ptr(obj_frame),
                                    float(point_dist_thresh), _abi.ptr(keep), stride, _abi.ptr(out), _abi.ptr(m_cnt),
-                                   _abi.ptr(c_cnt), _abi.ptr(ws), ws.numel(), _abi.stream()))
+                                   _abi.ptr(c_cnt), _abi.ptr(rows), rows_stride, _abi.ptr(rows_cnt),
+                                   _abi.ptr(ws), ws.numel(), _abi.stream()))
     return (keep, out, m_cnt, c_cnt) if merged else keep
 
 
@@ -67,7 +92,7 @@ def replace_with_completed_pts(original_points, sc_instances, point_dist_thresh=
     d_pts = torch.from_numpy(pts).to(dev).view(1, -1, 3)
     d_sc = torch.from_numpy(sc).to(dev).view(1, -1, 3)
     frame = torch.zeros((1,), dtype=torch.int32, device=dev)
-    _, merged, m_cnt, _ = splice_frames(d_pts, d_sc, frame, None, point_dist_thresh, merged=True)
+    _, merged, m_cnt, _ = splice_frames(d_pts, d_sc, frame, None, point_dist_thresh, merged=True)   # sc_instances is already unique
     return merged[0, : int(m_cnt[0])].cpu().numpy()
 
 

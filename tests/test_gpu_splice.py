@@ -159,6 +159,38 @@ def test_splice_candidate_queue_overflow_ragged(cuda):
         np.testing.assert_array_equal(merged[f, : int(m_cnt[f])].cpu().numpy(), want_merged[f])
 
 
+def test_all_instances_unique_rows_and_reference_merged_cloud(cuda):
+    """SEE_VCN.py:244 + 262 exactly: all_instances = np.unique(vstack(clustered), axis=0) per frame (lexicographic order,
+    duplicates across objects removed — two objects here are copies of each other and one shares a row block), then
+    vstack(all_instances, surviving raw points)."""
+    from seevcn_b200.see.surface_completion.SEE_VCN import all_instances_frames
+    pts, objs, frame, count = _scene(72, 3, 700, 14, 256)
+    objs[3] = objs[2]; frame[3] = frame[2]; count[3] = count[2]                 # a duplicate detection of the same object
+    objs[5, :40] = objs[4, 10:50]                                               # shared rows between neighbours
+    objs[7, 5] = objs[7, 4]                                                     # a repeated row inside one object
+    objs[8, 0, 0] = -0.0; objs[8, 1, 0] = 0.0
+    count[2:9] = objs.shape[1]                                                  # the manipulated rows all take part
+    order = np.argsort(frame, kind="stable")
+    objs, frame, count = objs[order], frame[order], count[order]
+    F = pts.shape[0]
+    stride = objs.shape[0] * objs.shape[1]
+    uniq, ucount = all_instances_frames(dev(objs, cuda), dev(frame, cuda), dev(count, cuda), F, stride)
+    want = [oracle.all_instances(objs[frame == f], count[frame == f]) for f in range(F)]
+    dropped = 0
+    for f in range(F):
+        assert int(ucount[f]) == len(want[f]) <= count[frame == f].sum()
+        dropped += int(count[frame == f].sum()) - len(want[f])
+        np.testing.assert_array_equal(uniq[f, : len(want[f])].cpu().numpy(), want[f])
+    assert dropped >= 256 + 40 + 1                                             # the duplicates really were removed
+    keep, merged, m_cnt, c_cnt = splice_frames(dev(pts, cuda), dev(objs, cuda), dev(frame, cuda), dev(count, cuda), 0.1,
+                                               merged=True, unique=True)
+    for f in range(F):
+        ref_merged, ref_keep = oracle.replace_with_completed_pts(pts[f], want[f], 0.1)
+        np.testing.assert_array_equal(keep[f].cpu().numpy().astype(bool), ref_keep)
+        assert int(c_cnt[f]) == len(want[f]) and int(m_cnt[f]) == len(ref_merged)
+        np.testing.assert_array_equal(merged[f, : len(ref_merged)].cpu().numpy(), ref_merged)
+
+
 def test_replace_with_completed_pts_reference_entry(cuda):
     rng = np.random.default_rng(8)
     pts = rng.uniform(-10, 10, (5000, 3)).astype(np.float32)
@@ -248,7 +280,11 @@ def test_pipeline_hard_voxels_second_iou_front_end(cuda):
     pts, boxes = synth.make_stream(2, n_beams=32, n_az=1090, n_boxes=10, first_seed=300)
     out = pipe.run(dev(pts, cuda), dev(boxes, cuda), seed=0)
     comp, cnt, ofr = out["clustered"].cpu().numpy(), out["completed_count"].cpu().numpy(), out["obj_frame"]
-    want_keep, want_merged = _want(pts, comp, ofr, cnt, 0.1)
+    want_keep, _ = _want(pts, comp, ofr, cnt, 0.1)
+    want_merged = []
+    for f in range(2):   # the reference's merged frame: np.unique of the frame's completed rows ++ the surviving raw points
+        sc = oracle.all_instances(comp[ofr == f], cnt[ofr == f])
+        want_merged.append(oracle.replace_with_completed_pts(pts[f], sc if len(sc) else None, 0.1)[0])
     coords = out["voxel_coords"].view(2, MV, 4).cpu().numpy()
     feats = out["voxel_features"].view(2, MV, 3).cpu().numpy()
     nums = out["voxel_num_points"].view(2, MV).cpu().numpy()
