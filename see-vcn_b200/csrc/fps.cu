@@ -136,6 +136,87 @@ fps_kernel(int n, int m, int bs, const float* __restrict__ dataset, float* __res
     }
 }
 
+// Fast path for n == PPT * bs exactly (every thread owns PPT valid points: 16,384 -> PPT 16, 2,048 -> 2, 1,024 -> 1).
+// The kernel above spends ~35 instructions per point and round on bounds predicates, index tracking and the tie rule of
+// the reference's tree; here a round is, per point, 3 subtractions, 3 multiply-adds, one min and one max:
+//  * the thread keeps only the running MAX of its updated distances; the point that holds it (the lowest j on ties, as a
+//    strict '>' scan finds it) is looked up afterwards among PPT registers;
+//  * the block argmax reduces ONE 64-bit key per thread: distance bits (non-negative floats order like unsigned ints) in
+//    the high word, ~bit_reverse(thread id) in the top bits of the low word — on equal distances the thread with the
+//    smallest bit-reversed id wins, which is exactly what the reference's shared-memory tree leaves (better() above) —
+//    and j in its low four bits, from which the winner's index tid + j * bs is rebuilt.
+__device__ __forceinline__ unsigned long long warp_max_u64(unsigned long long k) {
+#pragma unroll
+    for (int off = 16; off >= 1; off >>= 1) {
+        const unsigned long long o = __shfl_xor_sync(0xffffffffu, k, off);
+        k = o > k ? o : k;
+    }
+    return k;
+}
+
+template <int PPT>
+__global__ void __launch_bounds__(1024)
+fps_kernel_full(int n, int m, const float* __restrict__ dataset, float* __restrict__ temp, int* __restrict__ idxs) {
+    extern __shared__ float s_dyn[];
+    __shared__ unsigned long long s_k[2][32];
+    if (m <= 0) return;
+    const int tid = threadIdx.x, bs = blockDim.x;
+    const int nwarps = bs >> 5;
+    dataset += (size_t)blockIdx.x * n * 3;
+    idxs += (size_t)blockIdx.x * m;
+    if (temp) temp += (size_t)blockIdx.x * n;
+    float* sx = s_dyn; float* sy = s_dyn + n; float* sz = s_dyn + 2 * n;
+    for (int f = tid; f < 3 * n; f += bs) {
+        const float v = dataset[f];
+        const int k = f / 3, c = f - 3 * k;
+        s_dyn[c * n + k] = v;
+    }
+    __syncthreads();
+    constexpr int REG = PPT <= 4 ? PPT : (PPT <= 8 ? 6 : 8);     // coordinates held in registers; the rest from shared memory
+    float dist[PPT], px[REG], py[REG], pz[REG];
+#pragma unroll
+    for (int j = 0; j < PPT; ++j) {
+        dist[j] = 1e10f;   // pointnet2_utils.py:26
+        if (j < REG) { px[j] = sx[tid + j * bs]; py[j] = sy[tid + j * bs]; pz[j] = sz[tid + j * bs]; }
+    }
+    const float* mx = sx + tid; const float* my = sy + tid; const float* mz = sz + tid;
+    const unsigned low_tid = ~__brev((unsigned)tid) & 0xffc00000u;
+    int old = 0;
+    if (tid == 0) idxs[0] = 0;
+    for (int r = 1; r < m; ++r) {
+        const float x1 = sx[old], y1 = sy[old], z1 = sz[old];
+        float best = -1.f;
+#pragma unroll
+        for (int j = 0; j < PPT; ++j) {
+            float x2, y2, z2;
+            if (j < REG) { x2 = px[j]; y2 = py[j]; z2 = pz[j]; }
+            else { x2 = mx[j * bs]; y2 = my[j * bs]; z2 = mz[j * bs]; }
+            const float dx = __fsub_rn(x2, x1), dy = __fsub_rn(y2, y1), dz = __fsub_rn(z2, z1);
+            const float d = __fmaf_rn(dz, dz, __fmaf_rn(dy, dy, __fmul_rn(dx, dx)));
+            const float d2 = fminf(d, dist[j]);
+            dist[j] = d2;
+            best = fmaxf(best, d2);
+        }
+        unsigned jb = 0;
+#pragma unroll
+        for (int j = PPT - 1; j >= 0; --j) jb = dist[j] == best ? (unsigned)j : jb;     // lowest j holding the maximum
+        unsigned long long key = ((unsigned long long)__float_as_uint(best) << 32) | (low_tid | jb);
+        key = warp_max_u64(key);
+        const int buf = r & 1;
+        if ((tid & 31) == 0) s_k[buf][tid >> 5] = key;
+        __syncthreads();
+        unsigned long long w = (tid & 31) < nwarps ? s_k[buf][tid & 31] : 0ull;
+        w = warp_max_u64(w);
+        const unsigned low = (unsigned)w;
+        old = (int)__brev(~low & 0xffc00000u) + (int)(low & 0xfu) * bs;
+        if (tid == 0) idxs[r] = old;
+    }
+    if (temp) {
+#pragma unroll
+        for (int j = 0; j < PPT; ++j) temp[tid + j * bs] = dist[j];
+    }
+}
+
 // Any N: min-distance array in global `temp` (L2 resident), xyz from global.
 __global__ void __launch_bounds__(1024)
 fps_kernel_global(int n, int m, int bs, const float* __restrict__ dataset, float* __restrict__ temp, int* __restrict__ idxs) {
@@ -177,6 +258,14 @@ fps_kernel_global(int n, int m, int bs, const float* __restrict__ dataset, float
 template <int PPT>
 int launch_fps(int b, int n, int m, int bs, const float* dataset, float* temp, int* idxs, cudaStream_t st) {
     const size_t smem = (size_t)3 * n * sizeof(float);
+    if (n == PPT * bs && bs >= 32) {       // every thread owns exactly PPT points: the lean kernel
+        auto fast = fps_kernel_full<PPT>;
+        if (smem > 40 * 1024) SEEVCN_CUDA_CHECK(cudaFuncSetAttribute(fast, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        SEEVCN_PROF("fps", st);
+        fast<<<b, bs, smem, st>>>(n, m, dataset, temp, idxs);
+        SEEVCN_LAUNCH_CHECK();
+        return SEEVCN_OK;
+    }
     auto kern = fps_kernel<PPT, true>;
     if (smem > 40 * 1024)   // dynamic + 512 B static must stay under the 48 KB default
         SEEVCN_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

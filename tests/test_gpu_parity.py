@@ -179,7 +179,8 @@ def test_fps_ties_bit_exact_vs_reference_kernel(cuda):
     R = oracle.ref_kernels()
     if R is None:
         pytest.skip("oracle/_ref/libref_kernels.so not built")
-    for n, m, src in ((1024, 400, 150), (1000, 300, 77), (4096, 512, 300), (48, 48, 5)):
+    for n, m, src in ((1024, 400, 150), (1000, 300, 77), (4096, 512, 300), (48, 48, 5), (16384, 256, 3000), (2048, 300, 500),
+                      (64, 64, 9)):
         part, _, _ = synth.make_object_clouds(90 + n, 3, src, 0)
         tiled = np.tile(part, (1, n // src + 1, 1))[:, :n].copy()
         xyz = dev(tiled, cuda)
