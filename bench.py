@@ -419,7 +419,7 @@ def run_frames(args):
     pts_d = [p.to(dev) for p in pts_pin]
     boxes_d = [b.to(dev) for b in boxes_pin]
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev) if args.l2 == "flush" else None   # > 126 MB L2
-    hs = HostStream(pipe, F, P_pts, T_box)
+    hs = HostStream(pipe, F, P_pts, T_box, lag=args.lag)
     step_no = [0]
 
     def batches(n_steps, srcs_p, srcs_b):
@@ -711,7 +711,8 @@ def main():
     ap.add_argument("--precision", default=os.environ.get("SEEVCN_PRECISION", "bf16"), choices=["bf16", "fp32"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-gather", action="store_true", help="N > 1: skip the end-of-path collect (attribution runs)")
-    ap.add_argument("--streams", type=int, default=2, help="CUDA streams consecutive pipeline batches alternate on")
+    ap.add_argument("--streams", type=int, default=4, help="CUDA streams consecutive pipeline batches alternate on")
+    ap.add_argument("--lag", type=int, default=None, help="e2e: batches issued ahead of the one being finalized (default: HostStream's rule)")
     ap.add_argument("--l2", default="rotate", choices=["rotate", "flush"], help="how a step is kept from finding its inputs in L2")
     ap.add_argument("--gather", default="auto", choices=["auto", "peer", "nccl"], help="N > 1: how the results are collected")
     args = ap.parse_args()

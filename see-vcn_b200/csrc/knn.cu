@@ -191,12 +191,13 @@ __device__ void bitonic_sort(u64* s, int len) {
 // point — and skips a block when, for every lane, the squared distance from the query to the block's box
 // exceeds the lane's k-th best distance so far.  The box distance is evaluated with the operation order of
 // the point distance, so in fp32 it never exceeds the distance of a point inside the box and the result is
-// exactly the brute-force one (ties: lower index).  Blocks are visited nearest first (key = the smallest box
-// distance over the warp's queries), so the heaps fill with a tight k-th distance at once, and the walk ends
-// when the next key exceeds every lane's k-th distance: a far-away query only touches the blocks of the cap
-// of the cloud that faces it, a query inside the cloud only the patches around it.  The next block's points
-// are loaded (one coalesced 512 B read) while the current one is scanned from the warp's shared-memory tile.  Each warp ORs its neighbour sets into a private shared-memory mask and
-// then, one word per lane, into the object's global bit mask.
+// exactly the brute-force one (ties: lower index).  Blocks are visited nearest first: the warp sorts them once by
+// the smallest box distance over its 32 queries, so the heaps fill with a tight k-th distance at once and the walk ends at the first entry beyond
+// every lane's k-th distance: a far-away query only touches the blocks of the cap of the cloud that faces it, a
+// query inside the cloud only the patches around it.  Boxes are fetched two entries ahead and a needed block's
+// points (one coalesced 512 B read) one entry ahead, while the current one is scanned from the warp's
+// shared-memory tile.  Each warp ORs its neighbour sets into a private shared-memory mask and then, one word per
+// lane, into the object's global bit mask.
 //
 // (3) knn_emit_kernel, one CTA per object: complete[sorted(S)] repeated cyclically, and |S|.
 //
@@ -373,10 +374,26 @@ __device__ __forceinline__ void scan_block(TopK<32>& tk, bool active, float qx, 
 }
 
 // per warp in shared memory: heap k x 32 u64 | buffer kScanBuf x 32 u64 | block tile 32 float4 | union mask nwords u32 |
-// block keys nwords u32
+// walk order pow2(nwords) u32
 __host__ __device__ inline size_t scan_warp_smem(int k, int r) {
     const size_t nwords = (size_t)(r + 31) >> 5;
-    return ((size_t)(k + kScanBuf) * 32 * 8 + 512 + 2 * nwords * 4 + 15) & ~(size_t)15;
+    size_t np2 = 1;
+    while (np2 < nwords) np2 <<= 1;
+    return ((size_t)(k + kScanBuf) * 32 * 8 + 512 + (nwords + np2) * 4 + 15) & ~(size_t)15;
+}
+
+// ascending bitonic sort of s[0..len), len a power of two, by one warp
+__device__ __forceinline__ void warp_bitonic_sort_u32(unsigned* s, int len) {
+    for (int k = 2; k <= len; k <<= 1)
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            for (int t = lane_id(); t < (len >> 1); t += 32) {
+                const int i = ((t & ~(j - 1)) << 1) | (t & (j - 1));
+                const int p = i | j;
+                const unsigned a = s[i], b = s[p];
+                if ((a > b) == ((i & k) == 0)) { s[i] = b; s[p] = a; }
+            }
+            __syncwarp();
+        }
 }
 
 __global__ void __launch_bounds__(kScanThreads)
@@ -393,7 +410,7 @@ knn_scan_kernel(int np, int r, int k, const float4* __restrict__ ws_refs, const 
     u64* s_buf = s_list + (size_t)k * 32;
     float4* tile = reinterpret_cast<float4*>(s_buf + (size_t)kScanBuf * 32);
     unsigned* mask = reinterpret_cast<unsigned*>(tile + 32);
-    unsigned* wkey = mask + nwords;
+    unsigned* order = mask + nwords;
     const unsigned full = 0xffffffffu;
     for (int i = lane_id(); i < nwords; i += 32) mask[i] = 0u;
 
@@ -406,46 +423,60 @@ knn_scan_kernel(int np, int r, int k, const float4* __restrict__ ws_refs, const 
     TopK<32> tk;
     tk.init(s_list + lane_id(), s_buf + lane_id(), k);
 
-    // block key = the smallest box distance over the warp's queries (non-negative float bits order like unsigned)
+    // Walk order: blocks by the smallest box distance over the warp's queries, nearest first (non-negative float bits
+    // order like unsigned), so the walk may stop at the first entry beyond every lane's k-th distance.  Entry =
+    // distance bits with the low `ib` bits replaced by the block number (rounds the key DOWN, which keeps the stop
+    // test conservative; the order only decides how fast the heaps tighten, never the result).
+    const int ib = nwords > 1 ? 32 - __clz(nwords - 1) : 0;
+    const int np2 = 1 << ib;
+    const unsigned imask = (unsigned)np2 - 1u;
 #pragma unroll 4
     for (int blk = 0; blk < nwords; ++blk) {
         const float bd = box_sqdist(q.x, q.y, q.z, __ldg(&box[2 * blk]), __ldg(&box[2 * blk + 1]));
         const unsigned m = __reduce_min_sync(full, active ? __float_as_uint(bd) : 0xffffffffu);
-        if (lane_id() == 0) wkey[blk] = m;
+        if (lane_id() == 0) order[blk] = (m & ~imask) | (unsigned)blk;
     }
+    for (int j = nwords + lane_id(); j < np2; j += 32) order[j] = 0xffffffffu;
     __syncwarp();
+    warp_bitonic_sort_u32(order, np2);
 
-    // nearest unscanned block whose key does not exceed the largest k-th distance of the warp, or -1; marks it scanned
-    auto pick = [&]() -> int {
-        unsigned best = 0xffffffffu; int bi = -1;
-        for (int j = lane_id(); j < nwords; j += 32) { const unsigned v = wkey[j]; if (v < best) { best = v; bi = j; } }
-        const unsigned m = __reduce_min_sync(full, best);
-        const unsigned tmax = __reduce_max_sync(full, active ? __float_as_uint(tk.thr_f) : 0u);
-        if (m == 0xffffffffu || m > tmax) return -1;
-        const int src = __ffs(__ballot_sync(full, best == m)) - 1;
-        const int blk = __shfl_sync(full, bi, src);
-        if (lane_id() == src) wkey[blk] = 0xffffffffu;
-        __syncwarp();
-        return blk;
+    // Entry i's box is loaded two iterations ahead and its points one iteration ahead (when some lane still needs the
+    // block by the k-th distances as they stand then: they only shrink, so a needed block is never left out).
+    auto entry_blk = [&](int i) -> int { return i < nwords ? (int)(order[i] & imask) : -1; };
+    auto load_box = [&](int blk, float4& lo, float4& hi) {
+        if (blk >= 0) { lo = __ldg(&box[2 * blk]); hi = __ldg(&box[2 * blk + 1]); }
     };
-    auto load = [&](int blk) -> float4 {
+    auto needed = [&](float4 lo, float4 hi) -> bool {
+        return __any_sync(full, active && box_sqdist(q.x, q.y, q.z, lo, hi) <= tk.thr_f);
+    };
+    auto load_pts = [&](int blk) -> float4 {
         const int p = blk * 32 + lane_id();
-        return (blk >= 0 && p < r) ? __ldg(&refs[p]) : make_float4(0.f, 0.f, 0.f, 0.f);
+        return p < r ? __ldg(&refs[p]) : make_float4(0.f, 0.f, 0.f, 0.f);
     };
-
-    int cur = pick();
-    float4 regs = load(cur);
-    while (cur >= 0) {
-        const int nxt = pick();                   // chosen with the k-th distances as they stand: never skips a needed block
-        const float4 nregs = load(nxt);           // in flight while the current block is scanned
-        const float bd = box_sqdist(q.x, q.y, q.z, __ldg(&box[2 * cur]), __ldg(&box[2 * cur + 1]));
-        if (__any_sync(full, active && bd <= tk.thr_f)) {
-            tile[lane_id()] = regs;
+    const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    int blk0 = entry_blk(0), blk1 = entry_blk(1);
+    float4 lo0 = zero4, hi0 = zero4, lo1 = zero4, hi1 = zero4;
+    load_box(blk0, lo0, hi0);
+    load_box(blk1, lo1, hi1);
+    bool need0 = needed(lo0, hi0);                // heaps are empty: true whenever the warp has a query
+    float4 pts0 = need0 ? load_pts(blk0) : zero4;
+    unsigned tmax = 0x7f800000u;
+    for (int i = 0; i < nwords; ++i) {
+        if ((order[i] & ~imask) > tmax) break;    // sorted: every later entry is farther still
+        const int blk2 = entry_blk(i + 2);
+        float4 lo2 = zero4, hi2 = zero4;
+        load_box(blk2, lo2, hi2);
+        const bool need1 = blk1 >= 0 && needed(lo1, hi1);
+        const float4 pts1 = need1 ? load_pts(blk1) : zero4;
+        if (need0 && needed(lo0, hi0)) {
+            tile[lane_id()] = pts0;
             __syncwarp();
-            scan_block(tk, active, q.x, q.y, q.z, tile, min(32, r - cur * 32));
+            scan_block(tk, active, q.x, q.y, q.z, tile, min(32, r - blk0 * 32));
             __syncwarp();
+            tmax = __reduce_max_sync(full, active ? __float_as_uint(tk.thr_f) : 0u);
         }
-        cur = nxt; regs = nregs;
+        blk0 = blk1; lo0 = lo1; hi0 = hi1; need0 = need1; pts0 = pts1;
+        blk1 = blk2; lo1 = lo2; hi1 = hi2;
     }
     if (active)
         for (int j = 0; j < k; ++j) {

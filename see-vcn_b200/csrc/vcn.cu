@@ -26,17 +26,21 @@ int vcn_pointwise3(const LinearW& L, size_t rows, const float* X, int act, __nv_
 size_t vcn_fc_part_bytes(int rows, int cout, int cin);
 int vcn_fc_tc(const LinearW& L, int rows, const __nv_bfloat16* X, int ldx, int act, float* Yf32, __nv_bfloat16* Yb16, int ldb,
               float* part, cudaStream_t st);
+// split-K partial sums only (no reduce launch): the consumer sums the *ksplit slices of `part` in index order and adds L.b
+int vcn_fc_tc_partials(const LinearW& L, int rows, const __nv_bfloat16* X, int ldx, float* part, int* ksplit, cudaStream_t st);
 // vcn_chain.cu: fused per-point chains (tcgen05, activations kept in TMEM)
 int vcn_chain_pose(const seevcn_vcn_model* M, int num_obj, int n, const float* input, const VcnFrame* frames,
                    float* pose_feat, cudaStream_t st);
 int vcn_chain_enc1(const seevcn_vcn_model* M, int num_obj, int n, const float* input, const VcnFrame* frames,
                    const VcnPose* poses, __nv_bfloat16* F, float* g256, cudaStream_t st);
-int vcn_chain_enc2(const seevcn_vcn_model* M, int num_obj, int n, const __nv_bfloat16* F, const float* obj_bias,
-                   float* feat, cudaStream_t st);
+int vcn_chain_enc2(const seevcn_vcn_model* M, int num_obj, int n, const __nv_bfloat16* F, const float* obj_bias_part,
+                   int obj_bias_splits, float* feat, cudaStream_t st);
 
 namespace {
 
 // ---------------------------------------------------------------- per-object kernels --
+
+struct VcnMaxInit { float* dst[3] = {nullptr, nullptr, nullptr}; int width[3] = {0, 0, 0}; };
 
 // One CTA per object.  VC: theta = atan2(mean y, mean x); a = -theta; fview = p . R(a);
 // mean = mean(fview); writes centred = fview - mean  (VCN_VC.py:185-190).
@@ -44,10 +48,15 @@ namespace {
 // out rows (n,3) fp32: VC -> centred cloud (pose-encoder input); CN -> canonical cloud (encoder input).
 __global__ void __launch_bounds__(256)
 vcn_frame_kernel(int n, int viewer_centred, const float* __restrict__ input, const float* __restrict__ gt_boxes,
-                 VcnFrame* __restrict__ frames, float* __restrict__ out) {
+                 VcnFrame* __restrict__ frames, float* __restrict__ out, VcnMaxInit init = VcnMaxInit{}) {
     __shared__ float red[3][8];
     __shared__ VcnFrame fr;
     const int o = blockIdx.x;
+    // -inf into this object's rows of the max-pool targets of the chains that follow (saves their fill launches)
+#pragma unroll
+    for (int t = 0; t < 3; ++t)
+        if (init.dst[t])
+            for (int i = threadIdx.x; i < init.width[t]; i += 256) init.dst[t][(size_t)o * init.width[t] + i] = -__builtin_huge_valf();
     const float* p = input + (size_t)o * n * 3;
     float* q = out + (size_t)o * n * 3;
     auto block_sum3 = [&](float a, float b, float c, float& ra, float& rb, float& rc) {
@@ -108,14 +117,9 @@ vcn_frame_kernel(int n, int viewer_centred, const float* __restrict__ input, con
     }
 }
 
-// Thread per object: rel_pose (9) -> centre, rot (Gram-Schmidt, VCN_VC.py:12-49), and the
-// reg_rot / reg_centre outputs (VCN_VC.py:211-212).
-__global__ void vcn_pose_kernel(int num_obj, const float* __restrict__ rel_pose, int ld, const VcnFrame* __restrict__ frames,
-                                VcnPose* __restrict__ poses, float* __restrict__ reg_rot, float* __restrict__ reg_centre) {
-    const int o = blockIdx.x * blockDim.x + threadIdx.x;
-    if (o >= num_obj) return;
-    const float* r = rel_pose + (size_t)o * ld;
-    const VcnFrame f = frames[o];
+// rel_pose (9) -> centre, rot (Gram-Schmidt, VCN_VC.py:12-49), and the reg_rot / reg_centre outputs (VCN_VC.py:211-212).
+__device__ void pose_from_rel(int o, const float* r, const VcnFrame& f, VcnPose* __restrict__ poses,
+                              float* __restrict__ reg_rot, float* __restrict__ reg_centre) {
     VcnPose P;
     P.centre[0] = f.mean[0] + r[0]; P.centre[1] = f.mean[1] + r[1]; P.centre[2] = f.mean[2] + r[2];
     float x[3] = {r[3], r[4], r[5]}, yr[3] = {r[6], r[7], r[8]}, z[3], y[3];
@@ -145,6 +149,42 @@ __global__ void vcn_pose_kernel(int num_obj, const float* __restrict__ rel_pose,
     }
 }
 
+// Thread per object (layer-wise paths).
+__global__ void vcn_pose_kernel(int num_obj, const float* __restrict__ rel_pose, int ld, const VcnFrame* __restrict__ frames,
+                                VcnPose* __restrict__ poses, float* __restrict__ reg_rot, float* __restrict__ reg_centre) {
+    const int o = blockIdx.x * blockDim.x + threadIdx.x;
+    if (o >= num_obj) return;
+    pose_from_rel(o, rel_pose + (size_t)o * ld, frames[o], poses, reg_rot, reg_centre);
+}
+
+// The tail of the pose branch in one launch, one CTA (288 threads = 9 warps) per object:
+// h = leaky(sum of the split-K slices of pose_fc.0 + b0)  (the slices summed in index order: what fc_reduce_kernel does),
+// rel = W2 h + b2 (pose_fc.2, 512 -> 9: warp j owns output j, lanes split K as linear_skinny_kernel does), then the pose.
+constexpr int kPoseHidden = 512;
+__global__ void __launch_bounds__(288)
+vcn_pose_tail_kernel(int num_obj, int ksplit, const float* __restrict__ part, const float* __restrict__ b0,
+                     const float* __restrict__ w2, const float* __restrict__ b2, const VcnFrame* __restrict__ frames,
+                     VcnPose* __restrict__ poses, float* __restrict__ reg_rot, float* __restrict__ reg_centre) {
+    __shared__ float h[kPoseHidden];
+    __shared__ float rel[9];
+    const int o = blockIdx.x;
+    for (int c = threadIdx.x; c < kPoseHidden; c += 288) {
+        float s = part[(size_t)o * kPoseHidden + c];
+        for (int k = 1; k < ksplit; ++k) s += part[((size_t)k * num_obj + o) * kPoseHidden + c];
+        if (b0) s += b0[c];
+        h[c] = apply_act(s, ACT_LEAKY);
+    }
+    __syncthreads();
+    const int j = warp_id();
+    float acc = 0.f;
+    for (int k = lane_id(); k < kPoseHidden; k += 32) acc = fmaf(h[k], w2[(size_t)j * kPoseHidden + k], acc);
+#pragma unroll
+    for (int off = 16; off >= 1; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
+    if (lane_id() == 0) rel[j] = acc + (b2 ? b2[j] : 0.f);
+    __syncthreads();
+    if (threadIdx.x == 0) pose_from_rel(o, rel, frames[o], poses, reg_rot, reg_centre);
+}
+
 // pc_cn = (fview - centre) . rot^T  (VCN_VC.py:200); fview recomputed from the raw input.
 __global__ void __launch_bounds__(256)
 vcn_canon_kernel(int n, const float* __restrict__ input, const VcnFrame* __restrict__ frames,
@@ -169,12 +209,24 @@ vcn_canon_kernel(int n, const float* __restrict__ input, const VcnFrame* __restr
 // CN: (c * length) rotated by +heading, + centre (VCN_CN.py:153-155).
 __global__ void __launch_bounds__(256)
 vcn_output_kernel(int m, int viewer_centred, const float* __restrict__ coarse_cn, const VcnFrame* __restrict__ frames,
-                  const VcnPose* __restrict__ poses, float* __restrict__ coarse) {
+                  const VcnPose* __restrict__ poses, float* __restrict__ coarse, int ksplit = 0,
+                  const float* __restrict__ bias = nullptr) {
     const int o = blockIdx.y;
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= m) return;
     const VcnFrame f = frames[o];
+    float cs[3];
     const float* c = coarse_cn + ((size_t)o * m + i) * 3;
+    if (ksplit > 0) {   // coarse_cn holds the split-K slices of shape_fc.4: sum them in index order, add the bias
+        const size_t slice = (size_t)gridDim.y * m * 3;
+#pragma unroll
+        for (int d = 0; d < 3; ++d) {
+            float s = c[d];
+            for (int k = 1; k < ksplit; ++k) s += c[k * slice + d];
+            cs[d] = s + (bias ? bias[i * 3 + d] : 0.f);
+        }
+        c = cs;
+    }
     const float ct = cosf(f.theta), st = sinf(f.theta);
     float v0, v1, v2;
     if (viewer_centred) {
@@ -525,34 +577,44 @@ extern "C" int seevcn_vcn_forward(const seevcn_vcn_model* M, int num_obj, int n,
 
     if (precision == 0) {
         // ---- fused tcgen05 chains (vcn_chain.cu): one launch per chain, activations stay in TMEM ----
+        VcnMaxInit init;
+        init.dst[0] = g256; init.width[0] = 256;
+        init.dst[1] = feat; init.width[1] = 1024;
+        int ks = 0;
         if (M->viewer_centred) {
-            vcn_frame_kernel<<<num_obj, 256, 0, st>>>(n, 1, input, nullptr, frames, nullptr);
+            init.dst[2] = pose_feat; init.width[2] = 1024;
+            vcn_frame_kernel<<<num_obj, 256, 0, st>>>(n, 1, input, nullptr, frames, nullptr, init);
             SEEVCN_LAUNCH_CHECK();
-            TRY(fill(pose_feat, (size_t)num_obj * 1024, NEG_INF, st));
             TRY(vcn_chain_pose(M, num_obj, n, input, frames, pose_feat, st));
             TRY(to_bf16(pose_feat, num_obj, 1024, fcxA));
-            TRY(vcn_fc_tc(M->pose_fc0, num_obj, fcxA, 1024, ACT_LEAKY, h512, nullptr, 0, fc_part, st));
-            TRY(linear_f32(M->pose_fc2, num_obj, h512, 512, nullptr, 1, ACT_NONE, rel, 16, nullptr, st));
-            vcn_pose_kernel<<<div_up(num_obj, 128), 128, 0, st>>>(num_obj, rel, 16, frames, poses, reg_rot, reg_centre);
+            SEEVCN_REQUIRE(M->pose_fc0.cout == kPoseHidden && M->pose_fc2.cout == 9, "vcn_forward: unexpected pose_fc shape");
+            TRY(vcn_fc_tc_partials(M->pose_fc0, num_obj, fcxA, 1024, fc_part, &ks, st));
+            vcn_pose_tail_kernel<<<num_obj, 288, 0, st>>>(num_obj, ks, fc_part, M->pose_fc0.b, M->pose_fc2.w, M->pose_fc2.b,
+                                                          frames, poses, reg_rot, reg_centre);
             SEEVCN_LAUNCH_CHECK();
         } else {
-            vcn_frame_kernel<<<num_obj, 256, 0, st>>>(n, 0, input, gt_boxes, frames, nullptr);
+            vcn_frame_kernel<<<num_obj, 256, 0, st>>>(n, 0, input, gt_boxes, frames, nullptr, init);
             SEEVCN_LAUNCH_CHECK();
         }
-        TRY(fill(g256, (size_t)num_obj * 256, NEG_INF, st));
-        TRY(fill(feat, (size_t)num_obj * 1024, NEG_INF, st));
         for (int o0 = 0; o0 < num_obj; o0 += w.chunk) {
             const int nb = std::min(w.chunk, num_obj - o0);
             TRY(vcn_chain_enc1(M, nb, n, input + (size_t)o0 * n * 3, frames + o0, poses + o0, actA16, g256 + (size_t)o0 * 256, st));
             TRY(to_bf16(g256 + (size_t)o0 * 256, nb, 256, fcxA));
-            TRY(vcn_fc_tc(M->enc2_0_global, nb, fcxA, 256, ACT_NONE, objbias + (size_t)o0 * 512, nullptr, 0, fc_part, st));
-            TRY(vcn_chain_enc2(M, nb, n, actA16, objbias + (size_t)o0 * 512, feat + (size_t)o0 * 1024, st));
+            // per-object bias of mlp_conv2.0 = W[:, :256] . global + b: the chain sums the split-K slices itself
+            TRY(vcn_fc_tc_partials(M->enc2_0_global, nb, fcxA, 256, fc_part, &ks, st));
+            TRY(vcn_chain_enc2(M, nb, n, actA16, fc_part, ks, feat + (size_t)o0 * 1024, st));
         }
         TRY(to_bf16(feat, num_obj, 1024, fcxA));
         TRY(vcn_fc_tc(M->fc0, num_obj, fcxA, 1024, ACT_RELU, nullptr, fcxB, 1024, fc_part, st));
         TRY(vcn_fc_tc(M->fc2, num_obj, fcxB, 1024, ACT_RELU, nullptr, fcxA, 1024, fc_part, st));
-        if ((3 * M->num_coarse) % 128 == 0) TRY(vcn_fc_tc(M->fc4, num_obj, fcxA, 1024, ACT_NONE, coarse_cn, nullptr, 0, fc_part, st));
-        else TRY(linear_f32_from_bf16(M->fc4, num_obj, fcxA, coarse_cn));
+        if ((3 * M->num_coarse) % 128 == 0) {
+            TRY(vcn_fc_tc_partials(M->fc4, num_obj, fcxA, 1024, fc_part, &ks, st));
+            vcn_output_kernel<<<dim3(div_up(M->num_coarse, 256), num_obj), 256, 0, st>>>(M->num_coarse, M->viewer_centred,
+                                                                                         fc_part, frames, poses, coarse, ks, M->fc4.b);
+            SEEVCN_LAUNCH_CHECK();
+            return SEEVCN_OK;
+        }
+        TRY(linear_f32_from_bf16(M->fc4, num_obj, fcxA, coarse_cn));
         vcn_output_kernel<<<dim3(div_up(M->num_coarse, 256), num_obj), 256, 0, st>>>(M->num_coarse, M->viewer_centred,
                                                                                      coarse_cn, frames, poses, coarse);
         SEEVCN_LAUNCH_CHECK();

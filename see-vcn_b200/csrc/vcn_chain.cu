@@ -80,7 +80,8 @@ struct ChainArgs {
     const VcnPose* poses;
     int xform;
     const float* w0; const float* b0; int act0;     // producer layer (K0, 3), (K0)
-    const float* b1; const float* obj_bias; int act1;   // first GEMM: bias (C1), per-object bias (num_obj, C1)
+    const float* b1; const float* obj_bias; int act1;   // first GEMM: bias (C1), per-object bias (num_obj, C1) ...
+    int obj_bias_splits;           // ... given as this many split-K slices (num_obj, C1) that are summed in index order
     const float* b2;               // last GEMM bias (C2)
     __nv_bfloat16* F; int ldf;     // STORE: last GEMM output, bf16 (rows, ldf)
     float* colmax;                 // (num_obj, C2), pre-filled with -inf
@@ -375,8 +376,14 @@ vcn_chain_kernel(const __grid_constant__ CUtensorMap tmap_w1, const __grid_const
             const size_t row = (size_t)obj * a.n + p0 + pt;            // global point row (valid lanes)
 
             if (C::HAS_L1) {   // bias of the first GEMM for this object: b1 + per-object bias
-                for (int c = ptid; c < C::C1; c += NUM_POINT_THREADS)
-                    s_bias1[c] = (a.b1 ? a.b1[c] : 0.f) + (a.obj_bias ? a.obj_bias[(size_t)obj * C::C1 + c] : 0.f);
+                for (int c = ptid; c < C::C1; c += NUM_POINT_THREADS) {
+                    float ob = 0.f;
+                    if (a.obj_bias) {
+                        ob = a.obj_bias[(size_t)obj * C::C1 + c];
+                        for (int k = 1; k < a.obj_bias_splits; ++k) ob += a.obj_bias[((size_t)k * a.num_obj + obj) * C::C1 + c];
+                    }
+                    s_bias1[c] = ob + (a.b1 ? a.b1[c] : 0.f);
+                }
             }
 
             if (C::PRODUCER && tile + 1 < t_end) produce(tile + 1, ti + 1);   // one tile ahead of the epilogues
@@ -557,9 +564,11 @@ int vcn_chain_enc1(const seevcn_vcn_model* M, int num_obj, int n, const float* i
     return launch_chain<CHAIN_ENC1>(tw2, tw2, tw2, a, st);
 }
 
-// enc2 chain: f (rows, 256) bf16 -> mlp_conv2.0 (local half, + per-object bias) -> mlp_conv2.3, max -> feat (num_obj, 1024)
-int vcn_chain_enc2(const seevcn_vcn_model* M, int num_obj, int n, const __nv_bfloat16* F, const float* obj_bias,
-                   float* feat, cudaStream_t st) {
+// enc2 chain: f (rows, 256) bf16 -> mlp_conv2.0 (local half, + per-object bias) -> mlp_conv2.3, max -> feat (num_obj, 1024).
+// The per-object bias (global half of mlp_conv2.0 times the global feature) arrives as `obj_bias_splits` split-K slices
+// (num_obj, 512) without the layer's own bias; the chain sums them in index order and adds the bias.
+int vcn_chain_enc2(const seevcn_vcn_model* M, int num_obj, int n, const __nv_bfloat16* F, const float* obj_bias_part,
+                   int obj_bias_splits, float* feat, cudaStream_t st) {
     if (num_obj == 0) return SEEVCN_OK;
     CUtensorMap tw1, tw2, tx;
     int rc = make_tmap(&tw1, M->enc2_0_local.w16, 512, 256, 256);
@@ -572,7 +581,7 @@ int vcn_chain_enc2(const seevcn_vcn_model* M, int num_obj, int n, const __nv_bfl
     a.num_obj = num_obj; a.n = n; a.tiles_per_obj = div_up(n, TM); a.num_tiles = num_obj * a.tiles_per_obj;
     a.input = nullptr; a.frames = nullptr; a.poses = nullptr; a.xform = 0;
     a.w0 = nullptr; a.b0 = nullptr; a.act0 = ACT_NONE;
-    a.b1 = nullptr /* folded into obj_bias by the caller */; a.obj_bias = obj_bias; a.act1 = ACT_RELU;
+    a.b1 = M->enc2_0_global.b; a.obj_bias = obj_bias_part; a.obj_bias_splits = obj_bias_splits; a.act1 = ACT_RELU;
     a.b2 = M->enc2_3.b; a.F = nullptr; a.ldf = 0; a.colmax = feat;
     return launch_chain<CHAIN_ENC2>(tw1, tw2, tx, a, st);
 }

@@ -372,8 +372,9 @@ size_t vcn_fc_part_bytes(int rows, int cout, int cin) {
 }
 
 // X bf16 (rows, ldx >= kpad, zero padded).  part: >= vcn_fc_part_bytes(rows, cout, cin).  cout % 128 == 0.
-int vcn_fc_tc(const LinearW& L, int rows, const __nv_bfloat16* X, int ldx, int act, float* Yf32, __nv_bfloat16* Yb16, int ldb,
-              float* part, cudaStream_t st) {
+// Leaves the *ksplit split-K slices (slice k at part + k * rows * cout, no bias, no activation) for the consumer to sum.
+int vcn_fc_tc_partials(const LinearW& L, int rows, const __nv_bfloat16* X, int ldx, float* part, int* ksplit, cudaStream_t st) {
+    *ksplit = 0;
     if (rows == 0) return SEEVCN_OK;
     SEEVCN_REQUIRE(L.kpad % BK == 0 && ldx >= L.kpad && L.cout % 4 == 0, "vcn_fc_tc: bad layer shape");
     // per device and cheap: set on every launch (a process-wide "done" flag would skip the second GPU of a process)
@@ -393,8 +394,18 @@ int vcn_fc_tc(const LinearW& L, int rows, const __nv_bfloat16* X, int ldx, int a
     const int grid = a.num_tiles < seevcn_num_sms() ? a.num_tiles : seevcn_num_sms();
     vcn_linear_tc_kernel<<<grid, NUM_THREADS, SMEM_BYTES, st>>>(tw, tx, a);
     SEEVCN_LAUNCH_CHECK();
+    *ksplit = a.ksplit;
+    return SEEVCN_OK;
+}
+
+int vcn_fc_tc(const LinearW& L, int rows, const __nv_bfloat16* X, int ldx, int act, float* Yf32, __nv_bfloat16* Yb16, int ldb,
+              float* part, cudaStream_t st) {
+    if (rows == 0) return SEEVCN_OK;
+    int ksplit = 0;
+    const int rc = vcn_fc_tc_partials(L, rows, X, ldx, part, &ksplit, st);
+    if (rc != SEEVCN_OK) return rc;
     const int total = rows * (L.cout / 4);
-    fc_reduce_kernel<<<div_up(total, 256), 256, 0, st>>>(rows, L.cout, a.ksplit, part, L.b, act, Yf32, Yb16, ldb);
+    fc_reduce_kernel<<<div_up(total, 256), 256, 0, st>>>(rows, L.cout, ksplit, part, L.b, act, Yf32, Yb16, ldb);
     SEEVCN_LAUNCH_CHECK();
     return SEEVCN_OK;
 }

@@ -328,12 +328,18 @@ class HostStream:
 
         hs = HostStream(pipe, frames, pts_per_frame, boxes_per_frame)
         for res in hs.run(batches):      # batches: iterable of (points_pinned (F,P,3), boxes_pinned (F,T,7))
-            res["clustered"], res["voxel_coords"], ...   # pinned host views, valid for the next `depth - 4` batches (copy them if they must live longer)
+            res["clustered"], res["voxel_coords"], ...   # pinned host views, valid for the next batch (copy them if they must live longer)
     """
     KEYS = ("clustered", "voxel_coords", "voxel_features", "voxel_num_points")
 
-    def __init__(self, pipe, frames, pts_per_frame, boxes_per_frame, depth=5):
-        assert depth >= 5   # uploads run 3 batches ahead: a slot is reused only after its batch was finalized (finalize may re-voxelize from it)
+    def __init__(self, pipe, frames, pts_per_frame, boxes_per_frame, depth=None, lag=None):
+        # lag: how many batches stay issued-but-not-finalized behind the one being issued (one per compute stream keeps
+        # every stream a full batch ahead of the host).  Uploads run 3 batches ahead and a slot is reused only after its
+        # batch was finalized (finalize may re-voxelize from it): depth >= lag + 4.
+        # Measured (C2, B200): 2 streams -> lag 1 (287 k vs 265 k objects/s), 3 or more -> one per stream (4 streams: 324 k).
+        self.lag = (pipe.streams if pipe.streams >= 3 else 1) if lag is None else max(1, int(lag))
+        depth = self.lag + 4 if depth is None else depth
+        assert depth >= self.lag + 4
         self.pipe, self.depth = pipe, depth
         dev = pipe.device
         self.dev = dev
@@ -417,11 +423,12 @@ class HostStream:
         if state["up"] == 0:
             return
         h, i = crop(0), 0
-        # prev: stage B queued, M not read yet; fin: finalized (M known), download not issued yet; pending: D2H issued
+        # unfin: stage B queued, M not read yet (`lag` batches); fin: finalized (M known), download not issued yet; pending: D2H issued
         # (up to two in flight, so a slow transfer does not stop the launches).
         # The bulk download of a batch is issued one iteration AFTER its finalize: issued right away it would sit on the
         # D2H copy engine in front of the few bytes of box counts the next stage B launch is waiting for.
-        prev = fin = None
+        fin = None
+        unfin = []
         pending = []
         while h is not None:
             upload_next()                                            # batch i+3: overlaps the kernels below
@@ -432,10 +439,12 @@ class HostStream:
                 fin = None
                 if len(pending) > 2:
                     yield self._collect(pending.pop(0))
-            if prev is not None:
-                fin = (prev[0], self.pipe.finalize(prev[1]))
-            prev, h, i = (i, out), h_next, i + 1
-        for item in (fin, (prev[0], self.pipe.finalize(prev[1]))):
+            unfin.append((i, out))
+            if len(unfin) > self.lag:
+                j, o = unfin.pop(0)
+                fin = (j, self.pipe.finalize(o))
+            h, i = h_next, i + 1
+        for item in [fin] + [(j, self.pipe.finalize(o)) for j, o in unfin]:
             if item is not None:
                 pending.append((item[0] % D, self._download(item[0] % D, item[1])))
         for p in pending:
