@@ -20,6 +20,14 @@
 // shuffles per 32x32 block), then shared-memory atomics across the 4 lane quadrants and the tiles of one
 // object that a CTA owns (tiles are dealt out in contiguous runs), then one global atomic per channel.
 //
+// The pose chain differs (its last layer has K = 128: 8 MMAs per chunk cannot hide that epilogue).  Its
+// activations go through SHARED memory instead (written by the producer / the first GEMM's epilogue in the
+// SWIZZLE_128B K-major layout) and its last GEMM runs CHANNELS x POINTS: the weight chunk is the A operand,
+// the activations the B operand, a thread owns one output channel and the max over the tile's points is a
+// per-thread max over accumulator columns.  Tensor memory then holds FOUR accumulators (each issuer alternates
+// between two) and the first GEMM of tile t+1 is issued in the middle of tile t's last GEMM.
+// Pose chain, 308 objects x 1024 points: 123 us in the points x channels form -> 75 us.
+//
 // Warp roles (640 threads, one CTA per SM, persistent):
 //   warp 0      TMA producer (weight k-blocks; enc2: also the 128 x 256 input tile)
 //   warps 1, 3  MMA issuers (one elected thread each).  A single thread sustains one tcgen05.mma per ~94-120
@@ -27,7 +35,7 @@
 //               (tools/microbench/mma_rate.cu: 2230 MAC/clk/SM with one issuer, 3710 with two), so the two
 //               accumulators are driven by two issuers: warp 1 owns accumulator 0 (even chunks), warp 3
 //               accumulator 1 (odd chunks); the weight ring interleaves the k-blocks of the two chunks in flight
-//   warp 2      TMEM allocator (512 columns: 2 accumulators x 128 | activations up to 256 | input 32)
+//   warp 2      TMEM allocator (512 columns: 2 accumulators x 128 | activations up to 256 | input 32; pose: 4 accumulators)
 //   warps 4-19  point warps: lane quadrant q = warp % 4, column quarter cq = (warp - 4) / 4 (32 of the 128
 //               accumulator columns): 4 warps per scheduler keep the latency-bound producer / epilogue code busy
 #include <cuda.h>
@@ -60,16 +68,16 @@ enum { XF_VIEW = 0, XF_CANON = 1, XF_GT = 2 };   // producer transform of the ra
 
 template <int MODE> struct Cfg;
 template <> struct Cfg<CHAIN_POSE> {
-    static constexpr int K0 = 64, C1 = 128, C2 = 1024, KH = 128, STAGES = 8;
-    static constexpr bool PRODUCER = true, HAS_L1 = true, X_SMEM = false, STORE = false;
+    static constexpr int K0 = 64, C1 = 128, C2 = 1024, KH = 128, STAGES = 6, NUM_ACC = 4;
+    static constexpr bool PRODUCER = true, HAS_L1 = true, X_SMEM = false, STORE = false, H_SMEM = true;
 };
 template <> struct Cfg<CHAIN_ENC1> {
-    static constexpr int K0 = 128, C1 = 0, C2 = 256, KH = 128, STAGES = 8;
-    static constexpr bool PRODUCER = true, HAS_L1 = false, X_SMEM = false, STORE = true;
+    static constexpr int K0 = 128, C1 = 0, C2 = 256, KH = 128, STAGES = 8, NUM_ACC = 2;
+    static constexpr bool PRODUCER = true, HAS_L1 = false, X_SMEM = false, STORE = true, H_SMEM = false;
 };
 template <> struct Cfg<CHAIN_ENC2> {
-    static constexpr int K0 = 256, C1 = 512, C2 = 1024, KH = 512, STAGES = 8;
-    static constexpr bool PRODUCER = false, HAS_L1 = true, X_SMEM = true, STORE = false;
+    static constexpr int K0 = 256, C1 = 512, C2 = 1024, KH = 512, STAGES = 8, NUM_ACC = 2;
+    static constexpr bool PRODUCER = false, HAS_L1 = true, X_SMEM = true, STORE = false, H_SMEM = false;
 };
 
 struct ChainArgs {
@@ -92,7 +100,7 @@ struct ChainArgs {
 template <int MODE>
 constexpr int chain_smem_bytes() {
     using C = Cfg<MODE>;
-    return 1024 /*align*/ + (C::X_SMEM ? TM * C::K0 * 2 : 0) + C::STAGES * W_STAGE_BYTES + C::C2 * 4 /*tilemax*/ +
+    return 1024 /*align*/ + (C::X_SMEM ? TM * C::K0 * 2 : 0) + (C::H_SMEM ? 2 * TM * C::KH * 2 + 2 * TM * C::K0 * 2 : 0) + C::STAGES * W_STAGE_BYTES + C::C2 * 4 /*tilemax*/ +
            C::C2 * 4 /*bias2*/ + (C::HAS_L1 ? C::C1 * 4 : 0) /*bias1*/ + (C::PRODUCER ? C::K0 * 16 : 0) /*w0*/ + 768 /*barriers*/;
 }
 
@@ -148,13 +156,33 @@ vcn_chain_kernel(const __grid_constant__ CUtensorMap tmap_w1, const __grid_const
     constexpr uint32_t HA_COL = H_COL + C::KH / 2;     // producer output when a first GEMM follows (pose chain), 2 buffers
     // The point warps run the producer one tile AHEAD of the epilogues (software pipeline), so its target is
     // double buffered: pose -> two input buffers at HA_COL, enc1 -> two activation buffers at H_COL.
-    constexpr bool HA_DOUBLE = C::PRODUCER && C::HAS_L1, H_DOUBLE = C::PRODUCER && !C::HAS_L1;
+    // H_SMEM (pose chain): the last GEMM runs CHANNELS x POINTS — the weight chunk is the A operand and the activations,
+    // written by the first GEMM's epilogue into shared memory ([k-block][128 points][64] bf16, SWIZZLE_128B, two buffers),
+    // are the B operand.  A thread then owns one output channel, so the max over the tile's points is a per-thread
+    // max over accumulator columns: no transposing shuffle network in the epilogue of a K = 128 layer that could not hide it.
+    constexpr bool HA_DOUBLE = C::PRODUCER && C::HAS_L1, H_DOUBLE = (C::PRODUCER && !C::HAS_L1) || C::H_SMEM;
+    constexpr int H_BUF_BYTES = TM * C::KH * 2;
+    // ... and so does the producer's output (the A operand of the first GEMM, one 128-byte row per point), which leaves all
+    // 512 tensor-memory columns to FOUR accumulators: each MMA issuer alternates between two, so it issues its next chunk
+    // while the previous one is still being drained (a K = 128 chunk is 8 MMAs; with two accumulators the issuers spent
+    // 35 % of their cycles waiting for one to come back).
+    constexpr int NUM_ACC = C::NUM_ACC;
+    constexpr int HA_BUF_BYTES = TM * C::K0 * 2;
+    static_assert(!C::H_SMEM || C::K0 == BK, "H_SMEM: the producer output is one 128-byte swizzle row per point");
+    // EARLY_L1 (pose chain): the first GEMM of tile t+1 is issued in the MIDDLE of tile t's last GEMM (after SPLIT of its
+    // chunks) and its epilogue runs between the max epilogues of tile t, so that tile t+1's activations are in shared
+    // memory when tile t's MMAs end — otherwise the tensor pipe idles through the tail of the max epilogues plus the
+    // first GEMM and its epilogue (measured: 36 % of the issuer's cycles waiting on h_full).
+    constexpr bool EARLY_L1 = C::H_SMEM;
+    constexpr int SPLIT = 4;
 
     extern __shared__ uint8_t smem_raw[];
     // 1024-byte alignment (SWIZZLE_128B) by OFFSET, so the compiler still knows these pointers are shared memory
     uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     uint8_t* smem_x = smem;                                                    // [KB1][128 rows][64] bf16 (enc2)
-    uint8_t* smem_w = smem + (C::X_SMEM ? TM * C::K0 * 2 : 0);                 // ring
+    uint8_t* smem_h = smem + (C::X_SMEM ? TM * C::K0 * 2 : 0);                 // [2][KB2][128 rows][64] bf16 (H_SMEM)
+    uint8_t* smem_ha = smem_h + (C::H_SMEM ? 2 * H_BUF_BYTES : 0);             // [2][128 rows][64] bf16 (H_SMEM)
+    uint8_t* smem_w = smem_ha + (C::H_SMEM ? 2 * HA_BUF_BYTES : 0);            // ring
     uint32_t* tilemax = reinterpret_cast<uint32_t*>(smem_w + STAGES * W_STAGE_BYTES);
     float* s_bias2 = reinterpret_cast<float*>(tilemax + C::C2);
     float* s_bias1 = s_bias2 + C::C2;
@@ -162,9 +190,9 @@ vcn_chain_kernel(const __grid_constant__ CUtensorMap tmap_w1, const __grid_const
     uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(s_w0) + (C::PRODUCER ? C::K0 * 16 : 0));
     uint64_t* w_full = bars;                    // [STAGES]
     uint64_t* w_empty = bars + STAGES;          // [STAGES]
-    uint64_t* acc_full = bars + 2 * STAGES;     // [2]
-    uint64_t* acc_empty = acc_full + 2;         // [2]
-    uint64_t* x_full = acc_empty + 2;           // input tile landed in smem (enc2)
+    uint64_t* acc_full = bars + 2 * STAGES;     // [NUM_ACC <= 4]
+    uint64_t* acc_empty = acc_full + 4;         // [NUM_ACC <= 4]
+    uint64_t* x_full = acc_empty + 4;           // input tile landed in smem (enc2)
     uint64_t* x_empty = x_full + 1;             // first GEMM finished reading it
     uint64_t* ha_full = x_empty + 1;            // [2] producer output in TMEM (pose), double buffered
     uint64_t* ha_free = ha_full + 2;            // [2]
@@ -184,7 +212,7 @@ vcn_chain_kernel(const __grid_constant__ CUtensorMap tmap_w1, const __grid_const
     }
     if (warp == 1 && lane == 0) {
         for (int s = 0; s < STAGES; ++s) { mbar_init(&w_full[s], 1); mbar_init(&w_empty[s], 1); }
-        for (int s = 0; s < 2; ++s) { mbar_init(&acc_full[s], 1); mbar_init(&acc_empty[s], NUM_POINT_WARPS); }
+        for (int s = 0; s < NUM_ACC; ++s) { mbar_init(&acc_full[s], 1); mbar_init(&acc_empty[s], NUM_POINT_WARPS); }
         mbar_init(x_full, 1); mbar_init(x_empty, 2);      // "free" barriers: one commit per MMA issuer
         for (int s = 0; s < 2; ++s) {
             mbar_init(&ha_full[s], NUM_POINT_WARPS); mbar_init(&ha_free[s], 2);
@@ -213,9 +241,9 @@ vcn_chain_kernel(const __grid_constant__ CUtensorMap tmap_w1, const __grid_const
         if (lane == 0) {
             uint32_t pos = 0;     // ring position; stage = pos % STAGES, phase = (pos / STAGES) & 1
             int ti = 0;
-            auto produce = [&](const CUtensorMap* tm, int n_chunks, int kbs) {
-                for (int g = 0; g < n_chunks; g += 2) {
-                    const int members = min(2, n_chunks - g);
+            auto produce = [&](const CUtensorMap* tm, int c_begin, int c_end, int kbs) {
+                for (int g = c_begin; g < c_end; g += 2) {
+                    const int members = min(2, c_end - g);
                     for (int kb = 0; kb < kbs; ++kb)
                         for (int m = 0; m < members; ++m, ++pos) {
                             const uint32_t stage = pos % STAGES, phase = (pos / STAGES) & 1;
@@ -226,6 +254,7 @@ vcn_chain_kernel(const __grid_constant__ CUtensorMap tmap_w1, const __grid_const
                         }
                 }
             };
+            if (EARLY_L1 && t_begin < t_end) produce(&tmap_w1, 0, N1, KB1);
             for (int tile = t_begin; tile < t_end; ++tile, ++ti) {
                 if (C::X_SMEM) {
                     const int obj = tile / a.tiles_per_obj;
@@ -235,31 +264,42 @@ vcn_chain_kernel(const __grid_constant__ CUtensorMap tmap_w1, const __grid_const
 #pragma unroll
                     for (int kb = 0; kb < KB1; ++kb) tma_load_2d(smem_x + kb * (TM * BK * 2), &tmap_x, kb * BK, row0, x_full);
                 }
-                if (C::HAS_L1) produce(&tmap_w1, N1, KB1);
-                produce(&tmap_w2, N2, KB2);
+                if (EARLY_L1) {
+                    produce(&tmap_w2, 0, SPLIT, KB2);
+                    if (tile + 1 < t_end) produce(&tmap_w1, 0, N1, KB1);
+                    produce(&tmap_w2, SPLIT, N2, KB2);
+                } else {
+                    if (C::HAS_L1) produce(&tmap_w1, 0, N1, KB1);
+                    produce(&tmap_w2, 0, N2, KB2);
+                }
             }
         }
     } else if (warp == 1 || warp == 3) {
         // =================================================================== MMA issuers ==
         {   // the whole warp runs the loop (uniform control flow); one elected lane issues
-            const uint32_t me = warp == 1 ? 0u : 1u;        // accumulator owned by this issuer
-            const uint32_t d_tmem = tmem_base + ACC_COL + me * TN;
+            const uint32_t me = warp == 1 ? 0u : 1u;        // this issuer takes the chunks with running index = me (mod 2)
             const uint64_t desc_w0 = make_desc(smem_u32(smem_w));
             const uint64_t desc_x0 = make_desc(smem_u32(smem_x));
+            const uint64_t desc_h0 = make_desc(smem_u32(smem_h));
+            const uint64_t desc_ha0 = make_desc(smem_u32(smem_ha));
             uint32_t pos = 0, ai = 0;                        // same sequences as the producer / the point warps
             int ti = 0;
             long long c_tot = 0, c_a = 0, c_acc = 0, c_w = 0, c_h = 0, t_;
             const bool prof = (a.dbg & 4) != 0;
 #define PROF_WAIT(ctr, stmt) do { if (prof) { t_ = clock64(); stmt; ctr += clock64() - t_; } else { stmt; } } while (0)
             if (prof) c_tot = -clock64();
-            // one phase (= one GEMM of the chain) of the current tile; a_tmem < 0 selects the smem A operand
-            auto issue = [&](int n_chunks, int kbs, bool a_from_smem, uint32_t a_tmem) {
+            // one phase (= one GEMM of the chain) of the current tile.  a_mode 0: A from tensor memory at a_src, weights B;
+            // 1: A = the input tile in shared memory, weights B; 2: A = weights, B = activation buffer a_src in shared memory;
+            // 3: A = producer-output buffer a_src in shared memory (one k-block), weights B
+            auto issue = [&](int n_chunks, int kbs, int a_mode, uint32_t a_src) {
                 for (int g = 0; g < n_chunks; g += 2) {
                     const int members = min(2, n_chunks - g);
-                    const int mine = (int)((me - ai) & 1u);          // member index of the chunk on my accumulator
+                    const int mine = (int)((me - ai) & 1u);          // member index of my chunk in this group
                     if (mine < members) {
-                        const uint32_t use = (ai + mine) >> 1;        // how often my accumulator has been used
-                        PROF_WAIT(c_acc, mbar_wait(&acc_empty[me], (use & 1) ^ 1));
+                        const uint32_t chunk = ai + mine;             // running chunk index: accumulator chunk % NUM_ACC
+                        const uint32_t accn = chunk % NUM_ACC, use = chunk / NUM_ACC;
+                        const uint32_t d_tmem = tmem_base + ACC_COL + accn * TN;
+                        PROF_WAIT(c_acc, mbar_wait(&acc_empty[accn], (use & 1) ^ 1));
                         tc_fence_after();
                         for (int kb = 0; kb < kbs; ++kb) {
                             const uint32_t p = pos + kb * members + mine;
@@ -268,19 +308,29 @@ vcn_chain_kernel(const __grid_constant__ CUtensorMap tmap_w1, const __grid_const
                             tc_fence_after();
                             const uint64_t db = desc_w0 + (uint64_t)((stage * W_STAGE_BYTES) >> 4);
                             if (elect_one()) {
-                                if (a_from_smem) {
+                                if (a_mode == 1) {
                                     const uint64_t da = desc_x0 + (uint64_t)((kb * (TM * BK * 2)) >> 4);
 #pragma unroll
                                     for (int k = 0; k < BK / UMMA_K; ++k)
                                         tc_mma(d_tmem, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), kIdesc, (kb | k) != 0);
+                                } else if (a_mode == 3) {
+                                    const uint64_t da = desc_ha0 + (uint64_t)((a_src * HA_BUF_BYTES) >> 4);
+#pragma unroll
+                                    for (int k = 0; k < BK / UMMA_K; ++k)
+                                        tc_mma(d_tmem, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), kIdesc, (kb | k) != 0);
+                                } else if (a_mode == 2) {
+                                    const uint64_t dh = desc_h0 + (uint64_t)((a_src * H_BUF_BYTES + kb * (TM * BK * 2)) >> 4);
+#pragma unroll
+                                    for (int k = 0; k < BK / UMMA_K; ++k)
+                                        tc_mma(d_tmem, db + (uint64_t)(k * 2), dh + (uint64_t)(k * 2), kIdesc, (kb | k) != 0);
                                 } else {
-                                    const uint32_t ta = a_tmem + kb * (BK / 2);
+                                    const uint32_t ta = a_src + kb * (BK / 2);
 #pragma unroll
                                     for (int k = 0; k < BK / UMMA_K; ++k)
                                         tc_mma_ts(d_tmem, ta + k * (UMMA_K / 2), db + (uint64_t)(k * 2), kIdesc, (kb | k) != 0);
                                 }
                                 tc_commit(&w_empty[stage]);
-                                if (kb == kbs - 1) tc_commit(&acc_full[me]);
+                                if (kb == kbs - 1) tc_commit(&acc_full[accn]);
                             }
                             __syncwarp();
                         }
@@ -289,20 +339,31 @@ vcn_chain_kernel(const __grid_constant__ CUtensorMap tmap_w1, const __grid_const
                     ai += members;
                 }
             };
+            // first GEMM of the tile with running index tix
+            auto first_gemm = [&](int tix) {
+                const uint32_t ab = HA_DOUBLE ? (tix & 1) : 0u, apar = HA_DOUBLE ? ((tix >> 1) & 1) : (tix & 1);
+                if (C::X_SMEM) PROF_WAIT(c_a, mbar_wait(x_full, tix & 1)); else PROF_WAIT(c_a, mbar_wait(&ha_full[ab], apar));
+                tc_fence_after();
+                if (C::H_SMEM) issue(N1, KB1, 3, ab); else issue(N1, KB1, C::X_SMEM ? 1 : 0, tmem_base + HA_COL + ab * (C::K0 / 2));
+                if (elect_one()) { if (C::X_SMEM) tc_commit(x_empty); else tc_commit(&ha_free[ab]); }   // my MMAs of this GEMM are done reading A
+                __syncwarp();
+            };
+            if (EARLY_L1 && t_begin < t_end) first_gemm(0);
             for (int tile = t_begin; tile < t_end; ++tile, ++ti) {
                 const uint32_t tpar = ti & 1;
-                if (C::HAS_L1) {
-                    const uint32_t ab = HA_DOUBLE ? tpar : 0u, apar = HA_DOUBLE ? ((ti >> 1) & 1) : tpar;
-                    if (C::X_SMEM) PROF_WAIT(c_a, mbar_wait(x_full, tpar)); else PROF_WAIT(c_a, mbar_wait(&ha_full[ab], apar));
-                    tc_fence_after();
-                    issue(N1, KB1, C::X_SMEM, tmem_base + HA_COL + ab * (C::K0 / 2));
-                    if (elect_one()) { if (C::X_SMEM) tc_commit(x_empty); else tc_commit(&ha_free[ab]); }   // my MMAs of this GEMM are done reading A
-                    __syncwarp();
-                }
+                if (C::HAS_L1 && !EARLY_L1) first_gemm(ti);
                 const uint32_t hb = H_DOUBLE ? tpar : 0u, hpar = H_DOUBLE ? ((ti >> 1) & 1) : tpar;
                 PROF_WAIT(c_h, mbar_wait(&h_full[hb], hpar));
                 tc_fence_after();
-                issue(N2, KB2, false, tmem_base + H_COL + hb * (C::KH / 2));
+                if (EARLY_L1) {
+                    issue(SPLIT, KB2, 2, hb);
+                    if (tile + 1 < t_end) first_gemm(ti + 1);
+                    issue(N2 - SPLIT, KB2, 2, hb);
+                } else if (C::H_SMEM) {
+                    issue(N2, KB2, 2, hb);
+                } else {
+                    issue(N2, KB2, 0, tmem_base + H_COL + hb * (C::KH / 2));
+                }
                 if (elect_one()) tc_commit(&h_free[hb]);
                 __syncwarp();
             }
@@ -347,7 +408,6 @@ vcn_chain_kernel(const __grid_constant__ CUtensorMap tmap_w1, const __grid_const
                 if (C::HAS_L1) mbar_wait(&ha_free[pb], ppar ^ 1); else mbar_wait(&h_free[pb], ppar ^ 1);
                 tc_fence_after();
                 constexpr int CH = C::K0 / 4;                 // channels per thread (column quarter cq): 16 or 32
-                const uint32_t dst = lane_base + (C::HAS_L1 ? HA_COL : H_COL) + pb * (C::K0 / 2) + cq * (CH / 2);
                 uint32_t pk[CH / 2];
 #pragma unroll
                 for (int i = 0; i < CH / 2; ++i) {
@@ -356,107 +416,167 @@ vcn_chain_kernel(const __grid_constant__ CUtensorMap tmap_w1, const __grid_const
                     const float vb = act_apply(fmaf(wb.z, u2, fmaf(wb.y, u1, fmaf(wb.x, u0, wb.w))), slope0);
                     pk[i] = pack_bf16(va, vb);
                 }
-                if constexpr (CH == 16) tc_st8(dst, pk); else tc_st16(dst, pk);
-                tc_wait_st();
-                tc_fence_before();
+                if constexpr (C::H_SMEM) {
+                    // 16 channels = two 16-byte chunks of this point's 128-byte row
+                    uint8_t* rowp = smem_ha + pb * HA_BUF_BYTES + pt * 128;
+#pragma unroll
+                    for (int g = 0; g < 2; ++g)
+                        *reinterpret_cast<uint4*>(rowp + (((cq * 2 + g) ^ (pt & 7)) << 4)) =
+                            make_uint4(pk[4 * g], pk[4 * g + 1], pk[4 * g + 2], pk[4 * g + 3]);
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                } else {
+                    const uint32_t dst = lane_base + (C::HAS_L1 ? HA_COL : H_COL) + pb * (C::K0 / 2) + cq * (CH / 2);
+                    if constexpr (CH == 16) tc_st8(dst, pk); else tc_st16(dst, pk);
+                    tc_wait_st();
+                    tc_fence_before();
+                }
                 __syncwarp();
                 if (lane == 0) mbar_arrive(C::HAS_L1 ? &ha_full[pb] : &h_full[pb]);
             }
         };
 
-        if (C::PRODUCER && t_begin < t_end) produce(t_begin, 0);
         uint32_t ai = 0;
-        int ti = 0;
-        for (int tile = t_begin; tile < t_end; ++tile, ++ti) {
-            const uint32_t tpar = ti & 1;
-            const int obj = tile / a.tiles_per_obj;
-            const int p0 = (tile - obj * a.tiles_per_obj) * TM;       // first point of the tile inside the object
-            const int nvalid = min(TM, a.n - p0);
-            const bool valid = pt < nvalid;
-            const size_t row = (size_t)obj * a.n + p0 + pt;            // global point row (valid lanes)
-
-            if (C::HAS_L1) {   // bias of the first GEMM for this object: b1 + per-object bias
-                for (int c = ptid; c < C::C1; c += NUM_POINT_THREADS) {
-                    float ob = 0.f;
-                    if (a.obj_bias) {
-                        ob = a.obj_bias[(size_t)obj * C::C1 + c];
-                        for (int k = 1; k < a.obj_bias_splits; ++k) ob += a.obj_bias[((size_t)k * a.num_obj + obj) * C::C1 + c];
-                    }
-                    s_bias1[c] = ob + (a.b1 ? a.b1[c] : 0.f);
+        // bias of the first GEMM: b1 + the object's bias (split-K slices summed in index order)
+        auto load_bias1 = [&](int obj) {
+            for (int c = ptid; c < C::C1; c += NUM_POINT_THREADS) {
+                float ob = 0.f;
+                if (a.obj_bias) {
+                    ob = a.obj_bias[(size_t)obj * C::C1 + c];
+                    for (int k = 1; k < a.obj_bias_splits; ++k) ob += a.obj_bias[((size_t)k * a.num_obj + obj) * C::C1 + c];
                 }
+                s_bias1[c] = ob + (a.b1 ? a.b1[c] : 0.f);
             }
-
-            if (C::PRODUCER && tile + 1 < t_end) produce(tile + 1, ti + 1);   // one tile ahead of the epilogues
-
-            if (C::HAS_L1) {
-                named_bar_sync(1, NUM_POINT_THREADS);          // s_bias1 complete
-                // ---- first GEMM epilogue: bias + act -> bf16 -> TMEM (A operand of the last GEMM) ----
-                for (int j = 0; j < N1; ++j, ++ai) {
-                    const uint32_t acc = ai & 1;
-                    mbar_wait(&acc_full[acc], (ai >> 1) & 1);
-                    tc_fence_after();
-                    if (j == 0) { mbar_wait(&h_free[0], tpar ^ 1); tc_fence_after(); }
-                    uint32_t r0[32];
-                    tc_ld32(lane_base + ACC_COL + acc * TN + cq * 32, r0);
-                    // accumulator quarter drained into registers: hand it back before the stores
-                    tc_fence_before();
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(&acc_empty[acc]);
-                    const float* bj = s_bias1 + j * TN + cq * 32;
-                    uint32_t pk[16];
-#pragma unroll
-                    for (int i = 0; i < 16; ++i) {
-                        const float2 b = *reinterpret_cast<const float2*>(bj + 2 * i);
-                        pk[i] = pack_bf16(act_apply(__uint_as_float(r0[2 * i]) + b.x, slope1),
-                                          act_apply(__uint_as_float(r0[2 * i + 1]) + b.y, slope1));
-                    }
-                    tc_st16(lane_base + H_COL + j * (TN / 2) + cq * 16, pk);
-                }
-                tc_wait_st();
-                tc_fence_before();
-                __syncwarp();
-                if (lane == 0) mbar_arrive(&h_full[0]);
-            }
-
-            // ---- last GEMM epilogue: bias, optional bf16 store, max over the tile's points ----
-            for (int j = 0; j < N2; ++j, ++ai) {
-                const uint32_t acc = ai & 1;
-                mbar_wait(&acc_full[acc], (ai >> 1) & 1);
+        };
+        // ---- first GEMM epilogue of the tile with running index tix: bias + act -> bf16 -> A operand (TMEM) or
+        //      B operand (shared memory, H_SMEM) of the last GEMM ----
+        auto epilogue1 = [&](int tix) {
+            const uint32_t hb = H_DOUBLE ? (tix & 1) : 0u, hfpar = H_DOUBLE ? (((tix >> 1) & 1) ^ 1) : ((tix & 1) ^ 1);
+            for (int j = 0; j < N1; ++j, ++ai) {
+                const uint32_t acc = ai % NUM_ACC;
+                mbar_wait(&acc_full[acc], (ai / NUM_ACC) & 1);
                 tc_fence_after();
+                if (j == 0) { mbar_wait(&h_free[hb], hfpar); tc_fence_after(); }
                 uint32_t r0[32];
                 tc_ld32(lane_base + ACC_COL + acc * TN + cq * 32, r0);
+                // accumulator quarter drained into registers: hand it back before the stores
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&acc_empty[acc]);
-                if (a.dbg & 2) continue;
-                const int cbase = j * TN + cq * 32;
-                const float* bj = s_bias2 + cbase;
-                uint32_t pk[16];                      // 32 channels as bf16x2: register i = channels 2i, 2i+1
+                const float* bj = s_bias1 + j * TN + cq * 32;
+                uint32_t pk[16];
 #pragma unroll
                 for (int i = 0; i < 16; ++i) {
-                    if constexpr (C::STORE) {
-                        const float2 b = *reinterpret_cast<const float2*>(bj + 2 * i);
-                        pk[i] = pack_bf16(__uint_as_float(r0[2 * i]) + b.x, __uint_as_float(r0[2 * i + 1]) + b.y);
-                    } else {      // max-only chains: the bias commutes with the max and is added once per object at the flush
-                        pk[i] = pack_bf16(__uint_as_float(r0[2 * i]), __uint_as_float(r0[2 * i + 1]));
-                    }
+                    const float2 b = *reinterpret_cast<const float2*>(bj + 2 * i);
+                    pk[i] = pack_bf16(act_apply(__uint_as_float(r0[2 * i]) + b.x, slope1),
+                                      act_apply(__uint_as_float(r0[2 * i + 1]) + b.y, slope1));
                 }
-                if (C::STORE) {
-                    if (valid) {
-                        uint4* dst = reinterpret_cast<uint4*>(a.F + row * a.ldf + cbase);
+                if constexpr (C::H_SMEM) {
+                    // row = this thread's point, 32 channels = four 16-byte chunks of its 128-byte row in k-block ch0 / 64
+                    const int ch0 = j * TN + cq * 32;
+                    uint8_t* rowp = smem_h + hb * H_BUF_BYTES + (ch0 / BK) * (TM * BK * 2) + pt * 128;
+                    const int chunk0 = (ch0 % BK) / 8;
 #pragma unroll
-                        for (int g = 0; g < 4; ++g) dst[g] = make_uint4(pk[4 * g], pk[4 * g + 1], pk[4 * g + 2], pk[4 * g + 3]);
-                    }
+                    for (int g = 0; g < 4; ++g)
+                        *reinterpret_cast<uint4*>(rowp + (((chunk0 + g) ^ (pt & 7)) << 4)) =
+                            make_uint4(pk[4 * g], pk[4 * g + 1], pk[4 * g + 2], pk[4 * g + 3]);
+                } else {
+                    tc_st16(lane_base + H_COL + j * (TN / 2) + cq * 16, pk);
                 }
-                if (!valid) {
+            }
+            if constexpr (C::H_SMEM) {
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy stores -> the MMA's async-proxy reads
+            } else {
+                tc_wait_st();
+                tc_fence_before();
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&h_full[hb]);
+        };
+        // ---- last GEMM epilogue, chunk j: bias, optional bf16 store, max over the tile's points ----
+        auto epilogue2 = [&](int j, int nvalid, size_t row) {
+            const bool valid = pt < nvalid;
+            const uint32_t acc = ai % NUM_ACC;
+            mbar_wait(&acc_full[acc], (ai / NUM_ACC) & 1);
+            ++ai;
+            tc_fence_after();
+            uint32_t r0[32];
+            tc_ld32(lane_base + ACC_COL + acc * TN + cq * 32, r0);
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&acc_empty[acc]);
+            if (a.dbg & 2) return;
+            if constexpr (C::H_SMEM) {
+                // lane = channel j * 128 + q * 32 + lane, registers = 32 points of the tile
+                float m = -__builtin_huge_valf();
+                if (nvalid >= TM) {
 #pragma unroll
-                    for (int i = 0; i < 16; ++i) pk[i] = 0xff80ff80u;     // (-inf, -inf)
+                    for (int i = 0; i < 32; ++i) m = fmaxf(m, __uint_as_float(r0[i]));
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) if (cq * 32 + i < nvalid) m = fmaxf(m, __uint_as_float(r0[i]));
                 }
-                const uint32_t m2 = warp_transpose_max2(pk, lane);        // channels cbase + 2*(lane & 15), + 1
-                if (lane < 16) {
-                    atomicMax(&tilemax[cbase + 2 * lane], fkey(__uint_as_float(m2 << 16)));
-                    atomicMax(&tilemax[cbase + 2 * lane + 1], fkey(__uint_as_float(m2 & 0xffff0000u)));
+                // rounded to bf16 like every pooled feature (see warp_transpose_max2): max and rounding commute
+                atomicMax(&tilemax[j * TN + q * 32 + lane], fkey(__bfloat162float(__float2bfloat16_rn(m))));
+                return;
+            }
+            const int cbase = j * TN + cq * 32;
+            const float* bj = s_bias2 + cbase;
+            uint32_t pk[16];                      // 32 channels as bf16x2: register i = channels 2i, 2i+1
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+                if constexpr (C::STORE) {
+                    const float2 b = *reinterpret_cast<const float2*>(bj + 2 * i);
+                    pk[i] = pack_bf16(__uint_as_float(r0[2 * i]) + b.x, __uint_as_float(r0[2 * i + 1]) + b.y);
+                } else {      // max-only chains: the bias commutes with the max and is added once per object at the flush
+                    pk[i] = pack_bf16(__uint_as_float(r0[2 * i]), __uint_as_float(r0[2 * i + 1]));
                 }
+            }
+            if (C::STORE) {
+                if (valid) {
+                    uint4* dst = reinterpret_cast<uint4*>(a.F + row * a.ldf + cbase);
+#pragma unroll
+                    for (int g = 0; g < 4; ++g) dst[g] = make_uint4(pk[4 * g], pk[4 * g + 1], pk[4 * g + 2], pk[4 * g + 3]);
+                }
+            }
+            if (!valid) {
+#pragma unroll
+                for (int i = 0; i < 16; ++i) pk[i] = 0xff80ff80u;     // (-inf, -inf)
+            }
+            const uint32_t m2 = warp_transpose_max2(pk, lane);        // channels cbase + 2*(lane & 15), + 1
+            if (lane < 16) {
+                atomicMax(&tilemax[cbase + 2 * lane], fkey(__uint_as_float(m2 << 16)));
+                atomicMax(&tilemax[cbase + 2 * lane + 1], fkey(__uint_as_float(m2 & 0xffff0000u)));
+            }
+        };
+
+        if (C::PRODUCER && t_begin < t_end) produce(t_begin, 0);
+        if (EARLY_L1 && t_begin < t_end) {      // no per-object bias in this chain: staged once; first tile's first GEMM
+            load_bias1(0);
+            named_bar_sync(1, NUM_POINT_THREADS);
+            if (t_begin + 1 < t_end) produce(t_begin + 1, 1);
+            epilogue1(0);
+        }
+        int ti = 0;
+        for (int tile = t_begin; tile < t_end; ++tile, ++ti) {
+            const int obj = tile / a.tiles_per_obj;
+            const int p0 = (tile - obj * a.tiles_per_obj) * TM;       // first point of the tile inside the object
+            const int nvalid = min(TM, a.n - p0);
+            const size_t row = (size_t)obj * a.n + p0 + pt;            // global point row (valid lanes)
+
+            if (EARLY_L1) {
+                // the producer runs TWO tiles ahead here: tile + 1's first GEMM is issued in the middle of this tile
+                for (int j = 0; j < SPLIT; ++j) epilogue2(j, nvalid, row);
+                if (tile + 2 < t_end) produce(tile + 2, ti + 2);
+                if (tile + 1 < t_end) epilogue1(ti + 1);
+                for (int j = SPLIT; j < N2; ++j) epilogue2(j, nvalid, row);
+            } else {
+                if (C::HAS_L1) load_bias1(obj);
+                if (C::PRODUCER && tile + 1 < t_end) produce(tile + 1, ti + 1);   // one tile ahead of the epilogues
+                if (C::HAS_L1) {
+                    named_bar_sync(1, NUM_POINT_THREADS);          // s_bias1 complete
+                    epilogue1(ti);
+                }
+                for (int j = 0; j < N2; ++j) epilogue2(j, nvalid, row);
             }
 
             // ---- object finished on this CTA: publish the max ----
