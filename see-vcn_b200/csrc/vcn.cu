@@ -52,6 +52,8 @@ vcn_frame_kernel(int n, int viewer_centred, const float* __restrict__ input, con
     __shared__ float red[3][8];
     __shared__ VcnFrame fr;
     const int o = blockIdx.x;
+    pdl_launch_dependents();
+    pdl_wait();
     // -inf into this object's rows of the max-pool targets of the chains that follow (saves their fill launches)
 #pragma unroll
     for (int t = 0; t < 3; ++t)
@@ -168,6 +170,8 @@ vcn_pose_tail_kernel(int num_obj, int ksplit, const float* __restrict__ part, co
     __shared__ float h[kPoseHidden];
     __shared__ float rel[9];
     const int o = blockIdx.x;
+    pdl_launch_dependents();
+    pdl_wait();
     for (int c = threadIdx.x; c < kPoseHidden; c += 288) {
         float s = part[(size_t)o * kPoseHidden + c];
         for (int k = 1; k < ksplit; ++k) s += part[((size_t)k * num_obj + o) * kPoseHidden + c];
@@ -213,6 +217,8 @@ vcn_output_kernel(int m, int viewer_centred, const float* __restrict__ coarse_cn
                   const float* __restrict__ bias = nullptr) {
     const int o = blockIdx.y;
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    pdl_launch_dependents();
+    pdl_wait();
     if (i >= m) return;
     const VcnFrame f = frames[o];
     float cs[3];
@@ -256,6 +262,8 @@ __global__ void bf16_to_f32_kernel(size_t n, const __nv_bfloat16* __restrict__ s
 __global__ void f32_to_bf16_kernel(size_t rows, int cols, const float* __restrict__ src, int lds,
                                    __nv_bfloat16* __restrict__ dst, int ldd) {
     const size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    pdl_launch_dependents();
+    pdl_wait();
     if (e >= rows * (size_t)ldd) return;
     const size_t r = e / ldd; const int c = (int)(e - r * ldd);
     dst[e] = __float2bfloat16(c < cols ? src[r * lds + c] : 0.f);
@@ -559,7 +567,8 @@ extern "C" int seevcn_vcn_forward(const seevcn_vcn_model* M, int num_obj, int n,
     float* fc_part = reinterpret_cast<float*>(ws + w.fc_part);
     auto to_bf16 = [&](const float* X, int rows, int cols, __nv_bfloat16* xb) -> int {
         const size_t tot = (size_t)rows * cols;
-        f32_to_bf16_kernel<<<(unsigned)div_up(tot, (size_t)256), 256, 0, st>>>(rows, cols, X, cols, xb, cols);
+        SEEVCN_CUDA_CHECK(launch_pdl(f32_to_bf16_kernel, dim3((unsigned)div_up(tot, (size_t)256)), dim3(256), 0, st,
+                                     (size_t)rows, cols, X, cols, xb, cols));
         SEEVCN_LAUNCH_CHECK();
         return SEEVCN_OK;
     };
@@ -583,17 +592,17 @@ extern "C" int seevcn_vcn_forward(const seevcn_vcn_model* M, int num_obj, int n,
         int ks = 0;
         if (M->viewer_centred) {
             init.dst[2] = pose_feat; init.width[2] = 1024;
-            vcn_frame_kernel<<<num_obj, 256, 0, st>>>(n, 1, input, nullptr, frames, nullptr, init);
+            SEEVCN_CUDA_CHECK(launch_pdl(vcn_frame_kernel, dim3(num_obj), dim3(256), 0, st, n, 1, input, nullptr, frames, nullptr, init));
             SEEVCN_LAUNCH_CHECK();
             TRY(vcn_chain_pose(M, num_obj, n, input, frames, pose_feat, st));
             TRY(to_bf16(pose_feat, num_obj, 1024, fcxA));
             SEEVCN_REQUIRE(M->pose_fc0.cout == kPoseHidden && M->pose_fc2.cout == 9, "vcn_forward: unexpected pose_fc shape");
             TRY(vcn_fc_tc_partials(M->pose_fc0, num_obj, fcxA, 1024, fc_part, &ks, st));
-            vcn_pose_tail_kernel<<<num_obj, 288, 0, st>>>(num_obj, ks, fc_part, M->pose_fc0.b, M->pose_fc2.w, M->pose_fc2.b,
-                                                          frames, poses, reg_rot, reg_centre);
+            SEEVCN_CUDA_CHECK(launch_pdl(vcn_pose_tail_kernel, dim3(num_obj), dim3(288), 0, st, num_obj, ks, fc_part, M->pose_fc0.b,
+                                         M->pose_fc2.w, M->pose_fc2.b, frames, poses, reg_rot, reg_centre));
             SEEVCN_LAUNCH_CHECK();
         } else {
-            vcn_frame_kernel<<<num_obj, 256, 0, st>>>(n, 0, input, gt_boxes, frames, nullptr, init);
+            SEEVCN_CUDA_CHECK(launch_pdl(vcn_frame_kernel, dim3(num_obj), dim3(256), 0, st, n, 0, input, gt_boxes, frames, nullptr, init));
             SEEVCN_LAUNCH_CHECK();
         }
         for (int o0 = 0; o0 < num_obj; o0 += w.chunk) {
@@ -609,8 +618,8 @@ extern "C" int seevcn_vcn_forward(const seevcn_vcn_model* M, int num_obj, int n,
         TRY(vcn_fc_tc(M->fc2, num_obj, fcxB, 1024, ACT_RELU, nullptr, fcxA, 1024, fc_part, st));
         if ((3 * M->num_coarse) % 128 == 0) {
             TRY(vcn_fc_tc_partials(M->fc4, num_obj, fcxA, 1024, fc_part, &ks, st));
-            vcn_output_kernel<<<dim3(div_up(M->num_coarse, 256), num_obj), 256, 0, st>>>(M->num_coarse, M->viewer_centred,
-                                                                                         fc_part, frames, poses, coarse, ks, M->fc4.b);
+            SEEVCN_CUDA_CHECK(launch_pdl(vcn_output_kernel, dim3(div_up(M->num_coarse, 256), num_obj), dim3(256), 0, st,
+                                         M->num_coarse, M->viewer_centred, fc_part, frames, poses, coarse, ks, M->fc4.b));
             SEEVCN_LAUNCH_CHECK();
             return SEEVCN_OK;
         }

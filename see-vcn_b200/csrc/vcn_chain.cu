@@ -205,6 +205,7 @@ vcn_chain_kernel(const __grid_constant__ CUtensorMap tmap_w1, const __grid_const
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(h_free + 2);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    pdl_launch_dependents();
     // contiguous run of tiles per CTA: consecutive tiles of an object share the shared-memory max
     const int t_begin = (int)((long long)a.num_tiles * blockIdx.x / gridDim.x);
     const int t_end = (int)((long long)a.num_tiles * (blockIdx.x + 1) / gridDim.x);
@@ -237,6 +238,7 @@ vcn_chain_kernel(const __grid_constant__ CUtensorMap tmap_w1, const __grid_const
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    pdl_wait();      // the set-up above (and the staging of the constant weights) overlapped the preceding kernel's tail
 
     if (warp == 0) {
         // ================================================================== TMA producer ==
@@ -666,7 +668,7 @@ int launch_chain(const CUtensorMap& tw1, const CUtensorMap& tw2, const CUtensorM
     b.prof = nullptr;
     {
         SEEVCN_PROF(MODE == CHAIN_POSE ? "vcn_chain_pose" : MODE == CHAIN_ENC1 ? "vcn_chain_enc1" : "vcn_chain_enc2", st);
-        vcn_chain_kernel<MODE><<<grid, NUM_THREADS, smem, st>>>(tw1, tw2, tx, b);
+        SEEVCN_CUDA_CHECK(launch_pdl(vcn_chain_kernel<MODE>, dim3(grid), dim3(NUM_THREADS), (size_t)smem, st, tw1, tw2, tx, b));
     }
     SEEVCN_LAUNCH_CHECK();
     return SEEVCN_OK;

@@ -35,6 +35,27 @@ struct seevcn_vcn_model {
     size_t blob_bytes = 0;
 };
 
+// Programmatic dependent launch (the VCN forward is ~20 short dependent kernels on one stream).  Every kernel of the
+// forward starts with pdl_launch_dependents() — the next kernel's CTAs may be scheduled and run their prologue (barrier
+// init, TMEM allocation, tensor-map prefetch, staging of constant weights) while this one is still running — and calls
+// pdl_wait() before it touches anything a predecessor wrote (or still reads): that returns when the preceding grid has
+// completed and its writes are visible.  Since every kernel waits at its top, completion of the predecessor implies
+// completion of everything before it.  Both are no-ops in a kernel that was launched the ordinary way.
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
+// kernel<<<grid, block, smem, st>>>(args...) with the programmatic-stream-serialization attribute
+template <typename... KArgs, typename... Args>
+static inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 // Activation codes used by every linear kernel
 enum { ACT_NONE = 0, ACT_RELU = 1, ACT_LEAKY = 2 };   // LeakyReLU slope 0.01 (torch default)
 

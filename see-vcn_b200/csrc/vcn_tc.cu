@@ -69,6 +69,7 @@ vcn_linear_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_co
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    pdl_launch_dependents();
 
     if (warp == 0 && lane == 0) {
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_w) : "memory");
@@ -87,6 +88,7 @@ vcn_linear_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_co
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    pdl_wait();      // everything above overlapped the tail of the preceding kernel
 
     if (warp == 0) {
         if (lane == 0) {
@@ -338,6 +340,8 @@ __global__ void __launch_bounds__(256)
 fc_reduce_kernel(int rows, int cout, int ksplit, const float* __restrict__ part, const float* __restrict__ bias, int act,
                  float* __restrict__ Yf32, __nv_bfloat16* __restrict__ Yb16, int ldb) {
     const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    pdl_launch_dependents();
+    pdl_wait();
     const int groups = cout / 4;
     if (e >= rows * groups) return;
     const int r = e / groups, c = (e - r * groups) * 4;
@@ -392,7 +396,7 @@ int vcn_fc_tc_partials(const LinearW& L, int rows, const __nv_bfloat16* X, int l
     a.num_tiles = mn * a.ksplit;
     a.part = part;
     const int grid = a.num_tiles < seevcn_num_sms() ? a.num_tiles : seevcn_num_sms();
-    vcn_linear_tc_kernel<<<grid, NUM_THREADS, SMEM_BYTES, st>>>(tw, tx, a);
+    SEEVCN_CUDA_CHECK(launch_pdl(vcn_linear_tc_kernel, dim3(grid), dim3(NUM_THREADS), SMEM_BYTES, st, tw, tx, a));
     SEEVCN_LAUNCH_CHECK();
     *ksplit = a.ksplit;
     return SEEVCN_OK;
@@ -405,7 +409,8 @@ int vcn_fc_tc(const LinearW& L, int rows, const __nv_bfloat16* X, int ldx, int a
     const int rc = vcn_fc_tc_partials(L, rows, X, ldx, part, &ksplit, st);
     if (rc != SEEVCN_OK) return rc;
     const int total = rows * (L.cout / 4);
-    fc_reduce_kernel<<<div_up(total, 256), 256, 0, st>>>(rows, L.cout, ksplit, part, L.b, act, Yf32, Yb16, ldb);
+    SEEVCN_CUDA_CHECK(launch_pdl(fc_reduce_kernel, dim3(div_up(total, 256)), dim3(256), 0, st, rows, L.cout, ksplit,
+                                 static_cast<const float*>(part), L.b, act, Yf32, Yb16, ldb));
     SEEVCN_LAUNCH_CHECK();
     return SEEVCN_OK;
 }
