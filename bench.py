@@ -480,6 +480,28 @@ def run_frames(args):
         _, pts = D.max_sum(0.0, n_pts * steps)
         return ms, objs, pts, launches, prof, n_pts, n_vox, my_ms
 
+    def isolated_stages(n_steps):
+        """The same batches on ONE stream with the event scopes on: every launch group timed while it has the GPU to itself.
+        (In the timed region batches of neighbouring steps share the SMs, which is what makes the step short but stretches
+        each kernel's own duration.)  Untimed; reported as `stages` next to the in-region table."""
+        old = pipe.streams
+        pipe.streams = 1
+        try:
+            for _ in stream(2, pts_d, boxes_d):
+                pass
+            D.sync_all()
+            _abi.prof_enable(True)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in stream(n_steps, pts_d, boxes_d):
+                pass
+            e1.record()
+            e1.synchronize()
+            _abi.prof_enable(False)
+            return _abi.prof_report(), e0.elapsed_time(e1)
+        finally:
+            pipe.streams = old
+
     def timed_e2e(steps, warmup):
         """Public host-buffer API: pinned host frames in, pinned host results out, every batch's H2D and D2H
         inside the timed region (copies of neighbouring batches overlap the kernels, see HostStream)."""
@@ -503,6 +525,10 @@ def run_frames(args):
         sampler.start()
     ms_res, n_obj_res, n_vox_pts, launches, prof, pts_step_rank0, vox_step_rank0, my_ms = timed_resident(args.steps, args.warmup)
     obj_rank0 = int(round(n_obj_res / args.steps / world))
+    iso_steps = max(1, min(args.steps, 40))
+    prof_iso, ms_iso = isolated_stages(iso_steps) if args.streams > 1 else (prof, my_ms * iso_steps / args.steps)
+    if args.streams <= 1:
+        iso_steps = args.steps
     ms_e2e, n_obj_e2e, h2d, d2h = timed_e2e(args.steps, max(args.warmup, 3))
     clocks = sampler.summary() if rank == 0 else None
     # per-rank diagnostics (scaling attribution): step time and the main stage groups of every rank
@@ -530,9 +556,12 @@ def run_frames(args):
             "mean_vfe": ("hbm", (60.0 + 4.0 + 12.0) * vox_step_rank0),
             "splice": ("hbm", 13.0 * fr * P_pts + 12.0 * RESAMPLE * obj_rank0),
         }
-        stages = stage_table(prof, steps, ms_res, alg, pk)
+        stages_region = stage_table(prof, steps, ms_res, alg, pk)
+        stages = stage_table(prof_iso, iso_steps, ms_iso, alg, pk)
         cnt2, ms2 = prof.get("vcn_chain_enc2", (0, 0.0))
         achieved = FLOP_ENC2_EXEC * obj_rank0 * steps / (ms2 / 1e3) / 1e12 if ms2 > 0 else None
+        cnt2i, ms2i = prof_iso.get("vcn_chain_enc2", (0, 0.0))
+        achieved_iso = FLOP_ENC2_EXEC * obj_rank0 * iso_steps / (ms2i / 1e3) / 1e12 if ms2i > 0 else None
         peak = pk["bf16_tflops"]
         cpu = None
         if world == 1 and not args.no_cpu:
@@ -560,11 +589,20 @@ def run_frames(args):
                          "frac": achieved / peak if achieved else None, "traffic": ncu_traffic("vcn_chain_kernel<2>"),
                          "peak_source": pk["source"] + " burst bf16 (cuBLAS); sustained is %.0f" % pk["bf16_tflops_sustained"],
                          "launches": cnt2, "us_per_launch": 1e3 * ms2 / cnt2 if cnt2 else None,
+                         "timed": f"CUDA events on the launching stream inside the timed region ({args.streams} compute streams: "
+                                  "kernels of neighbouring batches share the SMs)",
+                         "alone": {"achieved": achieved_iso, "frac": achieved_iso / peak if achieved_iso else None,
+                                   "us_per_launch": 1e3 * ms2i / cnt2i if cnt2i else None, "launches": cnt2i,
+                                   "timed": "same batches on one stream, untimed pass after the timed region"},
                          "flop_per_object": FLOP_ENC2_EXEC,
                          "note": "flops as executed (W_local x + per-object bias: 655,360 MAC/pt); the reference graph's "
                                  "cat([global, local]) -> conv form is 786,432 MAC/pt (SURVEY.md §8a6)",
                          "achieved_reference_graph": achieved * FLOP_ENC2_REF / FLOP_ENC2_EXEC if achieved else None},
             "stages": stages,
+            "stages_note": f"`stages`: every launch group timed with the GPU to itself ({iso_steps} steps on one stream, "
+                           f"{ms_iso / iso_steps:.3f} ms/step); `stages_in_timed_region`: the same scopes inside the timed "
+                           f"region, where {args.streams} streams overlap neighbouring batches",
+            "stages_in_timed_region": stages_region,
             "cpu_baseline": cpu, "clocks": clocks,
         }
         if per_rank is not None:
@@ -622,7 +660,17 @@ def run_c4(args):
                 op["sampled"].copy_(sampled, non_blocking=True)
         return st
 
-    def timed(steps, warmup, srcs, host_out):
+    def timed(steps, warmup, srcs, host_out, one_stream=False):
+        nonlocal streams
+        all_streams = streams
+        if one_stream:          # untimed pass for the per-stage table: every launch group with the GPU to itself
+            streams = streams[:1]
+        try:
+            return timed_(steps, warmup, srcs, host_out)
+        finally:
+            streams = all_streams
+
+    def timed_(steps, warmup, srcs, host_out):
         for i in range(warmup):
             step(i, srcs, host_out)
         D.sync_all()
@@ -652,6 +700,10 @@ def run_c4(args):
     if rank == 0:
         sampler.start()
     ms_res, n_obj, launches, prof = timed(args.steps, args.warmup, sets_d, False)
+    iso_steps = max(1, min(args.steps, 10))
+    ms_iso, _, _, prof_iso = timed(iso_steps, 2, sets_d, False, one_stream=True) if len(streams) > 1 else (ms_res, 0, 0, prof)
+    if len(streams) <= 1:
+        iso_steps = args.steps
     ms_e2e, n_obj_e2e, _, _ = timed(args.steps, max(args.warmup, 3), sets_pin, True)
     clocks = sampler.summary() if rank == 0 else None
     if rank == 0:
@@ -664,10 +716,12 @@ def run_c4(args):
             "knn_scan_kernel": ("alu", 8.0 * N * NC * O),          # upper bound: every (query, reference) pair once
             "gather_points": ("hbm", (4.0 + 24.0) * 1024 * O),
         }
-        stages = stage_table(prof, steps, ms_res, alg, pk)
+        stages_region = stage_table(prof, steps, ms_res, alg, pk)
+        stages = stage_table(prof_iso, iso_steps, ms_iso, alg, pk)
         cnt_f, ms_f = prof.get("fps", (0, 0.0))
         fps_bytes = (12.0 * NC + 4.0 * 1024) * O
         achieved = fps_bytes * steps / (ms_f / 1e3) / 1e9 if ms_f > 0 else None
+        cnt_fi, ms_fi = prof_iso.get("fps", (0, 0.0))
         cpu = None
         if world == 1 and not args.no_cpu:
             cpu = cpu_baseline("C4", host_threads())
@@ -691,9 +745,17 @@ def run_c4(args):
                          "traffic": ncu_traffic("fps_kernel"), "peak_source": pk["source"] + " HBM copy",
                          "launches": cnt_f, "us_per_launch": 1e3 * ms_f / cnt_f if cnt_f else None,
                          "rounds_per_s": 1023.0 * O * steps / (ms_f / 1e3) if ms_f > 0 else None,
+                         "alone": {"us_per_launch": 1e3 * ms_fi / cnt_fi if cnt_fi else None,
+                                   "rounds_per_s": 1023.0 * O * iso_steps / (ms_fi / 1e3) if ms_fi > 0 else None,
+                                   "timed": "same steps on one stream, untimed pass after the timed region"},
                          "note": "compulsory bytes 12 N + 4 M per object (SURVEY.md §8d); the kernel is a serial on-chip latency "
                                  "chain (M - 1 dependent argmax rounds), not a bandwidth problem"},
-            "stages": stages, "cpu_baseline": cpu, "clocks": clocks,
+            "stages": stages,
+            "stages_note": f"`stages`: every launch group timed with the GPU to itself ({iso_steps} steps on one stream, "
+                           f"{ms_iso / iso_steps:.3f} ms/step); `stages_in_timed_region`: the same scopes inside the timed "
+                           f"region, where {len(streams)} streams overlap neighbouring steps",
+            "stages_in_timed_region": stages_region,
+            "cpu_baseline": cpu, "clocks": clocks,
         }))
     D.close()
 

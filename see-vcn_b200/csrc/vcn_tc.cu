@@ -168,6 +168,21 @@ vcn_linear_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_co
                 if (p0 >= nvalid) break;                   // warp-uniform
                 uint32_t r[32];
                 tc_ld32(t_base + ch * 32, r);
+                if (a.part) {
+                    // split-K slice: raw accumulators, one coalesced 128-byte store per row and warp
+                    if (c_ok) {
+                        float* pp = a.part + ((size_t)ks * a.rows + row0 + p0) * a.cout + c;
+                        if (p0 + 32 <= nvalid) {
+#pragma unroll
+                            for (int j = 0; j < 32; ++j) pp[(size_t)j * a.cout] = __uint_as_float(r[j]);
+                        } else {
+#pragma unroll
+                            for (int j = 0; j < 32; ++j)
+                                if (p0 + j < nvalid) pp[(size_t)j * a.cout] = __uint_as_float(r[j]);
+                        }
+                    }
+                    continue;
+                }
                 if (one_obj && c_ok && p0 + 32 <= nvalid) {
                     // fast path: full chunk, one object, valid channel
                     if (a.Y) {
@@ -201,7 +216,6 @@ vcn_linear_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_co
                         if (p >= nvalid) continue;
                         const int row = row0 + p;
                         const int o = row / a.rows_per_obj;
-                        if (a.part) { a.part[((size_t)ks * a.rows + row) * a.cout + c] = __uint_as_float(r[j]); continue; }
                         float v = __uint_as_float(r[j]) + bt;
                         if (!one_obj && a.obj_bias) v += a.obj_bias[(size_t)o * a.cout + c];
                         v = fmaxf(v, slope * v);

@@ -57,6 +57,10 @@ class CompletionPipeline:
         # leaving them idle.  Every batch keeps its own stream from the crop to the voxels; nothing is shared but the weights.
         self.streams = max(1, int(streams))
         self._side_streams = None
+        # pinned landing slots for the few bytes that travel to the host per batch (box counts, M): a ring, because a
+        # pinned allocation per call costs the host ~0.2 ms per batch.  A slot is handed out again 64 calls later; at most
+        # 2 x (streams + 3) are ever in flight.
+        self._pin_slots, self._pin_slot_bytes, self._pin_next = None, 8192, 0
 
     def _to_host_async(self, t):
         """Small device tensor (4-byte elements) -> pinned host copy, written by a copy kernel on the current stream
@@ -65,7 +69,14 @@ class CompletionPipeline:
         tools/diag_latency.py) and needs a side stream that waits on a compute event.  Returns (pinned tensor, event)."""
         from . import _abi
         t = t.contiguous()
-        host = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
+        nbytes = t.numel() * t.element_size()
+        if nbytes <= self._pin_slot_bytes:
+            if self._pin_slots is None:
+                self._pin_slots = torch.empty((64, self._pin_slot_bytes), dtype=torch.uint8).pin_memory()
+            host = self._pin_slots[self._pin_next % 64, :nbytes].view(t.dtype).view(t.shape)
+            self._pin_next += 1
+        else:
+            host = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
         with _abi.device_guard(self.device):
             _abi.check(_abi.lib().seevcn_copy_to_pinned(_abi.ptr(t), _abi.c_void_p(host.data_ptr()),
                                                         t.numel() * t.element_size(), _abi.stream()))

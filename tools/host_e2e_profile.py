@@ -18,7 +18,7 @@ def main():
     from seevcn_b200.pipeline import CompletionPipeline, HostStream
     dev = torch.device("cuda", 0)
     pipe = CompletionPipeline("VCN_VC", oracle.make_state_dict("VCN_VC", 0), dev, sel_k=bench.SEL_K, cluster_eps=bench.CLUSTER_EPS,
-                              splice_thresh=bench.SPLICE_THRESH)
+                              splice_thresh=bench.SPLICE_THRESH, streams=int(os.environ.get("STREAMS", "4")))
     pts, boxes = bench.make_inputs(8, 1000)
     pp, bp = torch.from_numpy(pts).pin_memory(), torch.from_numpy(boxes).pin_memory()
     hs = HostStream(pipe, 8, pts.shape[1], boxes.shape[1])
@@ -35,7 +35,9 @@ def main():
     torch.cuda.synchronize()
     print("wall per step %.3f ms" % (1e3 * (time.perf_counter() - t0) / n))
     st = pstats.Stats(pr)
-    st.sort_stats("tottime").print_stats(8)
+    st.sort_stats("tottime").print_stats(30)
+    st.print_callers("torch.empty")
+    print("allocator:", {k: v for k, v in torch.cuda.memory_stats(dev).items() if k in ("num_alloc_retries", "num_device_alloc", "num_device_free", "allocation.all.allocated", "segment.all.allocated")})
     # per-stage GPU time inside the e2e loop (library event scopes) next to the resident loop: which stage slows down?
     from seevcn_b200 import _abi
     pts_d, boxes_d = pp.to(dev), bp.to(dev)
