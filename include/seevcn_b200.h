@@ -429,6 +429,18 @@ int seevcn_copy_to_pinned(const void* src_device, void* dst_pinned_host, size_t 
  * device memory with SM loads; the pinned buffer must stay untouched until an event recorded after it has completed. */
 int seevcn_copy_from_pinned(const void* src_pinned_host, void* dst_device, size_t bytes, seevcn_stream_t stream);
 
+/* ------------------------------------------------- end-of-path collection (row e) ---- */
+/* Replaces the pickled all_gather of per-rank results (pcdet/utils/commu_utils.py:50-111, used by sc_multiproc.py:81-85).
+ * Packs one batch into a contiguous record in `send`:
+ *   header_words int32 {num_objects, num_voxels, frame_offset, feat_width, 0...} | clustered (clustered_words fp32) |
+ *   coords (num_voxels x 4 int32) | feats (num_voxels x 3 fp32) | nums (num_voxels int32).  One kernel on `stream`. */
+int seevcn_gather_pack(int header_words, int num_objects, int num_voxels, int frame_offset, int feat_width,
+                       long long clustered_words, const float* clustered, const int* coords, const float* feats,
+                       const int* nums, void* send, seevcn_stream_t stream);
+/* Delivers `bytes` of `send` to every dst[r] (this rank's slot in the receive buffer of rank r, mapped into this process
+ * by the caller: CUDA VMM / symmetric memory) with one device-to-device copy each on `stream`. */
+int seevcn_gather_broadcast(const void* send, size_t bytes, void* const* dst, int num_dst, seevcn_stream_t stream);
+
 /* ------------------------------------------------------------------ parity metric ---- */
 
 /* ref: chamfer_dist_kernel  see/surface_completion/models/vcn/extensions/chamfer_dist/chamfer.cu:15-145

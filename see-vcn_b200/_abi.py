@@ -89,6 +89,8 @@ SIGNATURES = {
     "seevcn_shuffle_perm": (ctypes.c_uint, [ctypes.c_uint] * 3),
     "seevcn_chamfer": (I, [I, I, I, P, P, P, P, P]),
     "seevcn_copy_to_pinned": (I, [P, P, c_size_t, P]),
+    "seevcn_gather_pack": (I, [I, I, I, I, I, ctypes.c_longlong, P, P, P, P, P, P]),
+    "seevcn_gather_broadcast": (I, [P, c_size_t, POINTER(c_void_p), I, P]),
     "seevcn_copy_from_pinned": (I, [P, P, c_size_t, P]),
 }
 

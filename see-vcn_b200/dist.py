@@ -103,7 +103,8 @@ class FrameGather:
     backend "peer": the receive buffers live in symmetric memory (torch.distributed._symmetric_memory: CUDA VMM
       allocations mapped into every rank of the node); a record is delivered with ONE device-to-device copy per peer
       over NVLink, issued on a side stream — the copy engines move it, no SM is taken from the persistent tcgen05
-      kernels of the next batch — followed by a signal-pad barrier.  Only the bytes a batch really has travel.
+      kernels of the next batch; a signal-pad barrier in ``wait()`` establishes that everything has landed.  Only the
+      bytes a batch really has travel.
     backend "nccl": all_gather_into_tensor of fixed-capacity slots (the fallback when symmetric memory is unavailable;
       also what the CPU / gloo tests run).
     Two generations of receive buffers alternate: the records of push k stay valid from ``wait()`` until the rank's
@@ -150,6 +151,10 @@ class FrameGather:
                 self._recv_flat = symm.empty((2 * words,), dtype=torch.float32, device=self.dev)
                 self._hdl = symm.rendezvous(self._recv_flat, group=g)
                 self._peer = [[self._hdl.get_buffer(r, (2, self.world, self._slot_words), torch.float32, 0) for r in range(self.world)]]
+                import ctypes
+                # this rank's slot in every peer's receive buffer, per generation, as raw pointers for seevcn_gather_broadcast
+                self._peer_dst = [(ctypes.c_void_p * self.world)(*[self._peer[0][r][gen, self.rank].data_ptr() for r in range(self.world)])
+                                  for gen in range(2)]
                 self.kind = "peer"
             except Exception as e:   # noqa: BLE001
                 if self.backend == "peer":
@@ -166,8 +171,12 @@ class FrameGather:
                 "mb_sent_per_push_per_peer": round(self.bytes_sent / max(self.pushes, 1) / 1e6, 2)}
 
     # -- producer side ----------------------------------------------------------------------------------------------
-    def push(self, out, frame_offset=0):
-        """Queue the collection of one finalized pipeline batch (dict of CompletionPipeline.run / run_stream)."""
+    def push(self, out, frame_offset=0, sync=False):
+        """Queue the collection of one finalized pipeline batch (dict of CompletionPipeline.run / run_stream).
+        backend "peer": the record is on its way to every rank when this returns; that every rank's records have LANDED is
+        established by the barrier in ``wait()`` (collective: every rank calls it at the same point), or right here with
+        ``sync=True``.  The reference gathers once, after its last frame (sc_multiproc.py:81-85); a consumer that reads
+        every batch calls ``wait()`` / ``parts()`` per batch and gets the lock-step it needs."""
         clustered = out.get("clustered", out.get("surface"))
         coords, feats, nums = out["voxel_coords"], out["voxel_features"], out["voxel_num_points"]
         n_obj, m, c = int(clustered.shape[0]), int(coords.shape[0]), int(feats.shape[1])
@@ -179,29 +188,54 @@ class FrameGather:
         self._gen ^= 1
         used = self.HEADER + n_obj * self.S * 3 + m * 8
         done = out.get("_done")
-        cur = torch.cuda.current_stream(self.dev) if self._side is not None else None
         side = self._side
         if side is not None:
             if done is not None:
                 side.wait_event(done)
             else:
-                side.wait_stream(cur)
+                side.wait_stream(torch.cuda.current_stream(self.dev))
+        if self.dev.type == "cuda" and self.kind == "peer" and not sync:
+            # the common case, kept short (this sits on the host's critical path once per batch): raw stream handle, two C calls
+            from . import _abi
+            L, st = _abi.lib(), _abi.c_void_p(side.cuda_stream)
+            clustered, coords, feats, nums = clustered.contiguous(), coords.contiguous(), feats.contiguous(), nums.contiguous()
+            _abi.check(L.seevcn_gather_pack(self.HEADER, n_obj, m, int(frame_offset), c, n_obj * self.S * 3, _abi.ptr(clustered),
+                                            _abi.ptr(coords), _abi.ptr(feats), _abi.ptr(nums), _abi.ptr(self._send), st))
+            _abi.check(L.seevcn_gather_broadcast(_abi.ptr(self._send), used * 4, self._peer_dst[g], self.world, st))
+            self._unsynced = True
+            self._keep = (getattr(self, "_keep", None) or [])[-3:] + [(out, None, clustered, coords, feats, nums)]
+            self.pushes += 1
+            self.bytes_sent += used * 4
+            return g
         ctx = torch.cuda.stream(side) if side is not None else _nullctx()
         with ctx:
             send = self._send
-            hdr = self._hdr_ring[self.pushes % 8]
-            hdr[0], hdr[1], hdr[2], hdr[3] = n_obj, m, frame_offset, c
-            send[: self.HEADER].view(torch.int32).copy_(hdr, non_blocking=True)
-            o = self.HEADER
-            send[o: o + n_obj * self.S * 3].copy_(clustered.reshape(-1), non_blocking=True); o += n_obj * self.S * 3
-            send[o: o + m * 4].view(torch.int32).copy_(coords.reshape(-1), non_blocking=True); o += m * 4
-            send[o: o + m * 3].copy_(feats.reshape(-1), non_blocking=True); o += m * 3
-            send[o: o + m].view(torch.int32).copy_(nums.reshape(-1), non_blocking=True)
-            if self.kind == "peer":
-                for r in range(self.world):                      # one D2D copy per peer: copy engines over NVLink
-                    self._peer[0][r][g, self.rank, :used].copy_(send[:used], non_blocking=True)
-                self._hdl.barrier(channel=g)                     # every rank's copies of this generation have landed
+            hdr = None
+            if self.dev.type == "cuda":
+                # one pack kernel + (peer) one device-to-device copy per peer, issued from C: ~15 python-level copies per
+                # push cost the host 0.12 ms per batch, which is what an 8-rank node is short of
+                from . import _abi
+                clustered, coords, feats, nums = clustered.contiguous(), coords.contiguous(), feats.contiguous(), nums.contiguous()
+                _abi.check(_abi.lib().seevcn_gather_pack(self.HEADER, n_obj, m, int(frame_offset), c, n_obj * self.S * 3,
+                                                         _abi.ptr(clustered), _abi.ptr(coords), _abi.ptr(feats), _abi.ptr(nums),
+                                                         _abi.ptr(send), _abi.stream()))
+                if self.kind == "peer":
+                    _abi.check(_abi.lib().seevcn_gather_broadcast(_abi.ptr(send), used * 4, self._peer_dst[g], self.world,
+                                                                  _abi.stream()))
+                    if sync:
+                        self._hdl.barrier(channel=g)             # every rank's copies of this generation have landed
+                    else:
+                        self._unsynced = True
             else:
+                hdr = self._hdr_ring[self.pushes % 8]
+                hdr[0], hdr[1], hdr[2], hdr[3] = n_obj, m, frame_offset, c
+                send[: self.HEADER].view(torch.int32).copy_(hdr, non_blocking=True)
+                o = self.HEADER
+                send[o: o + n_obj * self.S * 3].copy_(clustered.reshape(-1), non_blocking=True); o += n_obj * self.S * 3
+                send[o: o + m * 4].view(torch.int32).copy_(coords.reshape(-1), non_blocking=True); o += m * 4
+                send[o: o + m * 3].copy_(feats.reshape(-1), non_blocking=True); o += m * 3
+                send[o: o + m].view(torch.int32).copy_(nums.reshape(-1), non_blocking=True)
+            if self.kind != "peer":
                 dst = self._recv[g]
                 if self.dev.type == "cuda":
                     w = dist.all_gather_into_tensor(dst.view(-1), send, group=self.group, async_op=True)
@@ -212,7 +246,8 @@ class FrameGather:
                 ev = torch.cuda.Event()
                 ev.record(side)
                 self._events[g] = ev
-        self._keep = (out, hdr)
+        # sources stay referenced for a few pushes: the pack runs on the side stream, behind the allocator's back
+        self._keep = (getattr(self, "_keep", None) or [])[-3:] + [(out, hdr, clustered, coords, feats, nums)]
         self.pushes += 1
         self.bytes_sent += used * 4 if self.kind == "peer" else self._slot_words * 4
         return g
@@ -222,6 +257,13 @@ class FrameGather:
         for w in self._works:
             w.wait()
         self._works = []
+        if self.kind == "peer" and getattr(self, "_unsynced", False):
+            with torch.cuda.stream(self._side):
+                self._hdl.barrier(channel=0)                     # behind every copy this rank queued; returns when all ranks' have landed
+                ev = torch.cuda.Event()
+                ev.record(self._side)
+            self._events[0] = ev
+            self._unsynced = False
         if self._side is not None:
             for ev in self._events:
                 if ev is not None:
