@@ -442,7 +442,7 @@ def run_frames(args):
         b = 0
         for out in pipe.run_stream(batches(n_steps, srcs_p, srcs_b)):
             if gather is not None:
-                gather.push(out, frame_offset=rank * frames_rank + (b % nb) * F, sync=args.gather_sync)
+                gather.push(out, frame_offset=rank * frames_rank + (b % nb) * F, sync=not args.gather_async)
             b += 1
             yield out
         if gather is not None:
@@ -776,7 +776,7 @@ def main():
     ap.add_argument("--streams", type=int, default=4, help="CUDA streams consecutive pipeline batches alternate on")
     ap.add_argument("--lag", type=int, default=None, help="e2e: batches issued ahead of the one being finalized (default: HostStream's rule)")
     ap.add_argument("--l2", default="rotate", choices=["rotate", "flush"], help="how a step is kept from finding its inputs in L2")
-    ap.add_argument("--gather-sync", action="store_true", help="N > 1: barrier after every push instead of one in wait()")
+    ap.add_argument("--gather-async", action="store_true", help="N > 1: no barrier after a push, one in wait() (attribution runs)")
     ap.add_argument("--gather", default="auto", choices=["auto", "peer", "nccl"], help="N > 1: how the results are collected")
     args = ap.parse_args()
     if args.steps is None:
