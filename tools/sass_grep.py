@@ -5,7 +5,7 @@ import collections, os, re, subprocess, sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 LIB = os.path.join(ROOT, "see-vcn_b200", "csrc", "libseevcn_b200.so")
-WANT = ["UTCHMMA", "UTCBAR", "UTMALDG", "UTMAPF", "LDTM", "STTM", "SYNCS", "REDUX", "MATCH", "ATOMS", "RED.", "ATOMG", "HMMA", "DMMA", "IMMA"]
+WANT = ["UTCHMMA", "UTCBAR", "UTMALDG", "UTMASTG", "UTMACMDFLUSH", "UTMAPF", "FENCE.VIEW.ASYNC", "ACQBULK", "LDTM", "STTM", "SYNCS", "REDUX", "MATCH", "ATOMS", "RED.", "ATOMG", "HMMA", "DMMA", "IMMA"]
 
 
 def main():
@@ -23,7 +23,7 @@ def main():
         if c.get("UTCHMMA") or c.get("UTMALDG") or c.get("LDTM") or c.get("REDUX") or c.get("MATCH"):
             rows.append((name, n_inst, dict(c)))
     print("SASS mnemonic counts of see-vcn_b200/csrc/libseevcn_b200.so (cuobjdump -sass, sm_100a), produced by tools/sass_grep.py")
-    print("UTCHMMA = tcgen05.mma (bf16), UTMALDG = TMA tensor load, LDTM/STTM = tcgen05.ld/st (tensor memory), UTCBAR = tcgen05.commit,")
+    print("UTCHMMA = tcgen05.mma (bf16), UTMALDG / UTMASTG = TMA tensor load / store, FENCE.VIEW.ASYNC = fence.proxy.async, LDTM/STTM = tcgen05.ld/st (tensor memory), UTCBAR = tcgen05.commit,")
     print("SYNCS = mbarrier ops, REDUX/MATCH = warp reduce / match, HMMA = legacy mma.sync (expected: 0).\n")
     print("whole library: " + ", ".join(f"{k} {v}" for k, v in sorted(tot.items())) + "\n")
     for name, n, c in rows:
