@@ -144,7 +144,7 @@ __device__ __forceinline__ uint32_t warp_transpose_max2(uint32_t (&r)[16], int l
 template <int MODE>
 // launch bound 768 > the 640 threads launched: caps the kernel at 80 registers per thread (51k of the SM's 64k), which
 // leaves room for small CTAs of ANOTHER stream (the kNN scan of the neighbouring batch: 128 threads, 32 KB of shared
-// memory) next to a pose / enc1 chain CTA, whose SM would otherwise idle between pipeline hand-offs.
+// memory) next to an enc1 chain CTA (135 KB of shared memory), whose SM would otherwise idle between pipeline hand-offs.
 __global__ void __launch_bounds__(768, 1)
 vcn_chain_kernel(const __grid_constant__ CUtensorMap tmap_w1, const __grid_constant__ CUtensorMap tmap_w2,
                  const __grid_constant__ CUtensorMap tmap_x, const ChainArgs a) {
