@@ -24,6 +24,24 @@ def test_header_symbols_are_exported_and_bound():
     assert set(_abi.SIGNATURES) == set(syms)
 
 
+def test_ctypes_signatures_match_header_arity():
+    """every ctypes signature has as many arguments as the prototype in the header (a mismatch corrupts the call silently)"""
+    text = open(os.path.join(ROOT, "include", "seevcn_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    text = re.sub(r"//[^\n]*", "", text)
+    protos = re.findall(r"\b(seevcn_[a-z0-9_]+)\s*\(([^;{]*?)\)\s*;", text, flags=re.S)
+    assert len(protos) >= 20
+    seen = set()
+    for name, args in protos:
+        if name in seen:
+            continue
+        seen.add(name)
+        args = args.strip()
+        n = 0 if args in ("", "void") else args.count(",") + 1
+        assert n == len(_abi.SIGNATURES[name][1]), f"{name}: header has {n} parameters, _abi.py binds {len(_abi.SIGNATURES[name][1])}"
+    assert seen == set(_abi.SIGNATURES)
+
+
 def test_version_and_error_string():
     L = _abi.lib()
     assert L.seevcn_abi_version() == 2
