@@ -74,7 +74,11 @@ def main():
             e["dram_bytes_per_launch"] += b; e["launches_captured"] += 1
         for e in traffic.values():
             e["dram_bytes_per_launch"] /= max(e["launches_captured"], 1)
-        json.dump(traffic, open(os.path.join(P, "ncu_traffic.json"), "w"), indent=1)
+        tpath = os.path.join(P, "ncu_traffic.json")
+        if os.path.exists(tpath):      # kernels of other captures (e.g. the C4 FPS kernel) keep their entries
+            for k, v in json.load(open(tpath)).items():
+                traffic.setdefault(k, v)
+        json.dump(traffic, open(tpath, "w"), indent=1)
         print("wrote ncu summary + ncu_traffic.json", list(traffic)[:6])
 
 
